@@ -1,0 +1,77 @@
+"""Synthetic inputs for tests and benchmarks.
+
+The reference ships no sample images and no frozen graphs, so both are synthesised:
+  * pages: uint8 grayscale, background N(225, 6^2) clipped, text-like dark runs in a column
+    layout and 1-3 px wide vertical / horizontal rules, ``numpy.default_rng(seed=page_index)``;
+  * graphs: ``graphdef.build_aru_graphdef`` with fixed seeds; ``SEPARATOR`` / ``HEADING`` name the
+    two configurations that play ``separator_detection_net.pb`` / ``heading_detection_net.pb``.
+The classifier gain/bias were calibrated offline with ``tests/golden/calibrate_logits.py`` so
+that about 5 % of the pixels of a synthetic page exceed the reference's 0.05 separator threshold
+(separator_net_post_processor.py:147-149) instead of the mask being trivially all-on.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .graphdef import build_aru_graphdef
+
+# name -> kwargs of build_aru_graphdef (logit_gain/logit_bias from calibrate_logits.py)
+NETS = {
+    "separator": dict(graph="ARU", scale_space_num=5, num_scales_att=3, n_class=2, seed=0,
+                      logit_gain=1.0, logit_bias=(0.1, 0.1)),
+    "heading": dict(graph="ARU", scale_space_num=5, num_scales_att=3, n_class=2, seed=1,
+                    logit_gain=1.0, logit_bias=(0.1, 0.1)),
+    "ru": dict(graph="RU", scale_space_num=5, n_class=2, seed=2, logit_gain=1.0, logit_bias=(0.1, 0.1)),
+    "aru_s6a5": dict(graph="ARU", scale_space_num=6, num_scales_att=5, n_class=2, seed=3,
+                     logit_gain=1.0, logit_bias=(0.1, 0.1)),
+}
+
+
+def synth_pb(name: str = "separator", **overrides) -> bytes:
+    kw = dict(NETS[name])
+    kw.update(overrides)
+    return build_aru_graphdef(**kw)
+
+
+def synth_page(h: int, w: int, seed: int = 0) -> np.ndarray:
+    """uint8 [h, w] newspaper-like page."""
+    rng = np.random.default_rng(seed)
+    img = np.clip(rng.normal(225.0, 6.0, size=(h, w)), 0, 255)
+    n_cols = int(rng.integers(2, 6))
+    margin = max(4, w // 40)
+    col_w = (w - margin * (n_cols + 1)) // n_cols
+    line_h = max(3, h // 170)
+    for c in range(n_cols):
+        x0 = margin + c * (col_w + margin)
+        y = margin + int(rng.integers(0, 3 * line_h))
+        while y + line_h < h - margin:
+            if rng.random() < 0.04:                        # paragraph gap
+                y += int(rng.integers(2, 6)) * line_h
+                continue
+            x = x0
+            x_end = x0 + col_w - (int(rng.integers(0, col_w // 2)) if rng.random() < 0.15 else 0)
+            th = int(rng.integers(max(2, line_h - 2), line_h + 1))
+            while x < x_end:
+                wl = int(rng.integers(2, max(3, col_w // 6)))
+                x1 = min(x + wl, x_end)
+                img[y:y + th, x:x1] = rng.normal(60.0, 25.0, size=(min(th, h - y), x1 - x)).clip(0, 255)
+                x = x1 + int(rng.integers(1, 4))
+            y += line_h + int(rng.integers(1, 3))
+        if c < n_cols - 1 and rng.random() < 0.8:           # vertical rule between columns
+            xr = x0 + col_w + margin // 2
+            t = int(rng.integers(1, 4))
+            y0, y1 = sorted(int(v) for v in rng.integers(margin, h - margin, size=2))
+            if y1 - y0 > h // 8:
+                img[y0:y1, xr:xr + t] = rng.normal(40.0, 10.0, size=(y1 - y0, min(t, w - xr))).clip(0, 255)
+    for _ in range(int(rng.integers(1, 5))):                # horizontal rules
+        yr = int(rng.integers(margin, h - margin))
+        x0, x1 = sorted(int(v) for v in rng.integers(margin, w - margin, size=2))
+        t = int(rng.integers(1, 4))
+        if x1 - x0 > w // 8:
+            img[yr:yr + t, x0:x1] = rng.normal(40.0, 10.0, size=(min(t, h - yr), x1 - x0)).clip(0, 255)
+    return img.astype(np.uint8)
+
+
+def page_to_net_input(page_u8: np.ndarray) -> np.ndarray:
+    """What the reference feeds the net: gray / 255.0 as float64 (net_post_processing_helper.py:31)."""
+    return page_u8 / 255.0

@@ -1,0 +1,151 @@
+/*
+ * aru_b200.h - C ABI of libaru_b200.so: the B200 (sm_100a) ARU-Net forward engine.
+ *
+ * Drop-in boundary for ONE call of the reference (paths relative to the reference repo):
+ *   article_separation/image_segmentation/net_post_processing/net_post_processing_helper.py
+ *     :36-53  load_graph(path_to_pb)            -> aru_create()  (+ the Python GraphDef loader)
+ *     :56-72  get_net_output(image, graph, dev) -> aru_forward() (replaces tf.Session.run)
+ * The reference has no FFI of its own (it is Python over TensorFlow 1.x), so these entry points are
+ * what a ctypes binding in that helper module would bind; INTEGRATION.md shows the stub.
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in the signatures (streams are void*).
+ * All functions return 0 on success and a non-zero ARU_E* code on failure; aru_last_error()
+ * returns the message of the last failure on that engine (or the global one for aru_create).
+ * One engine per (process, device); an engine is not re-entrant.
+ */
+#ifndef ARU_B200_H
+#define ARU_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARU_ABI_VERSION 1
+#define ARU_PROGRAM_MAGIC 0x31555241u /* "ARU1" */
+#define ARU_MAX_SCALES 8
+
+/* error codes */
+#define ARU_OK 0
+#define ARU_EINVAL 1   /* bad argument / malformed program */
+#define ARU_ECUDA 2    /* CUDA runtime or driver error     */
+#define ARU_ENOMEM 3   /* device or pinned-host allocation failed */
+#define ARU_EUNSUP 4   /* program uses a shape / op the kernels do not cover */
+#define ARU_ENODEV 5   /* no CUDA device: there is no CPU fallback by design */
+
+/* op kinds of the lowered program (produced by the Python GraphDef loader, program.py) */
+enum aru_op_kind {
+  ARU_OP_CONV = 1,    /* Conv2D SAME s1 + BiasAdd [+ residual Add] [+ Relu]; layers.py:191-247, ARU_v1.py:212-227 */
+  ARU_OP_DECONV = 2,  /* Conv2DBackpropInput 3x3 s2 SAME + BiasAdd + act; layers.py:342-367                       */
+  ARU_OP_MAXPOOL = 3, /* MaxPool 2x2 s2 SAME; layers.py:543-544                                                   */
+  ARU_OP_AVGPOOL = 4, /* AvgPool 2x2 s2 SAME (divisor = valid cells); layers.py:526-527                           */
+  ARU_OP_COMBINE = 5, /* upsample_simple x A, softmax over scales, Mul, AddN; ARU_v1.py:115,137,145-153           */
+  ARU_OP_UPSUM = 6,   /* stand-alone upsample_simple (ones-filter transposed conv); layers.py:716-720             */
+  ARU_OP_COPY = 7     /* channel-slice copy (a ConcatV2 input that could not be produced in place)                */
+};
+
+/* activations */
+enum aru_act { ARU_ACT_NONE = 0, ARU_ACT_RELU = 1, ARU_ACT_SOFTMAX = 2, ARU_ACT_SIGMOID = 3 };
+
+/* a channel slice [ch_off, ch_off+ch) of a buffer; buf < 0 means "absent" */
+typedef struct aru_view {
+  int32_t buf;
+  int32_t ch_off;
+  int32_t ch;
+} aru_view;
+
+typedef struct aru_op {
+  int32_t kind;     /* enum aru_op_kind */
+  int32_t ksize;    /* conv / deconv kernel size (3 or 4) */
+  int32_t stride;   /* deconv stride (2) / UPSUM factor */
+  int32_t act;      /* enum aru_act */
+  int32_t n_scales; /* COMBINE: number of attention scales A */
+  int32_t like_buf; /* DECONV/UPSUM/COMBINE: buffer whose spatial dims the output takes */
+  int64_t w_off;    /* offset (floats) of the filter in the weight blob, TF layout; -1 = none */
+  int64_t b_off;    /* offset (floats) of the bias; -1 = none */
+  aru_view in;      /* main input */
+  aru_view out;     /* main output (post-activation) */
+  aru_view out_pre; /* CONV: optional copy of the pre-activation value (bias added, before Relu) */
+  aru_view res;     /* CONV: optional residual operand added before the activation */
+  aru_view att[ARU_MAX_SCALES]; /* COMBINE: low-resolution 1-channel attention maps */
+  aru_view det[ARU_MAX_SCALES]; /* COMBINE: detection feature maps */
+  int32_t up_att[ARU_MAX_SCALES]; /* COMBINE: upsample factor of att[i] */
+  int32_t up_det[ARU_MAX_SCALES]; /* COMBINE: upsample factor of det[i] (1 = already full size) */
+} aru_op;
+
+typedef struct aru_buffer {
+  int32_t channels;
+  int32_t role; /* 0 = intermediate, 1 = graph input (inImg:0), 2 = graph output (output:0) */
+} aru_buffer;
+
+/* the lowered graph handed to aru_create(); all pointers are host memory, copied by the engine */
+typedef struct aru_graph_desc {
+  uint32_t magic;       /* ARU_PROGRAM_MAGIC */
+  uint32_t abi_version; /* ARU_ABI_VERSION */
+  int32_t n_buffers;
+  int32_t n_ops;
+  int64_t n_weights; /* floats in `weights` */
+  const aru_buffer* buffers;
+  const aru_op* ops;
+  const float* weights;
+} aru_graph_desc;
+
+typedef struct aru_engine aru_engine;
+
+/* engine options (aru_set_option) */
+#define ARU_OPT_CONV_PATH 1   /* 0 = auto (tcgen05 where it applies), 1 = force the CUDA-core kernels (validation) */
+#define ARU_OPT_USE_GRAPH 2   /* 1 = replay a captured CUDA graph per plan (default), 0 = plain launches */
+#define ARU_OPT_MICRO_BATCH 3 /* pages per pass through the net inside aru_forward (0 = auto) */
+
+int aru_abi_version(void);
+int aru_device_count(void);
+
+/* load_graph: build an engine for `g` on CUDA device `device`. Fails with ARU_ENODEV without a GPU. */
+int aru_create(const aru_graph_desc* g, int device, aru_engine** out);
+void aru_destroy(aru_engine* e);
+
+int aru_set_option(aru_engine* e, int option, int64_t value);
+int aru_num_classes(const aru_engine* e);
+
+/* Allocate the arena and build launch plans / CUDA graph for n pages of h x w. Implicit in aru_forward. */
+int aru_plan(aru_engine* e, int n, int h, int w);
+
+/*
+ * get_net_output: run the net on n pages of h x w.
+ *   in        float32 [n,h,w]   (gray/255), host memory (pageable or pinned)
+ *   out       float32 [n,h,w,c] class probabilities, host memory; may be NULL
+ *   out_u8    uint8   [n,h,w,c] = trunc(p*255) (separator_net_post_processor.py:147); may be NULL
+ *   out_mask  uint8   [n,h,w]   = 255 where out_u8[...,0] > thr*255 else 0 (helper.py:75-78); may be NULL
+ * Copies are issued on the engine's stream and the call returns after they completed.
+ */
+int aru_forward(aru_engine* e, const float* in, int n, int h, int w, float* out, uint8_t* out_u8,
+                uint8_t* out_mask, float thr);
+
+/* Same, but `in` / `out*` are DEVICE pointers on the engine's device and the work is only enqueued on
+ * `stream` (a cudaStream_t, NULL = the engine's own stream); n must not exceed the planned batch. */
+int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, float* out, uint8_t* out_u8,
+                       uint8_t* out_mask, float thr, void* stream);
+
+/* Block until everything enqueued on the engine's stream has finished. */
+int aru_sync(aru_engine* e);
+
+/* Introspection used by tests / bench: number of kernels one forward of the current plan launches,
+ * and a copy-out of an intermediate buffer as float32 NHWC (debugging / per-layer parity). */
+int aru_launches_per_forward(const aru_engine* e);
+int aru_read_buffer(aru_engine* e, int buf, int n_index, float* out_nhwc, size_t out_floats);
+int aru_buffer_dims(const aru_engine* e, int buf, int* h, int* w, int* c);
+
+/* Per-op timing of the current plan (CUDA events on the engine stream, plain launches):
+ * ms[i] receives the mean duration of op i over `iters` runs; n_ms must be >= n_ops. */
+int aru_profile_ops(aru_engine* e, int iters, float* ms, int n_ms);
+/* Kernel label ("conv_tc", "conv_direct", ...) the plan chose for op i. */
+const char* aru_op_kernel_name(const aru_engine* e, int op);
+
+const char* aru_last_error(const aru_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARU_B200_H */
