@@ -1,14 +1,25 @@
 // aru_common.cuh - shared types of the B200 ARU-Net engine (device + host).
 //
-// Activation storage ("chunk-planar"): a tensor with C channels, N pages of H x W is stored as
-//   [ceil(C/8)] [N] [H] [W] [8]  16-bit floats
-// i.e. 8 channels of one pixel are one 16-byte vector and consecutive pixels of a row are contiguous.
-// Why (B200): (1) a 3x3 tap of the implicit GEMM is then a *contiguous* K-major core matrix of
-// 8 pixels x 8 channels = 128 B that TMA lands in shared memory without any transposition and that
-// a tcgen05 no-swizzle descriptor addresses at any 16-byte shift; (2) the epilogue's one-thread-per-
-// pixel TMEM read-out stores 16 B per lane = 512 B contiguous per warp; (3) a ConcatV2 along
-// channels is just "more chunk planes" of one buffer. 1-channel tensors (input page, attention
-// logits) and the network output stay float32.
+// Activation storage ("flattened padded chunk-planar"): a tensor with C channels for N pages of
+// H x W lives in ceil(C/8) planes; every plane is a 1-D array of *positions*, one position = the 8
+// channels of one pixel = one 16-byte vector of 16-bit floats.  Pages are stacked with a one-pixel
+// zero frame that neighbouring rows / pages share:
+//     Wp = W + 2,  Hp = H + 2
+//     pos(n, y, x) = lead + (n*Hp + y + 1)*Wp + (x + 1)
+// Position 'pos + dy*Wp + dx' is the neighbour (y+dy, x+dx); out-of-image neighbours land on frame
+// positions, which are zero (the arena is cleared once per plan and kernels only ever store to
+// in-image positions).  Consequences, all of them deliberate (B200):
+//  (1) a KxK SAME convolution is a 1-D correlation over positions with K*K constant offsets - the
+//      implicit-GEMM A operand of tap (ky,kx) for 128 consecutive output positions is a *contiguous*
+//      128 x 16 B run, i.e. 16 canonical no-swizzle K-major core matrices that a tcgen05 shared-memory
+//      descriptor addresses at any 16-byte shift.  TF's asymmetric padding of even kernels
+//      (1 before / 2 after for 4x4) is just the offset table;
+//  (2) the tile stream of a CTA is a contiguous range of positions, so operand staging is a ring of
+//      2 KB bulk-copy (TMA engine) chunks with no 2-D bookkeeping, read amplification ~1.0;
+//  (3) the epilogue's one-lane-per-position TMEM read-out stores 16 B per lane = 512 B contiguous per
+//      warp and plane; a ConcatV2 along channels is "more planes" of one buffer.
+// 1-channel tensors (input page pyramid, attention logits) are dense float32 [N][H][W]; the network
+// output is dense float32 NHWC.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -19,15 +30,38 @@
 typedef __nv_bfloat16 act_t;
 typedef __nv_bfloat162 act2_t;
 #define ARU_ACT_NAME "bf16"
+#define ARU_UMMA_FMT 1u
 #else
 typedef __half act_t;       // fp16 storage / tensor-core operands, fp32 accumulate (DESIGN.md "numerics")
 typedef __half2 act2_t;
 #define ARU_ACT_NAME "fp16"
+#define ARU_UMMA_FMT 0u
 #endif
 
 namespace aru {
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Geometry of a chunk-planar tensor (identical for all tensors with the same N,H,W).
+struct Geo {
+  int N, H, W;
+  int Wp, Hp;
+  long long lead;   // positions before the frame of page 0
+  long long plane;  // positions per plane (multiple of 128)
+  __host__ __device__ long long pos(int n, int y, int x) const {
+    return lead + ((long long)n * Hp + y + 1) * Wp + (x + 1);
+  }
+};
+
+inline Geo make_geo(int N, int H, int W) {
+  Geo g;
+  g.N = N; g.H = H; g.W = W;
+  g.Wp = W + 2; g.Hp = H + 2;
+  g.lead = ((long long)(g.Wp + 1 + 128 + 127) / 128) * 128;
+  long long body = (long long)N * g.Hp * g.Wp;
+  g.plane = ((g.lead + body + 2LL * g.Wp + 640 + 127) / 128) * 128;
+  return g;
+}
 
 __device__ __forceinline__ float act_to_f(act_t v) {
 #ifdef ARU_USE_BF16
@@ -40,8 +74,7 @@ __device__ __forceinline__ act_t f_to_act(float v) {
 #ifdef ARU_USE_BF16
   return __float2bfloat16_rn(v);
 #else
-  // saturate instead of producing inf: an overflowing activation must not poison the 0*x products of
-  // zero-padded channels downstream
+  // saturate instead of producing inf: an overflowing activation must not poison later 0*x products
   return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
 #endif
 }
@@ -73,14 +106,5 @@ __device__ __forceinline__ uint4 pack8(const float f[8]) {
   v.w = pack2(f[6], f[7]);
   return v;
 }
-
-// A channel-slice view of a chunk-planar tensor (or a float32 plane when chunks == 0).
-struct TView {
-  void* base;        // first chunk of the view (act_t*) or float plane
-  long long plane;   // elements between consecutive chunks: N*H*W*8
-  int N, H, W;
-  int C;             // logical channels of the view
-  int chunks;        // ceil(C/8); 0 for float32 1-channel planes / NHWC float output
-};
 
 }  // namespace aru

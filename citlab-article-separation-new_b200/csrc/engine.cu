@@ -1,0 +1,909 @@
+// engine.cu - C ABI of libaru_b200.so (include/aru_b200.h): engine creation from the lowered op
+// program, per-shape planning (arena, launch list, CUDA graphs) and the pipelined forward pass that
+// replaces the reference's  sess.run('output:0', {'inImg:0': x})  (net_post_processing_helper.py:56-72).
+//
+// Threading model: one engine per (process, device), calls are not re-entrant (the reference calls the
+// net from a plain per-page loop, separator_net_post_processor.py:141).  There is no CPU fallback: without
+// a CUDA device aru_create fails with ARU_ENODEV.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/aru_b200.h"
+#include "aru_common.cuh"
+#include "kernels.h"
+
+using namespace aru;
+
+namespace {
+
+thread_local std::string g_error;  // message of a failed aru_create
+
+enum BufKind { KIND_PLANAR = 0, KIND_F32 = 1, KIND_OUT = 2 };
+
+struct OpWeights {
+  act_t* w16 = nullptr;     // direct conv / deconv pack [tap][cin_chunk][cout_chunk][8][8]
+  act_t* w_tc = nullptr;    // tcgen05 B image
+  float* w32 = nullptr;     // stem [tap][cpad] / small [tap][cin_pad][cout]
+  float* bias = nullptr;    // zero-padded to a multiple of 16
+  int cin = 0, cout = 0;
+  bool tc_shape_ok = false;
+};
+
+struct BufPlan {
+  int kind = KIND_PLANAR;
+  int channels = 0, chunks = 0;
+  int h = 0, w = 0;
+  bool sized = false;
+  Geo geo{};
+  size_t offset = 0;  // bytes into the arena
+  size_t bytes = 0;
+};
+
+struct Plan {
+  int n = 0, h = 0, w = 0;
+  std::vector<BufPlan> bufs;
+  std::vector<ConvTcPlan> tc;        // per op (ok == false when the op does not use the tensor-core kernel)
+  std::vector<const char*> kernel;   // per op label
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  float* in_dev[2] = {nullptr, nullptr};
+  float* out_dev[2] = {nullptr, nullptr};
+  uint8_t* u8_dev[2] = {nullptr, nullptr};
+  uint8_t* mask_dev[2] = {nullptr, nullptr};
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  bool d2h_pending[2] = {false, false};
+  int launches = 0;
+  uint64_t last_use = 0;
+};
+
+}  // namespace
+
+struct aru_engine {
+  int device = 0;
+  int num_sms = 0;
+  size_t max_smem = 0;
+  std::vector<aru_buffer> buffers;
+  std::vector<aru_op> ops;
+  std::vector<float> weights;
+  std::vector<OpWeights> opw;
+  std::vector<int> kind;  // per buffer
+  int input_buf = -1, output_buf = -1, n_class = 0;
+  int conv_path = 0, use_graph = 1, micro_batch = 0;
+  cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  int* err_flag = nullptr;
+  std::vector<std::unique_ptr<Plan>> plans;
+  Plan* cur = nullptr;
+  uint64_t tick = 0;
+  std::string error;
+};
+
+namespace {
+
+int fail(aru_engine* e, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->error = buf; else g_error = buf;
+  return code;
+}
+
+#define CU(e, call)                                                                                      \
+  do {                                                                                                   \
+    cudaError_t err__ = (call);                                                                          \
+    if (err__ != cudaSuccess)                                                                            \
+      return fail(e, err__ == cudaErrorMemoryAllocation ? ARU_ENOMEM : ARU_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                  cudaGetErrorString(err__), __FILE__, __LINE__);                                        \
+  } while (0)
+
+template <typename T>
+int upload(aru_engine* e, const std::vector<T>& host, T** dev) {
+  CU(e, cudaMalloc((void**)dev, std::max<size_t>(host.size() * sizeof(T), 16)));
+  CU(e, cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return ARU_OK;
+}
+
+bool view_ok(const aru_engine* e, const aru_view& v) {
+  return v.buf >= 0 && v.buf < (int)e->buffers.size() && v.ch > 0 && v.ch_off >= 0 &&
+         v.ch_off + v.ch <= e->buffers[v.buf].channels;
+}
+
+// ---- weight packing ------------------------------------------------------------------------------
+int pack_op_weights(aru_engine* e, int oi) {
+  const aru_op& op = e->ops[oi];
+  OpWeights& ow = e->opw[oi];
+  if (op.kind != ARU_OP_CONV && op.kind != ARU_OP_DECONV) return ARU_OK;
+  const int ks = op.ksize, cin = op.in.ch, cout = op.out.ch;
+  ow.cin = cin;
+  ow.cout = cout;
+  const size_t nw = (size_t)ks * ks * cin * cout;
+  if (op.w_off < 0 || op.b_off < 0 || (size_t)op.w_off + nw > e->weights.size() ||
+      (size_t)op.b_off + cout > e->weights.size())
+    return fail(e, ARU_EINVAL, "op %d: weight / bias offsets out of range", oi);
+  const float* w = e->weights.data() + op.w_off;
+  const float* b = e->weights.data() + op.b_off;
+  const int cinc = cdiv(cin, 8), coutc = cdiv(cout, 8);
+  std::vector<float> bias(std::max(16, cdiv(coutc * 8, 16) * 16), 0.f);
+  for (int i = 0; i < cout; ++i) bias[i] = b[i];
+  int rc = upload(e, bias, &ow.bias);
+  if (rc) return rc;
+  const int ik = e->kind[op.in.buf], okind = e->kind[op.out.buf];
+  if (op.kind == ARU_OP_CONV && ik == KIND_F32) {
+    // stem: [tap][cpad] (filter is [kh][kw][1][cout])
+    const int cpad = coutc * 8;
+    std::vector<float> p((size_t)ks * ks * cpad, 0.f);
+    for (int t = 0; t < ks * ks; ++t)
+      for (int c = 0; c < cout; ++c) p[(size_t)t * cpad + c] = w[(size_t)t * cout + c];
+    return upload(e, p, &ow.w32);
+  }
+  if (op.kind == ARU_OP_CONV && okind != KIND_PLANAR) {
+    // small: [tap][cin_pad][cout]
+    const int cpad = cinc * 8;
+    std::vector<float> p((size_t)ks * ks * cpad * cout, 0.f);
+    for (int t = 0; t < ks * ks; ++t)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int c = 0; c < cout; ++c) p[((size_t)t * cpad + ci) * cout + c] = w[((size_t)t * cin + ci) * cout + c];
+    return upload(e, p, &ow.w32);
+  }
+  // chunk-planar -> chunk-planar: direct pack [tap][cin_chunk][cout_chunk][ci][co]
+  std::vector<uint16_t> p((size_t)ks * ks * cinc * coutc * 64, host_f_to_act(0.f));
+  for (int t = 0; t < ks * ks; ++t)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co) {
+        // Conv2D filter [kh][kw][cin][cout]; Conv2DBackpropInput filter [kh][kw][cout][cin] (layers.py:356)
+        const float v = op.kind == ARU_OP_CONV ? w[((size_t)t * cin + ci) * cout + co] : w[((size_t)t * cout + co) * cin + ci];
+        p[((((size_t)t * cinc + ci / 8) * coutc + co / 8) * 8 + ci % 8) * 8 + co % 8] = host_f_to_act(v);
+      }
+  rc = upload(e, p, reinterpret_cast<uint16_t**>(&ow.w16));
+  if (rc) return rc;
+  if (op.kind == ARU_OP_CONV) {
+    const Geo dummy = make_geo(1, 8, 8);
+    ConvTcPlan tp = conv_tc_plan(ks, cin, cout, dummy, e->num_sms, e->max_smem);
+    if (tp.ok) {
+      std::vector<uint16_t> img(tp.wpack_bytes / 2);
+      conv_tc_pack_weights(tp, w, cin, cout, img.data());
+      rc = upload(e, img, reinterpret_cast<uint16_t**>(&ow.w_tc));
+      if (rc) return rc;
+      ow.tc_shape_ok = true;
+    }
+  }
+  return ARU_OK;
+}
+
+// ---- planning ------------------------------------------------------------------------------------
+void free_plan(Plan* p) {
+  if (!p) return;
+  for (int i = 0; i < 2; ++i) {
+    if (p->graph[i]) cudaGraphExecDestroy(p->graph[i]);
+    if (p->in_dev[i]) cudaFree(p->in_dev[i]);
+    if (p->out_dev[i]) cudaFree(p->out_dev[i]);
+    if (p->u8_dev[i]) cudaFree(p->u8_dev[i]);
+    if (p->mask_dev[i]) cudaFree(p->mask_dev[i]);
+    if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
+    if (p->ev_comp[i]) cudaEventDestroy(p->ev_comp[i]);
+    if (p->ev_d2h[i]) cudaEventDestroy(p->ev_d2h[i]);
+  }
+  if (p->arena) cudaFree(p->arena);
+}
+
+int set_dims(aru_engine* e, Plan* p, int buf, int h, int w, int op) {
+  BufPlan& b = p->bufs[buf];
+  if (b.sized) {
+    if (b.h != h || b.w != w)
+      return fail(e, ARU_EINVAL, "op %d: buffer %d written with two shapes (%dx%d vs %dx%d)", op, buf, b.h, b.w, h, w);
+    return ARU_OK;
+  }
+  b.h = h; b.w = w; b.sized = true;
+  return ARU_OK;
+}
+
+PV make_pv(const aru_engine* e, const Plan* p, const aru_view& v) {
+  PV pv;
+  if (v.buf < 0) return pv;
+  const BufPlan& b = p->bufs[v.buf];
+  pv.plane = b.geo.plane;
+  pv.chunks = cdiv(v.ch, 8);
+  pv.C = v.ch;
+  pv.p = reinterpret_cast<act_t*>(p->arena + b.offset) + (long long)(v.ch_off / 8) * b.geo.plane * 8;
+  return pv;
+}
+
+float* f32_ptr(const aru_engine* e, const Plan* p, int buf, int parity) {
+  if (buf == e->input_buf) return p->in_dev[parity];
+  if (buf == e->output_buf) return p->out_dev[parity];
+  return reinterpret_cast<float*>(p->arena + p->bufs[buf].offset);
+}
+
+// Enqueue op `oi` of plan p on stream st.
+int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
+  const aru_op& op = e->ops[oi];
+  const OpWeights& ow = e->opw[oi];
+  cudaError_t err = cudaSuccess;
+  const char* label = "?";
+  switch (op.kind) {
+    case ARU_OP_CONV: {
+      const BufPlan& bi = p->bufs[op.in.buf];
+      const BufPlan& bo = p->bufs[op.out.buf];
+      if (bi.kind == KIND_F32) {
+        label = "conv_stem";
+        err = launch_conv_stem(st, op.ksize, f32_ptr(e, p, op.in.buf, parity), make_pv(e, p, op.out),
+                               make_pv(e, p, op.out_pre), ow.w32, ow.bias, bo.geo, op.act);
+      } else if (bo.kind != KIND_PLANAR) {
+        label = "conv_small";
+        err = launch_conv_small(st, op.ksize, op.out.ch, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), ow.w32,
+                                ow.bias, bi.geo, op.act);
+      } else if (p->tc[oi].ok) {
+        label = "conv_tc";
+        err = launch_conv_tc(st, p->tc[oi], make_pv(e, p, op.in), make_pv(e, p, op.out), make_pv(e, p, op.out_pre),
+                             make_pv(e, p, op.res), ow.w_tc, ow.bias, bo.geo, op.act, e->err_flag);
+      } else {
+        label = "conv_direct";
+        err = launch_conv_direct(st, op.ksize, make_pv(e, p, op.in), make_pv(e, p, op.out), make_pv(e, p, op.out_pre),
+                                 make_pv(e, p, op.res), ow.w16, ow.bias, bo.geo, op.act);
+      }
+      break;
+    }
+    case ARU_OP_DECONV:
+      label = "deconv_direct";
+      err = launch_deconv_direct(st, make_pv(e, p, op.in), p->bufs[op.in.buf].geo, make_pv(e, p, op.out),
+                                 p->bufs[op.out.buf].geo, ow.w16, ow.bias, op.act);
+      break;
+    case ARU_OP_MAXPOOL:
+    case ARU_OP_AVGPOOL: {
+      const BufPlan& bi = p->bufs[op.in.buf];
+      const BufPlan& bo = p->bufs[op.out.buf];
+      if (bi.kind == KIND_F32) {
+        label = "pool_f32";
+        err = launch_pool_f32(st, op.kind == ARU_OP_MAXPOOL, f32_ptr(e, p, op.in.buf, parity),
+                              f32_ptr(e, p, op.out.buf, parity), p->n, bi.h, bi.w, bo.h, bo.w);
+      } else {
+        label = "pool";
+        err = launch_pool(st, op.kind == ARU_OP_MAXPOOL, make_pv(e, p, op.in), bi.geo, make_pv(e, p, op.out), bo.geo);
+      }
+      break;
+    }
+    case ARU_OP_COMBINE: {
+      label = "combine";
+      CombineArgs a{};
+      const BufPlan& bo = p->bufs[op.out.buf];
+      a.A = op.n_scales;
+      a.geo = bo.geo;
+      PV out = make_pv(e, p, op.out);
+      a.out = out.p; a.out_plane = out.plane; a.out_chunks = out.chunks;
+      for (int k = 0; k < op.n_scales; ++k) {
+        const BufPlan& ba = p->bufs[op.att[k].buf];
+        a.att[k] = f32_ptr(e, p, op.att[k].buf, parity);
+        a.att_h[k] = ba.h; a.att_w[k] = ba.w; a.att_up[k] = op.up_att[k];
+        a.att_oy[k] = (ba.h * op.up_att[k] - bo.h) / 2;
+        a.att_ox[k] = (ba.w * op.up_att[k] - bo.w) / 2;
+        const BufPlan& bd = p->bufs[op.det[k].buf];
+        PV det = make_pv(e, p, op.det[k]);
+        a.det[k] = det.p; a.det_plane[k] = det.plane; a.det_chunks[k] = det.chunks; a.det_geo[k] = bd.geo;
+        a.det_up[k] = op.up_det[k];
+        a.det_oy[k] = (bd.h * op.up_det[k] - bo.h) / 2;
+        a.det_ox[k] = (bd.w * op.up_det[k] - bo.w) / 2;
+      }
+      err = launch_combine(st, a);
+      break;
+    }
+    case ARU_OP_UPSUM: {
+      const BufPlan& bi = p->bufs[op.in.buf];
+      const BufPlan& bo = p->bufs[op.out.buf];
+      const int oy = (bi.h * op.stride - bo.h) / 2, ox = (bi.w * op.stride - bo.w) / 2;
+      if (bi.kind == KIND_F32) {
+        label = "upsum_f32";
+        err = launch_upsum_f32(st, f32_ptr(e, p, op.in.buf, parity), bi.h, bi.w, f32_ptr(e, p, op.out.buf, parity), p->n,
+                               bo.h, bo.w, op.stride, oy, ox);
+      } else {
+        label = "upsum";
+        err = launch_upsum(st, make_pv(e, p, op.in), bi.geo, make_pv(e, p, op.out), bo.geo, op.stride, oy, ox);
+      }
+      break;
+    }
+    case ARU_OP_COPY: {
+      label = "copy";
+      PV in = make_pv(e, p, op.in), out = make_pv(e, p, op.out);
+      for (int c = 0; c < in.chunks && err == cudaSuccess; ++c)
+        err = launch_copy(st, in.p + c * in.plane * 8, out.p + c * out.plane * 8, in.plane * 16);
+      break;
+    }
+    default:
+      return fail(e, ARU_EUNSUP, "op %d: unknown kind %d", oi, op.kind);
+  }
+  p->kernel[oi] = label;
+  if (err != cudaSuccess) return fail(e, ARU_ECUDA, "op %d (%s): launch failed: %s", oi, label, cudaGetErrorString(err));
+  return ARU_OK;
+}
+
+int run_all(aru_engine* e, Plan* p, int parity, cudaStream_t st) {
+  for (int i = 0; i < (int)e->ops.size(); ++i) {
+    int rc = run_op(e, p, i, parity, st);
+    if (rc) return rc;
+  }
+  return ARU_OK;
+}
+
+int check_err_flag(aru_engine* e) {
+  int flag = 0;
+  CU(e, cudaMemcpy(&flag, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(e->err_flag, 0, sizeof(int));
+    return fail(e, ARU_ECUDA, "conv_tc pipeline timeout (barrier class %d): protocol error in the tcgen05 kernel", flag);
+  }
+  return ARU_OK;
+}
+
+int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
+  std::unique_ptr<Plan> p(new Plan);
+  p->n = n; p->h = h; p->w = w;
+  const int nb = (int)e->buffers.size(), no = (int)e->ops.size();
+  p->bufs.resize(nb);
+  p->tc.resize(no);
+  p->kernel.assign(no, "?");
+  for (int i = 0; i < nb; ++i) {
+    p->bufs[i].kind = e->kind[i];
+    p->bufs[i].channels = e->buffers[i].channels;
+    p->bufs[i].chunks = cdiv(e->buffers[i].channels, 8);
+  }
+  int rc = set_dims(e, p.get(), e->input_buf, h, w, -1);
+  if (rc) return rc;
+  // shape inference in program order (the lowering emits ops topologically)
+  for (int i = 0; i < no; ++i) {
+    const aru_op& op = e->ops[i];
+    auto need = [&](int buf) -> bool { return buf >= 0 && p->bufs[buf].sized; };
+    switch (op.kind) {
+      case ARU_OP_CONV:
+      case ARU_OP_COPY: {
+        if (!need(op.in.buf)) return fail(e, ARU_EINVAL, "op %d reads buffer %d before it is produced", i, op.in.buf);
+        const BufPlan& bi = p->bufs[op.in.buf];
+        if ((rc = set_dims(e, p.get(), op.out.buf, bi.h, bi.w, i))) return rc;
+        if (op.out_pre.buf >= 0 && (rc = set_dims(e, p.get(), op.out_pre.buf, bi.h, bi.w, i))) return rc;
+        if (op.res.buf >= 0) {
+          if (!need(op.res.buf) || p->bufs[op.res.buf].h != bi.h || p->bufs[op.res.buf].w != bi.w)
+            return fail(e, ARU_EINVAL, "op %d: residual operand shape mismatch", i);
+        }
+        break;
+      }
+      case ARU_OP_MAXPOOL:
+      case ARU_OP_AVGPOOL: {
+        if (!need(op.in.buf)) return fail(e, ARU_EINVAL, "op %d reads buffer %d before it is produced", i, op.in.buf);
+        const BufPlan& bi = p->bufs[op.in.buf];
+        if ((rc = set_dims(e, p.get(), op.out.buf, cdiv(bi.h, 2), cdiv(bi.w, 2), i))) return rc;
+        break;
+      }
+      case ARU_OP_DECONV:
+      case ARU_OP_UPSUM: {
+        if (!need(op.in.buf) || !need(op.like_buf)) return fail(e, ARU_EINVAL, "op %d: operands not produced yet", i);
+        const BufPlan& bi = p->bufs[op.in.buf];
+        const BufPlan& bl = p->bufs[op.like_buf];
+        if (bi.h != cdiv(bl.h, op.stride) || bi.w != cdiv(bl.w, op.stride))
+          return fail(e, ARU_EINVAL, "op %d: transposed conv input %dx%d is not ceil(%dx%d / %d)", i, bi.h, bi.w, bl.h,
+                      bl.w, op.stride);
+        if ((rc = set_dims(e, p.get(), op.out.buf, bl.h, bl.w, i))) return rc;
+        break;
+      }
+      case ARU_OP_COMBINE: {
+        if (!need(op.like_buf)) return fail(e, ARU_EINVAL, "op %d: like buffer not produced yet", i);
+        const BufPlan& bl = p->bufs[op.like_buf];
+        for (int k = 0; k < op.n_scales; ++k) {
+          if (!need(op.att[k].buf) || !need(op.det[k].buf))
+            return fail(e, ARU_EINVAL, "op %d: attention operands not produced yet", i);
+          const BufPlan& ba = p->bufs[op.att[k].buf];
+          const BufPlan& bd = p->bufs[op.det[k].buf];
+          if (ba.h != cdiv(bl.h, op.up_att[k]) || ba.w != cdiv(bl.w, op.up_att[k]) ||
+              bd.h != cdiv(bl.h, op.up_det[k]) || bd.w != cdiv(bl.w, op.up_det[k]))
+            return fail(e, ARU_EINVAL, "op %d: scale %d operand sizes do not match the upsample factors", i, k);
+        }
+        if ((rc = set_dims(e, p.get(), op.out.buf, bl.h, bl.w, i))) return rc;
+        break;
+      }
+      default:
+        return fail(e, ARU_EUNSUP, "op %d: unknown kind %d", i, op.kind);
+    }
+  }
+  // arena layout (no aliasing between buffers: the zero frame of every tensor must stay intact)
+  size_t off = 0;
+  for (int i = 0; i < nb; ++i) {
+    BufPlan& b = p->bufs[i];
+    if (!b.sized) { b.bytes = 0; continue; }
+    if (b.kind == KIND_PLANAR) {
+      b.geo = make_geo(n, b.h, b.w);
+      b.bytes = (size_t)b.chunks * b.geo.plane * 16;
+    } else {
+      b.geo = make_geo(n, b.h, b.w);
+      b.bytes = (size_t)n * b.h * b.w * b.channels * sizeof(float);
+    }
+    if (i == e->input_buf || i == e->output_buf) { b.offset = 0; continue; }  // separate, double-buffered
+    b.offset = off;
+    off += (b.bytes + 255) / 256 * 256;
+  }
+  p->arena_bytes = std::max<size_t>(off, 256);
+  CU(e, cudaMalloc((void**)&p->arena, p->arena_bytes));
+  CU(e, cudaMemsetAsync(p->arena, 0, p->arena_bytes, e->s_comp));
+  const size_t in_bytes = (size_t)n * h * w * sizeof(float);
+  const size_t out_bytes = (size_t)n * h * w * e->n_class * sizeof(float);
+  for (int i = 0; i < 2; ++i) {
+    CU(e, cudaMalloc((void**)&p->in_dev[i], in_bytes));
+    CU(e, cudaMalloc((void**)&p->out_dev[i], out_bytes));
+    CU(e, cudaMemsetAsync(p->in_dev[i], 0, in_bytes, e->s_comp));
+    CU(e, cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
+    CU(e, cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
+    CU(e, cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming));
+  }
+  // kernel selection for the chunk-planar convolutions
+  for (int i = 0; i < no; ++i) {
+    const aru_op& op = e->ops[i];
+    if (op.kind != ARU_OP_CONV) continue;
+    if (p->bufs[op.in.buf].kind != KIND_PLANAR || p->bufs[op.out.buf].kind != KIND_PLANAR) continue;
+    if (e->conv_path == 1 || !e->opw[i].tc_shape_ok) continue;
+    p->tc[i] = conv_tc_plan(op.ksize, op.in.ch, op.out.ch, p->bufs[op.out.buf].geo, e->num_sms, e->max_smem);
+  }
+  // one eager pass (sets function attributes, validates every launch), then capture
+  rc = run_all(e, p.get(), 0, e->s_comp);
+  if (rc) { free_plan(p.get()); return rc; }
+  {
+    cudaError_t err = cudaStreamSynchronize(e->s_comp);
+    if (err != cudaSuccess) {
+      free_plan(p.get());
+      return fail(e, ARU_ECUDA, "first pass of the plan failed: %s", cudaGetErrorString(err));
+    }
+  }
+  if ((rc = check_err_flag(e))) { free_plan(p.get()); return rc; }
+  p->launches = no;
+  for (int i = 0; i < no; ++i)
+    if (e->ops[i].kind == ARU_OP_COPY) p->launches += cdiv(e->ops[i].in.ch, 8) - 1;
+  if (e->use_graph) {
+    for (int par = 0; par < 2; ++par) {
+      cudaGraph_t g = nullptr;
+      CU(e, cudaStreamBeginCapture(e->s_comp, cudaStreamCaptureModeThreadLocal));
+      rc = run_all(e, p.get(), par, e->s_comp);
+      cudaError_t err = cudaStreamEndCapture(e->s_comp, &g);
+      if (rc || err != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        free_plan(p.get());
+        return rc ? rc : fail(e, ARU_ECUDA, "graph capture failed: %s", cudaGetErrorString(err));
+      }
+      err = cudaGraphInstantiate(&p->graph[par], g, 0);
+      cudaGraphDestroy(g);
+      if (err != cudaSuccess) {
+        free_plan(p.get());
+        return fail(e, ARU_ECUDA, "graph instantiation failed: %s", cudaGetErrorString(err));
+      }
+    }
+  }
+  *out = p.get();
+  e->plans.push_back(std::move(p));
+  return ARU_OK;
+}
+
+int get_plan(aru_engine* e, int n, int h, int w, Plan** out) {
+  for (auto& p : e->plans)
+    if (p->n == n && p->h == h && p->w == w) {
+      p->last_use = ++e->tick;
+      *out = p.get();
+      return ARU_OK;
+    }
+  if (e->plans.size() >= 4) {  // evict the least recently used plan
+    size_t lru = 0;
+    for (size_t i = 1; i < e->plans.size(); ++i)
+      if (e->plans[i]->last_use < e->plans[lru]->last_use) lru = i;
+    cudaDeviceSynchronize();
+    if (e->cur == e->plans[lru].get()) e->cur = nullptr;
+    free_plan(e->plans[lru].get());
+    e->plans.erase(e->plans.begin() + lru);
+  }
+  int rc = build_plan(e, n, h, w, out);
+  if (rc) return rc;
+  (*out)->last_use = ++e->tick;
+  return ARU_OK;
+}
+
+int enqueue_forward(aru_engine* e, Plan* p, int parity, cudaStream_t st) {
+  if (e->use_graph && p->graph[parity]) {
+    CU(e, cudaGraphLaunch(p->graph[parity], st));
+    return ARU_OK;
+  }
+  return run_all(e, p, parity, st);
+}
+
+int ensure_quant(aru_engine* e, Plan* p, bool u8, bool mask) {
+  for (int i = 0; i < 2; ++i) {
+    if (u8 && !p->u8_dev[i]) CU(e, cudaMalloc((void**)&p->u8_dev[i], (size_t)p->n * p->h * p->w * e->n_class));
+    if (mask && !p->mask_dev[i]) CU(e, cudaMalloc((void**)&p->mask_dev[i], (size_t)p->n * p->h * p->w));
+  }
+  return ARU_OK;
+}
+
+int pick_micro_batch(const aru_engine* e, int n, int h, int w) {
+  if (e->micro_batch > 0) return std::min(n, e->micro_batch);
+  const long long px = (long long)h * w;
+  long long mb = (40LL << 20) / std::max<long long>(px, 1);
+  mb = std::max<long long>(1, std::min<long long>(mb, 32));
+  return (int)std::min<long long>(mb, n);
+}
+
+}  // namespace
+
+// ---- C ABI -----------------------------------------------------------------------------------------
+extern "C" {
+
+int aru_abi_version(void) { return ARU_ABI_VERSION; }
+
+int aru_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* aru_last_error(const aru_engine* e) { return e ? e->error.c_str() : g_error.c_str(); }
+
+int aru_create(const aru_graph_desc* g, int device, aru_engine** out) {
+  if (!g || !out) return fail(nullptr, ARU_EINVAL, "aru_create: null argument");
+  *out = nullptr;
+  if (g->magic != ARU_PROGRAM_MAGIC || g->abi_version != ARU_ABI_VERSION)
+    return fail(nullptr, ARU_EINVAL, "aru_create: bad magic / ABI version (got %08x / %u)", g->magic, g->abi_version);
+  if (g->n_buffers <= 0 || g->n_ops <= 0 || !g->buffers || !g->ops || (g->n_weights > 0 && !g->weights))
+    return fail(nullptr, ARU_EINVAL, "aru_create: empty program");
+  int ndev = aru_device_count();
+  if (ndev <= 0) return fail(nullptr, ARU_ENODEV, "no CUDA device: the B200 engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, ARU_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+  std::unique_ptr<aru_engine> e(new aru_engine);
+  e->device = device;
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return fail(nullptr, ARU_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(err));
+  cudaDeviceProp prop;
+  err = cudaGetDeviceProperties(&prop, device);
+  if (err != cudaSuccess) return fail(nullptr, ARU_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(err));
+  if (prop.major != 10)
+    return fail(nullptr, ARU_EUNSUP, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  e->num_sms = prop.multiProcessorCount;
+  e->max_smem = prop.sharedMemPerBlockOptin;
+  e->buffers.assign(g->buffers, g->buffers + g->n_buffers);
+  e->ops.assign(g->ops, g->ops + g->n_ops);
+  e->weights.assign(g->weights, g->weights + g->n_weights);
+  e->kind.resize(g->n_buffers);
+  for (int i = 0; i < g->n_buffers; ++i) {
+    const aru_buffer& b = e->buffers[i];
+    if (b.channels <= 0) return fail(nullptr, ARU_EINVAL, "buffer %d has %d channels", i, b.channels);
+    if (b.role == 1) {
+      if (e->input_buf >= 0 || b.channels != 1) return fail(nullptr, ARU_EUNSUP, "exactly one 1-channel input is supported");
+      e->input_buf = i;
+    }
+    if (b.role == 2) {
+      if (e->output_buf >= 0) return fail(nullptr, ARU_EUNSUP, "exactly one output is supported");
+      e->output_buf = i;
+      e->n_class = b.channels;
+    }
+    e->kind[i] = b.role == 2 ? KIND_OUT : (b.channels == 1 ? KIND_F32 : KIND_PLANAR);
+  }
+  if (e->input_buf < 0 || e->output_buf < 0) return fail(nullptr, ARU_EINVAL, "program lacks an input or output buffer");
+  // static validation of the ops
+  for (int i = 0; i < g->n_ops; ++i) {
+    const aru_op& op = e->ops[i];
+    auto bad = [&](const char* what) { return fail(nullptr, ARU_EINVAL, "op %d: %s", i, what); };
+    if (op.kind == ARU_OP_COMBINE) {
+      if (op.n_scales < 1 || op.n_scales > ARU_MAX_SCALES) return bad("bad number of attention scales");
+      if (!view_ok(e.get(), op.out) || e->kind[op.out.buf] != KIND_PLANAR || op.out.ch_off % 8) return bad("bad output view");
+      if (op.like_buf < 0 || op.like_buf >= g->n_buffers) return bad("bad like buffer");
+      for (int k = 0; k < op.n_scales; ++k) {
+        if (!view_ok(e.get(), op.att[k]) || e->kind[op.att[k].buf] != KIND_F32) return bad("attention map must be a 1-channel plane");
+        if (!view_ok(e.get(), op.det[k]) || e->kind[op.det[k].buf] != KIND_PLANAR || op.det[k].ch_off % 8)
+          return bad("bad detection map view");
+        if (op.up_att[k] < 1 || op.up_det[k] < 1) return bad("bad upsample factor");
+        if (op.up_det[k] == 1 && op.det[k].ch != op.out.ch) return bad("full-resolution detection map channel mismatch");
+      }
+      continue;
+    }
+    if (!view_ok(e.get(), op.in) || !view_ok(e.get(), op.out)) return bad("bad input / output view");
+    const int ik = e->kind[op.in.buf], ok = e->kind[op.out.buf];
+    if (ik == KIND_PLANAR && op.in.ch_off % 8) return bad("input channel offset must be a multiple of 8");
+    if (ok == KIND_PLANAR && op.out.ch_off % 8) return bad("output channel offset must be a multiple of 8");
+    if (ik == KIND_OUT) return bad("the network output cannot be read by an op");
+    switch (op.kind) {
+      case ARU_OP_CONV:
+        if (op.ksize != 3 && op.ksize != 4) return bad("only 3x3 and 4x4 convolutions are supported");
+        if (ik == KIND_F32) {
+          if (ok != KIND_PLANAR || op.out.ch > 16) return bad("1-channel input conv must produce <= 16 planar channels");
+          if (op.act != ARU_ACT_NONE && op.act != ARU_ACT_RELU) return bad("unsupported activation on a stem conv");
+          if (op.res.buf >= 0) return bad("residual on a stem conv");
+        } else if (ok != KIND_PLANAR) {
+          if (op.out.ch > 8) return bad("float-output conv supports C_out <= 8");
+          if (op.res.buf >= 0 || op.out_pre.buf >= 0) return bad("residual / pre-activation export on a float-output conv");
+          if (op.out.ch_off != 0 || op.out.ch != e->buffers[op.out.buf].channels) return bad("float outputs cannot be sliced");
+        } else {
+          if (op.act != ARU_ACT_NONE && op.act != ARU_ACT_RELU) return bad("unsupported activation");
+        }
+        if (op.out_pre.buf >= 0 && (!view_ok(e.get(), op.out_pre) || e->kind[op.out_pre.buf] != KIND_PLANAR ||
+                                    op.out_pre.ch != op.out.ch || op.out_pre.ch_off % 8))
+          return bad("bad pre-activation view");
+        if (op.res.buf >= 0 && (!view_ok(e.get(), op.res) || e->kind[op.res.buf] != KIND_PLANAR || op.res.ch != op.out.ch ||
+                                op.res.ch_off % 8))
+          return bad("bad residual view");
+        break;
+      case ARU_OP_DECONV:
+        if (op.ksize != 3 || op.stride != 2) return bad("only 3x3 stride-2 transposed convolutions are supported");
+        if (ik != KIND_PLANAR || ok != KIND_PLANAR) return bad("transposed conv needs planar tensors");
+        if (op.act != ARU_ACT_NONE && op.act != ARU_ACT_RELU) return bad("unsupported activation");
+        if (op.like_buf < 0 || op.like_buf >= g->n_buffers) return bad("bad like buffer");
+        break;
+      case ARU_OP_MAXPOOL:
+      case ARU_OP_AVGPOOL:
+        if (ik != ok && !(ik == KIND_F32 && ok == KIND_F32)) return bad("pool input / output kinds differ");
+        if (op.in.ch != op.out.ch) return bad("pool channel mismatch");
+        break;
+      case ARU_OP_UPSUM:
+        if (op.stride < 1 || op.like_buf < 0 || op.like_buf >= g->n_buffers) return bad("bad upsample");
+        if (ik != ok) return bad("upsample input / output kinds differ");
+        break;
+      case ARU_OP_COPY:
+        if (ik != KIND_PLANAR || ok != KIND_PLANAR || op.in.ch != op.out.ch) return bad("bad copy");
+        break;
+      default:
+        return fail(nullptr, ARU_EUNSUP, "op %d: unknown kind %d", i, op.kind);
+    }
+  }
+  err = cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaMalloc((void**)&e->err_flag, sizeof(int));
+  if (err == cudaSuccess) err = cudaMemset(e->err_flag, 0, sizeof(int));
+  if (err != cudaSuccess) return fail(nullptr, ARU_ECUDA, "stream / flag setup: %s", cudaGetErrorString(err));
+  e->opw.resize(g->n_ops);
+  for (int i = 0; i < g->n_ops; ++i) {
+    int rc = pack_op_weights(e.get(), i);
+    if (rc) {
+      g_error = e->error;
+      aru_destroy(e.release());
+      return rc;
+    }
+  }
+  *out = e.release();
+  return ARU_OK;
+}
+
+void aru_destroy(aru_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& p : e->plans) free_plan(p.get());
+  for (auto& w : e->opw) {
+    if (w.w16) cudaFree(w.w16);
+    if (w.w_tc) cudaFree(w.w_tc);
+    if (w.w32) cudaFree(w.w32);
+    if (w.bias) cudaFree(w.bias);
+  }
+  if (e->err_flag) cudaFree(e->err_flag);
+  if (e->s_comp) cudaStreamDestroy(e->s_comp);
+  if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+  if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+  delete e;
+}
+
+int aru_set_option(aru_engine* e, int option, int64_t value) {
+  if (!e) return ARU_EINVAL;
+  switch (option) {
+    case ARU_OPT_CONV_PATH:
+      if (value != 0 && value != 1) return fail(e, ARU_EINVAL, "ARU_OPT_CONV_PATH must be 0 or 1");
+      if (e->conv_path != (int)value) {  // plans bake the kernel choice in
+        cudaSetDevice(e->device);
+        cudaDeviceSynchronize();
+        for (auto& p : e->plans) free_plan(p.get());
+        e->plans.clear();
+        e->cur = nullptr;
+      }
+      e->conv_path = (int)value;
+      return ARU_OK;
+    case ARU_OPT_USE_GRAPH:
+      e->use_graph = value ? 1 : 0;
+      return ARU_OK;
+    case ARU_OPT_MICRO_BATCH:
+      if (value < 0 || value > 4096) return fail(e, ARU_EINVAL, "bad micro batch");
+      e->micro_batch = (int)value;
+      return ARU_OK;
+    default:
+      return fail(e, ARU_EINVAL, "unknown option %d", option);
+  }
+}
+
+int aru_num_classes(const aru_engine* e) { return e ? e->n_class : 0; }
+
+int aru_plan(aru_engine* e, int n, int h, int w) {
+  if (!e || n <= 0 || h <= 0 || w <= 0) return e ? fail(e, ARU_EINVAL, "aru_plan: bad shape") : ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  Plan* p = nullptr;
+  int rc = get_plan(e, n, h, w, &p);
+  if (rc) return rc;
+  e->cur = p;
+  return ARU_OK;
+}
+
+int aru_forward(aru_engine* e, const float* in, int n, int h, int w, float* out, uint8_t* out_u8, uint8_t* out_mask,
+                float thr) {
+  if (!e || !in || n <= 0 || h <= 0 || w <= 0) return e ? fail(e, ARU_EINVAL, "aru_forward: bad argument") : ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  const int mb = pick_micro_batch(e, n, h, w);
+  const size_t page_px = (size_t)h * w;
+  const int C = e->n_class;
+  int slot = 0;
+  std::vector<Plan*> used;
+  for (int i0 = 0; i0 < n; i0 += mb, ++slot) {
+    const int cnt = std::min(mb, n - i0);
+    Plan* p = nullptr;
+    int rc = get_plan(e, cnt, h, w, &p);
+    if (rc) return rc;
+    e->cur = p;
+    if (std::find(used.begin(), used.end(), p) == used.end()) used.push_back(p);
+    rc = ensure_quant(e, p, out_u8 != nullptr, out_mask != nullptr);
+    if (rc) return rc;
+    const int par = slot & 1;
+    // buffers of this parity are free once the device->host copies of their previous use are done
+    if (p->d2h_pending[par]) {
+      CU(e, cudaStreamWaitEvent(e->s_h2d, p->ev_d2h[par], 0));
+      CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_d2h[par], 0));
+    }
+    CU(e, cudaMemcpyAsync(p->in_dev[par], in + (size_t)i0 * page_px, (size_t)cnt * page_px * sizeof(float),
+                          cudaMemcpyHostToDevice, e->s_h2d));
+    CU(e, cudaEventRecord(p->ev_h2d[par], e->s_h2d));
+    CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_h2d[par], 0));
+    rc = enqueue_forward(e, p, par, e->s_comp);
+    if (rc) return rc;
+    if (out_u8 || out_mask) {
+      cudaError_t err = launch_quantize(e->s_comp, p->out_dev[par], out_u8 ? p->u8_dev[par] : nullptr,
+                                        out_mask ? p->mask_dev[par] : nullptr, (long long)cnt * page_px, C, thr);
+      if (err != cudaSuccess) return fail(e, ARU_ECUDA, "quantize launch: %s", cudaGetErrorString(err));
+    }
+    CU(e, cudaEventRecord(p->ev_comp[par], e->s_comp));
+    CU(e, cudaStreamWaitEvent(e->s_d2h, p->ev_comp[par], 0));
+    if (out)
+      CU(e, cudaMemcpyAsync(out + (size_t)i0 * page_px * C, p->out_dev[par], (size_t)cnt * page_px * C * sizeof(float),
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+    if (out_u8)
+      CU(e, cudaMemcpyAsync(out_u8 + (size_t)i0 * page_px * C, p->u8_dev[par], (size_t)cnt * page_px * C,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+    if (out_mask)
+      CU(e, cudaMemcpyAsync(out_mask + (size_t)i0 * page_px, p->mask_dev[par], (size_t)cnt * page_px,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+    CU(e, cudaEventRecord(p->ev_d2h[par], e->s_d2h));
+    p->d2h_pending[par] = true;
+  }
+  CU(e, cudaStreamSynchronize(e->s_d2h));
+  CU(e, cudaStreamSynchronize(e->s_comp));
+  for (Plan* p : used) p->d2h_pending[0] = p->d2h_pending[1] = false;
+  return check_err_flag(e);
+}
+
+int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, float* out, uint8_t* out_u8,
+                       uint8_t* out_mask, float thr, void* stream) {
+  if (!e || !in || n <= 0 || h <= 0 || w <= 0) return e ? fail(e, ARU_EINVAL, "aru_forward_device: bad argument") : ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->s_comp;
+  const int mb = pick_micro_batch(e, n, h, w);
+  const size_t page_px = (size_t)h * w;
+  const int C = e->n_class;
+  for (int i0 = 0; i0 < n; i0 += mb) {
+    const int cnt = std::min(mb, n - i0);
+    Plan* p = nullptr;
+    int rc = get_plan(e, cnt, h, w, &p);
+    if (rc) return rc;
+    e->cur = p;
+    CU(e, cudaMemcpyAsync(p->in_dev[0], in + (size_t)i0 * page_px, (size_t)cnt * page_px * sizeof(float),
+                          cudaMemcpyDeviceToDevice, st));
+    rc = enqueue_forward(e, p, 0, st);
+    if (rc) return rc;
+    if (out)
+      CU(e, cudaMemcpyAsync(out + (size_t)i0 * page_px * C, p->out_dev[0], (size_t)cnt * page_px * C * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+    if (out_u8 || out_mask) {
+      cudaError_t err = launch_quantize(st, p->out_dev[0], out_u8 ? out_u8 + (size_t)i0 * page_px * C : nullptr,
+                                        out_mask ? out_mask + (size_t)i0 * page_px : nullptr, (long long)cnt * page_px, C, thr);
+      if (err != cudaSuccess) return fail(e, ARU_ECUDA, "quantize launch: %s", cudaGetErrorString(err));
+    }
+  }
+  return ARU_OK;
+}
+
+int aru_sync(aru_engine* e) {
+  if (!e) return ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaStreamSynchronize(e->s_h2d));
+  CU(e, cudaStreamSynchronize(e->s_comp));
+  CU(e, cudaStreamSynchronize(e->s_d2h));
+  return check_err_flag(e);
+}
+
+int aru_launches_per_forward(const aru_engine* e) { return (e && e->cur) ? e->cur->launches : 0; }
+
+int aru_buffer_dims(const aru_engine* e, int buf, int* h, int* w, int* c) {
+  if (!e || !e->cur || buf < 0 || buf >= (int)e->buffers.size()) return ARU_EINVAL;
+  const BufPlan& b = e->cur->bufs[buf];
+  if (h) *h = b.h;
+  if (w) *w = b.w;
+  if (c) *c = b.channels;
+  return b.sized ? ARU_OK : ARU_EINVAL;
+}
+
+int aru_read_buffer(aru_engine* e, int buf, int n_index, float* out_nhwc, size_t out_floats) {
+  if (!e || !e->cur || buf < 0 || buf >= (int)e->buffers.size() || !out_nhwc)
+    return e ? fail(e, ARU_EINVAL, "aru_read_buffer: bad argument") : ARU_EINVAL;
+  Plan* p = e->cur;
+  const BufPlan& b = p->bufs[buf];
+  if (!b.sized || n_index < 0 || n_index >= p->n) return fail(e, ARU_EINVAL, "aru_read_buffer: bad buffer / page index");
+  const size_t cnt = (size_t)b.h * b.w * b.channels;
+  if (out_floats < cnt) return fail(e, ARU_EINVAL, "aru_read_buffer: output too small (%zu < %zu)", out_floats, cnt);
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaStreamSynchronize(e->s_comp));
+  if (b.kind != KIND_PLANAR) {
+    const float* src = f32_ptr(e, p, buf, 0) + (size_t)n_index * cnt;
+    CU(e, cudaMemcpy(out_nhwc, src, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    return ARU_OK;
+  }
+  float* tmp = nullptr;
+  CU(e, cudaMalloc((void**)&tmp, (size_t)p->n * cnt * sizeof(float)));
+  aru_view v{buf, 0, b.channels};
+  cudaError_t err = launch_unpack_nhwc(e->s_comp, make_pv(e, p, v), b.geo, tmp);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+  if (err == cudaSuccess) err = cudaMemcpy(out_nhwc, tmp + (size_t)n_index * cnt, cnt * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  if (err != cudaSuccess) return fail(e, ARU_ECUDA, "aru_read_buffer: %s", cudaGetErrorString(err));
+  return ARU_OK;
+}
+
+int aru_profile_ops(aru_engine* e, int iters, float* ms, int n_ms) {
+  if (!e || !e->cur || !ms || iters <= 0 || n_ms < (int)e->ops.size())
+    return e ? fail(e, ARU_EINVAL, "aru_profile_ops: bad argument / no plan") : ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  Plan* p = e->cur;
+  cudaEvent_t a, b;
+  CU(e, cudaEventCreate(&a));
+  CU(e, cudaEventCreate(&b));
+  for (int i = 0; i < (int)e->ops.size(); ++i) {
+    int rc = run_op(e, p, i, 0, e->s_comp);  // warm
+    if (rc) return rc;
+    CU(e, cudaEventRecord(a, e->s_comp));
+    for (int k = 0; k < iters; ++k)
+      if ((rc = run_op(e, p, i, 0, e->s_comp))) return rc;
+    CU(e, cudaEventRecord(b, e->s_comp));
+    CU(e, cudaEventSynchronize(b));
+    float t = 0.f;
+    CU(e, cudaEventElapsedTime(&t, a, b));
+    ms[i] = t / iters;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return check_err_flag(e);
+}
+
+const char* aru_op_kernel_name(const aru_engine* e, int op) {
+  if (!e || !e->cur || op < 0 || op >= (int)e->ops.size()) return "";
+  return e->cur->kernel[op];
+}
+
+int aru_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return ARU_EINVAL;
+  cudaError_t err = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (err != cudaSuccess) {
+    g_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(err);
+    cudaGetLastError();
+    return ARU_ENOMEM;
+  }
+  return ARU_OK;
+}
+
+void aru_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// kernels.h - host-side launchers of the engine's CUDA kernels (kernels_simple.cu, conv_tc.cu).
+#pragma once
+#include "aru_common.cuh"
+
+namespace aru {
+
+// A channel-slice view of a chunk-planar tensor: `p` points at position 0 of the first plane.
+struct PV {
+  act_t* p = nullptr;
+  long long plane = 0;  // positions between consecutive planes
+  int chunks = 0;       // planes in the view
+  int C = 0;            // logical channels
+};
+
+struct CombineArgs {
+  const float* att[8];
+  const act_t* det[8];
+  long long det_plane[8];
+  Geo det_geo[8];
+  int att_h[8], att_w[8], att_up[8], att_oy[8], att_ox[8];
+  int det_up[8], det_oy[8], det_ox[8], det_chunks[8];
+  int A;
+  act_t* out;
+  long long out_plane;
+  int out_chunks;
+  Geo geo;  // output geometry
+};
+
+// ---- CUDA-core kernels (kernels_simple.cu) -------------------------------------------------------
+cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w,
+                             const float* bias, const Geo& g, int act);
+cudaError_t launch_conv_direct(cudaStream_t st, int ks, PV in, PV out, PV out_pre, PV res, const act_t* w,
+                               const float* bias, const Geo& g, int act);
+cudaError_t launch_conv_small(cudaStream_t st, int ks, int cout, PV in, float* out, const float* w, const float* bias,
+                              const Geo& g, int act);
+cudaError_t launch_deconv_direct(cudaStream_t st, PV in, const Geo& gi, PV out, const Geo& go, const act_t* w,
+                                 const float* bias, int act);
+cudaError_t launch_pool(cudaStream_t st, bool is_max, PV in, const Geo& gi, PV out, const Geo& go);
+cudaError_t launch_pool_f32(cudaStream_t st, bool is_max, const float* in, float* out, int N, int Hi, int Wi, int Ho,
+                            int Wo);
+cudaError_t launch_combine(cudaStream_t st, const CombineArgs& a);
+cudaError_t launch_upsum(cudaStream_t st, PV in, const Geo& gi, PV out, const Geo& go, int up, int oy, int ox);
+cudaError_t launch_upsum_f32(cudaStream_t st, const float* in, int Hi, int Wi, float* out, int N, int H, int W, int up,
+                             int oy, int ox);
+cudaError_t launch_copy(cudaStream_t st, const void* in, void* out, long long bytes);
+cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uint8_t* mask, long long npix, int C,
+                            float thr);
+// debug read-back: chunk-planar view -> dense float32 NHWC [N][H][W][C]
+cudaError_t launch_unpack_nhwc(cudaStream_t st, PV in, const Geo& g, float* out);
+
+// ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) ---------------------------------------------
+struct ConvTcPlan {
+  bool ok = false;       // false: shape not covered by the tensor-core kernel (caller must use another kernel)
+  int ks = 0;
+  int cin_chunks = 0;
+  int cout_chunks = 0;   // real output planes
+  int npad = 0;          // UMMA N (multiple of 16)
+  int n_steps = 0;       // K=16 MMA steps per tile
+  int n_slots = 0;       // ring slots (128 positions each)
+  int n_stages = 0;      // TMEM accumulator stages
+  int grid = 0;
+  size_t smem_bytes = 0;
+  size_t wpack_bytes = 0;  // packed B image (16-bit elements)
+  long long tile_begin = 0, tile_end = 0;
+  const char* why = "";
+};
+
+// Decide whether / how the tcgen05 kernel runs conv (ks x ks, cin -> cout) on geometry g.
+ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, size_t max_smem);
+// Pack a TF-layout filter [ks][ks][cin][cout] (float32) into the kernel's shared-memory B image.
+void conv_tc_pack_weights(const ConvTcPlan& plan, const float* w_tf, int cin, int cout, uint16_t* dst);
+cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& plan, PV in, PV out, PV out_pre, PV res,
+                           const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag);
+
+// host-side 16-bit conversion matching act_t
+uint16_t host_f_to_act(float v);
+
+}  // namespace aru

@@ -1,0 +1,240 @@
+"""ctypes binding of libaru_b200.so (include/aru_b200.h) - the B200 ARU-Net forward engine.
+
+This is the host side of the drop-in boundary: ``Engine`` is what replaces the ``tf.Graph`` +
+``tf.Session`` pair of net_post_processing_helper.py:36-72.  There is no CPU path: if the shared
+library is missing or no sm_100 GPU is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+import weakref
+from typing import Optional, Tuple, Union
+
+import numpy as np
+
+from .graphdef import parse_graphdef
+from .program import CGraphDesc, Program, lower_graph
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libaru_b200.so")
+
+ARU_OK, ARU_EINVAL, ARU_ECUDA, ARU_ENOMEM, ARU_EUNSUP, ARU_ENODEV = 0, 1, 2, 3, 4, 5
+OPT_CONV_PATH, OPT_USE_GRAPH, OPT_MICRO_BATCH = 1, 2, 3
+
+# every symbol include/aru_b200.h declares (checked by tests/test_cabi.py)
+EXPORTS = [
+    "aru_abi_version", "aru_device_count", "aru_create", "aru_destroy", "aru_set_option", "aru_num_classes",
+    "aru_plan", "aru_forward", "aru_forward_device", "aru_sync", "aru_launches_per_forward", "aru_read_buffer",
+    "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"aru_b200 error {code}: {message}")
+        self.code = code
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the engine; fails loudly when it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); "
+                               "the B200 engine has no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+        fp = ctypes.POINTER(ctypes.c_float)
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        lib.aru_abi_version.restype = i32
+        lib.aru_device_count.restype = i32
+        lib.aru_create.argtypes = [ctypes.POINTER(CGraphDesc), i32, ctypes.POINTER(vp)]
+        lib.aru_create.restype = i32
+        lib.aru_destroy.argtypes = [vp]
+        lib.aru_destroy.restype = None
+        lib.aru_set_option.argtypes = [vp, i32, i64]
+        lib.aru_num_classes.argtypes = [vp]
+        lib.aru_plan.argtypes = [vp, i32, i32, i32]
+        lib.aru_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, ctypes.c_float]
+        lib.aru_forward_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, ctypes.c_float, vp]
+        lib.aru_sync.argtypes = [vp]
+        lib.aru_launches_per_forward.argtypes = [vp]
+        lib.aru_read_buffer.argtypes = [vp, i32, i32, fp, sz]
+        lib.aru_buffer_dims.argtypes = [vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        lib.aru_profile_ops.argtypes = [vp, i32, fp, i32]
+        lib.aru_op_kernel_name.argtypes = [vp, i32]
+        lib.aru_op_kernel_name.restype = ctypes.c_char_p
+        lib.aru_last_error.argtypes = [vp]
+        lib.aru_last_error.restype = ctypes.c_char_p
+        lib.aru_host_alloc.argtypes = [ctypes.POINTER(vp), sz]
+        lib.aru_host_free.argtypes = [vp]
+        lib.aru_host_free.restype = None
+        del u8p
+        _lib = lib
+        return lib
+
+
+# ------------------------------------------------------------------------------------------------
+# pinned host arrays
+# ------------------------------------------------------------------------------------------------
+class _PinnedPool:
+    """Recycles page-locked host blocks; numpy arrays handed out return their block on garbage collection."""
+
+    def __init__(self, max_cached_bytes: int = 8 << 30):
+        self.free = {}
+        self.cached = 0
+        self.max_cached = max_cached_bytes
+        self.lock = threading.Lock()
+
+    def _release(self, ptr: int, nbytes: int):
+        with self.lock:
+            if self.cached + nbytes <= self.max_cached:
+                self.free.setdefault(nbytes, []).append(ptr)
+                self.cached += nbytes
+                return
+        load_library().aru_host_free(ctypes.c_void_p(ptr))
+
+    def empty(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        ptr = None
+        with self.lock:
+            lst = self.free.get(nbytes)
+            if lst:
+                ptr = lst.pop()
+                self.cached -= nbytes
+        if ptr is None:
+            p = ctypes.c_void_p()
+            rc = load_library().aru_host_alloc(ctypes.byref(p), nbytes)
+            if rc != ARU_OK:
+                raise EngineError(rc, "pinned host allocation failed")
+            ptr = p.value
+        buf = (ctypes.c_byte * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._release, ptr, nbytes)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+PINNED = _PinnedPool()
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    return PINNED.empty(shape, dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# engine
+# ------------------------------------------------------------------------------------------------
+class Engine:
+    """One frozen graph on one GPU.  ``forward`` = the reference's ``sess.run(out, {x: image})``."""
+
+    def __init__(self, pb: Union[bytes, str, os.PathLike], device: int = 0, in_name: str = "inImg",
+                 out_name: str = "output"):
+        if not isinstance(pb, (bytes, bytearray)):
+            with open(pb, "rb") as f:
+                pb = f.read()
+        self.program: Program = lower_graph(parse_graphdef(bytes(pb)), in_name, out_name)
+        self.lib = load_library()
+        if self.lib.aru_abi_version() != 1:
+            raise RuntimeError("libaru_b200.so ABI version mismatch")
+        desc, keep = self.program.desc()
+        handle = ctypes.c_void_p()
+        rc = self.lib.aru_create(ctypes.byref(desc), int(device), ctypes.byref(handle))
+        del keep
+        if rc != ARU_OK:
+            raise EngineError(rc, (self.lib.aru_last_error(None) or b"").decode())
+        self.handle = handle
+        self.device = int(device)
+        self.n_class = self.lib.aru_num_classes(handle)
+        self._finalizer = weakref.finalize(self, self.lib.aru_destroy, handle)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != ARU_OK:
+            raise EngineError(rc, (self.lib.aru_last_error(self.handle) or b"").decode())
+
+    def close(self):
+        self._finalizer()
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.aru_set_option(self.handle, option, int(value)))
+
+    def plan(self, n: int, h: int, w: int):
+        self._check(self.lib.aru_plan(self.handle, n, h, w))
+
+    @property
+    def launches_per_forward(self) -> int:
+        return self.lib.aru_launches_per_forward(self.handle)
+
+    # -- forward ---------------------------------------------------------------------------------
+    @staticmethod
+    def _as_batch(images: np.ndarray) -> np.ndarray:
+        x = np.asarray(images)
+        if x.ndim == 2:
+            x = x[None]
+        elif x.ndim == 4:
+            if x.shape[-1] != 1:
+                raise ValueError(f"expected a 1-channel image batch, got shape {x.shape}")
+            x = x[..., 0]
+        elif x.ndim != 3:
+            raise ValueError(f"expected [H,W], [N,H,W] or [N,H,W,1], got shape {x.shape}")
+        return x
+
+    def forward(self, images: np.ndarray, want_u8: bool = False, want_mask: bool = False, threshold: float = 0.05,
+                want_prob: bool = True):
+        """images: float [N,H,W] in [0,1] (any float dtype; pinned float32 is zero-copy).
+        Returns prob float32 [N,H,W,C] (pinned), plus uint8 / mask arrays when requested."""
+        x = self._as_batch(images)
+        n, h, w = x.shape
+        if not (x.dtype == np.float32 and x.flags.c_contiguous):
+            xin = pinned_empty((n, h, w), np.float32)
+            np.copyto(xin, x, casting="unsafe")
+            x = xin
+        c = self.n_class
+        prob = pinned_empty((n, h, w, c), np.float32) if want_prob else None
+        u8 = pinned_empty((n, h, w, c), np.uint8) if want_u8 else None
+        mask = pinned_empty((n, h, w), np.uint8) if want_mask else None
+        ptr = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None  # noqa: E731
+        self._check(self.lib.aru_forward(self.handle, ptr(x), n, h, w, ptr(prob), ptr(u8), ptr(mask),
+                                         ctypes.c_float(threshold)))
+        outs = tuple(a for a in (prob, u8, mask) if a is not None)
+        return outs[0] if len(outs) == 1 else outs
+
+    def forward_device(self, in_ptr: int, n: int, h: int, w: int, out_ptr: int = 0, u8_ptr: int = 0, mask_ptr: int = 0,
+                       threshold: float = 0.05, stream: int = 0):
+        """Device-resident variant (raw device pointers, e.g. torch ``tensor.data_ptr()``); only enqueues."""
+        vp = lambda v: ctypes.c_void_p(v) if v else None  # noqa: E731
+        self._check(self.lib.aru_forward_device(self.handle, vp(in_ptr), n, h, w, vp(out_ptr), vp(u8_ptr), vp(mask_ptr),
+                                                ctypes.c_float(threshold), vp(stream)))
+
+    def sync(self):
+        self._check(self.lib.aru_sync(self.handle))
+
+    # -- introspection -----------------------------------------------------------------------------
+    def read_buffer(self, buf: int, page: int = 0) -> np.ndarray:
+        h, w, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.aru_buffer_dims(self.handle, buf, ctypes.byref(h), ctypes.byref(w), ctypes.byref(c)))
+        out = np.empty((h.value, w.value, c.value), np.float32)
+        self._check(self.lib.aru_read_buffer(self.handle, buf, page, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                             out.size))
+        return out
+
+    def read_node(self, node_name: str, page: int = 0) -> np.ndarray:
+        """Value of a GraphDef node that survived lowering (per-layer parity tests)."""
+        v = self.program.tensor_of_node[node_name]
+        full = self.read_buffer(v.buf, page)
+        return full[..., v.ch_off:v.ch_off + v.ch]
+
+    def profile_ops(self, iters: int = 5):
+        """[(op name, kernel label, ms)] for the current plan (CUDA events, plain launches)."""
+        n = len(self.program.ops)
+        ms = (ctypes.c_float * n)()
+        self._check(self.lib.aru_profile_ops(self.handle, iters, ms, n))
+        return [(self.program.ops[i].name, (self.lib.aru_op_kernel_name(self.handle, i) or b"").decode(), float(ms[i]))
+                for i in range(n)]

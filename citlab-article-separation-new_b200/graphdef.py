@@ -285,7 +285,7 @@ class GraphBuilder:
         return self._node(name, "AddN", xs, T=self.F, N=len(xs))
 
     def serialize(self) -> bytes:
-        return self.gd.SerializeToString()
+        return self.gd.SerializeToString(deterministic=True)
 
 
 def build_aru_graphdef(graph: str = "ARU", scale_space_num: int = 5, num_scales_att: int = 3,

@@ -18,12 +18,17 @@ from .graphdef import build_aru_graphdef
 # name -> kwargs of build_aru_graphdef (logit_gain/logit_bias from calibrate_logits.py)
 NETS = {
     "separator": dict(graph="ARU", scale_space_num=5, num_scales_att=3, n_class=2, seed=0,
-                      logit_gain=1.0, logit_bias=(0.1, 0.1)),
+                      logit_gain=0.773170, logit_bias=(-15.335476, 0.0)),
     "heading": dict(graph="ARU", scale_space_num=5, num_scales_att=3, n_class=2, seed=1,
-                    logit_gain=1.0, logit_bias=(0.1, 0.1)),
-    "ru": dict(graph="RU", scale_space_num=5, n_class=2, seed=2, logit_gain=1.0, logit_bias=(0.1, 0.1)),
+                    logit_gain=1.112696, logit_bias=(4.220346, 0.0)),
+    "ru": dict(graph="RU", scale_space_num=5, n_class=2, seed=2, logit_gain=0.592449, logit_bias=(-5.465143, 0.0)),
     "aru_s6a5": dict(graph="ARU", scale_space_num=6, num_scales_att=5, n_class=2, seed=3,
-                     logit_gain=1.0, logit_bias=(0.1, 0.1)),
+                     logit_gain=1.072904, logit_bias=(-19.107500, 0.0)),
+    # small nets for fast CPU tests / per-layer parity
+    "tiny": dict(graph="ARU", scale_space_num=3, num_scales_att=2, n_class=2, seed=4,
+                 logit_gain=0.5, logit_bias=(-3.0, 0.0)),
+    "tiny_sigmoid": dict(graph="RU", scale_space_num=2, n_class=1, seed=5, output="sigmoid",
+                         logit_gain=0.5, logit_bias=(-1.0,)),
 }
 
 
@@ -38,8 +43,9 @@ def synth_page(h: int, w: int, seed: int = 0) -> np.ndarray:
     rng = np.random.default_rng(seed)
     img = np.clip(rng.normal(225.0, 6.0, size=(h, w)), 0, 255)
     n_cols = int(rng.integers(2, 6))
-    margin = max(4, w // 40)
-    col_w = (w - margin * (n_cols + 1)) // n_cols
+    margin = max(1, min(max(4, w // 40), (min(h, w) - 1) // 2))
+    n_cols = max(1, min(n_cols, (w - margin) // (margin + 8)))
+    col_w = max(4, (w - margin * (n_cols + 1)) // n_cols)
     line_h = max(3, h // 170)
     for c in range(n_cols):
         x0 = margin + c * (col_w + margin)
@@ -49,19 +55,21 @@ def synth_page(h: int, w: int, seed: int = 0) -> np.ndarray:
                 y += int(rng.integers(2, 6)) * line_h
                 continue
             x = x0
-            x_end = x0 + col_w - (int(rng.integers(0, col_w // 2)) if rng.random() < 0.15 else 0)
+            x_end = x0 + col_w - (int(rng.integers(0, max(1, col_w // 2))) if rng.random() < 0.15 else 0)
             th = int(rng.integers(max(2, line_h - 2), line_h + 1))
             while x < x_end:
                 wl = int(rng.integers(2, max(3, col_w // 6)))
                 x1 = min(x + wl, x_end)
-                img[y:y + th, x:x1] = rng.normal(60.0, 25.0, size=(min(th, h - y), x1 - x)).clip(0, 255)
+                x1 = min(x1, w)
+                if x1 > x:
+                    img[y:y + th, x:x1] = rng.normal(60.0, 25.0, size=(min(th, h - y), x1 - x)).clip(0, 255)
                 x = x1 + int(rng.integers(1, 4))
             y += line_h + int(rng.integers(1, 3))
         if c < n_cols - 1 and rng.random() < 0.8:           # vertical rule between columns
             xr = x0 + col_w + margin // 2
             t = int(rng.integers(1, 4))
             y0, y1 = sorted(int(v) for v in rng.integers(margin, h - margin, size=2))
-            if y1 - y0 > h // 8:
+            if y1 - y0 > h // 8 and xr < w:
                 img[y0:y1, xr:xr + t] = rng.normal(40.0, 10.0, size=(y1 - y0, min(t, w - xr))).clip(0, 255)
     for _ in range(int(rng.integers(1, 5))):                # horizontal rules
         yr = int(rng.integers(margin, h - margin))

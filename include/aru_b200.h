@@ -145,6 +145,12 @@ const char* aru_op_kernel_name(const aru_engine* e, int op);
 
 const char* aru_last_error(const aru_engine* e);
 
+/* Page-locked host memory for the in / out arrays of aru_forward(): with pinned buffers the
+ * host<->device copies of consecutive micro-batches overlap the kernels (pageable memory works too,
+ * but serialises). */
+int aru_host_alloc(void** ptr, size_t bytes);
+void aru_host_free(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

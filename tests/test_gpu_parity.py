@@ -1,0 +1,204 @@
+"""GPU parity tests proper: the CUDA engine (through the C ABI) against the CPU oracle, the committed
+golden fixtures, and size-independent properties at the benchmark sizes.
+
+Tolerances are BASELINE.json's: probability maps max-abs <= 2e-2, mean-abs <= 1e-3 (16-bit operands,
+fp32 accumulate), >= 99.9 % pixel agreement of the binarised mask (u8 > 0.05*255, i.e. u8 >= 13;
+separator_net_post_processor.py:147-149).  The uint8 / mask kernels are integer work and are checked
+bit-exactly against numpy applied to the engine's own float output.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MAX_ABS, MEAN_ABS, MASK_AGREE = 2e-2, 1e-3, 0.999
+PATHS = [(0, "tcgen05"), (1, "cuda-core")]
+
+
+def _mask(p):
+    return (p[..., 0] * 255).astype(np.uint8) > 12.75
+
+
+def _check(got, ref, what=""):
+    assert got.shape == ref.shape and got.dtype == np.float32, what
+    assert np.isfinite(got).all(), what
+    d = np.abs(got - ref)
+    agree = float((_mask(got) == _mask(ref)).mean())
+    assert d.max() <= MAX_ABS, f"{what}: max-abs {d.max():.3e}"
+    assert d.mean() <= MEAN_ABS, f"{what}: mean-abs {d.mean():.3e}"
+    assert agree >= MASK_AGREE, f"{what}: mask agreement {agree:.5f}"
+
+
+@pytest.fixture(scope="module")
+def engines(built_lib):
+    from aru_b200.engine import Engine
+    from aru_b200.synth import synth_pb
+    cache = {}
+
+    def get(net):
+        if net not in cache:
+            cache[net] = Engine(synth_pb(net), device=0)
+        return cache[net]
+
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+@pytest.fixture(scope="module")
+def oracles():
+    from aru_b200.synth import synth_pb
+    from oracle.aru_oracle import Oracle
+    cache = {}
+
+    def get(net):
+        if net not in cache:
+            cache[net] = Oracle(synth_pb(net))
+        return cache[net]
+
+    return get
+
+
+def _native_loaded():
+    with open("/proc/self/maps") as f:
+        return "libaru_b200.so" in f.read()
+
+
+def test_native_library_is_what_runs(engines):
+    engines("tiny")
+    assert _native_loaded()
+
+
+@pytest.mark.parametrize("path,pname", PATHS)
+@pytest.mark.parametrize("fixture", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))), ids=os.path.basename)
+def test_golden_fixtures(engines, fixture, path, pname):
+    from aru_b200.engine import OPT_CONV_PATH
+    from aru_b200.synth import page_to_net_input
+    g = np.load(fixture)
+    net = os.path.basename(fixture).rsplit("_", 1)[0]
+    eng = engines(net)
+    eng.set_option(OPT_CONV_PATH, path)
+    got = eng.forward(page_to_net_input(g["page"]))[0]
+    _check(got, g["prob"], f"{os.path.basename(fixture)} [{pname}]")
+
+
+@pytest.mark.parametrize("path,pname", PATHS)
+@pytest.mark.parametrize("net,h,w", [
+    ("separator", 128, 96),      # /32 in both dims
+    ("separator", 150, 113),     # odd at every level (the CLI default 1500x1125, scaled down)
+    ("separator", 257, 130),     # W+2 spans several 128-position tiles; odd H
+    ("heading", 90, 68),         # heading default height 900, scaled down
+    ("ru", 77, 101),
+    ("aru_s6a5", 129, 97),
+    ("tiny", 8, 8), ("tiny", 9, 200), ("tiny", 200, 9), ("tiny", 1, 1),
+])
+def test_parity_with_oracle(engines, oracles, net, h, w, path, pname):
+    from aru_b200.engine import OPT_CONV_PATH
+    from aru_b200.synth import synth_page, page_to_net_input
+    x = page_to_net_input(synth_page(h, w, seed=h * 1000 + w))
+    ref = oracles(net).run(x)[0]
+    eng = engines(net)
+    eng.set_option(OPT_CONV_PATH, path)
+    _check(eng.forward(x)[0], ref, f"{net} {h}x{w} [{pname}]")
+
+
+@pytest.mark.parametrize("path,pname", PATHS)
+def test_per_layer_parity(engines, oracles, path, pname):
+    """Every surviving GraphDef node of the tiny net against the oracle's value of the same node."""
+    from aru_b200.engine import OPT_CONV_PATH
+    from aru_b200.synth import synth_page, page_to_net_input
+    eng, orc = engines("tiny"), oracles("tiny")
+    eng.set_option(OPT_CONV_PATH, path)
+    x = page_to_net_input(synth_page(45, 39, seed=3))
+    eng.forward(x)
+    checked = 0
+    for node in eng.program.tensor_of_node:
+        if orc.ir[node].op in ("Placeholder", "ConcatV2"):
+            continue
+        ref = orc.run(x, fetch=node)[0]
+        got = eng.read_node(node)
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert got.shape == ref.shape, node
+        assert np.abs(got - ref).max() <= 2e-2 * scale, f"{node} [{pname}]: {np.abs(got - ref).max():.3e} (scale {scale:.2f})"
+        checked += 1
+    assert checked > 40
+
+
+def test_batch_and_micro_batch_consistency(engines):
+    """forward([p0..p4]) == forward(pi) per page, bit-exact, for any micro-batch split (pages are independent)."""
+    from aru_b200.engine import OPT_CONV_PATH, OPT_MICRO_BATCH
+    from aru_b200.synth import synth_page, page_to_net_input
+    eng = engines("separator")
+    eng.set_option(OPT_CONV_PATH, 0)
+    xs = np.stack([page_to_net_input(synth_page(96, 80, s)) for s in range(5)])
+    eng.set_option(OPT_MICRO_BATCH, 0)
+    full = eng.forward(xs).copy()
+    for i in range(5):
+        assert np.array_equal(full[i], eng.forward(xs[i])[0]), i
+    eng.set_option(OPT_MICRO_BATCH, 2)       # 2 + 2 + 1: exercises the pipelined double buffering and a tail plan
+    assert np.array_equal(full, eng.forward(xs))
+    eng.set_option(OPT_MICRO_BATCH, 0)
+
+
+def test_uint8_and_mask_outputs_are_bit_exact(engines):
+    from aru_b200.synth import synth_page, page_to_net_input
+    eng = engines("separator")
+    xs = np.stack([page_to_net_input(synth_page(101, 77, s)) for s in range(3)])
+    prob, u8, mask = eng.forward(xs, want_u8=True, want_mask=True, threshold=0.05)
+    ref_u8 = np.array(prob * 255, dtype=np.uint8)                          # separator_net_post_processor.py:147
+    ref_mask = np.array((ref_u8[..., 0] > 0.05 * 255) * 255, dtype=np.uint8)  # helper.py:75-78
+    assert np.array_equal(u8, ref_u8) and np.array_equal(mask, ref_mask)
+    assert 0 < (mask > 0).mean() < 1
+
+
+def test_float64_input_and_4d_input(engines):
+    from aru_b200.net_boundary import GraphHandle, get_net_output
+    from aru_b200.synth import synth_pb, synth_page, page_to_net_input
+    x = page_to_net_input(synth_page(64, 48, 1))
+    assert x.dtype == np.float64
+    h = GraphHandle(synth_pb("tiny"))
+    a = get_net_output(x, h, gpu_device="0")
+    b = get_net_output(x[None, :, :, None].astype(np.float32), h, gpu_device="")
+    assert a.shape == (64, 48, 2) and a.dtype == np.float32 and a.flags.c_contiguous
+    assert np.array_equal(a, b)
+
+
+def test_tensor_core_and_cuda_core_paths_agree(engines):
+    from aru_b200.engine import OPT_CONV_PATH
+    from aru_b200.synth import synth_page, page_to_net_input
+    eng = engines("separator")
+    x = page_to_net_input(synth_page(300, 200, 9))
+    eng.set_option(OPT_CONV_PATH, 0)
+    a = eng.forward(x).copy()
+    names = {k for _, k, _ in eng.profile_ops(1)}
+    assert "conv_tc" in names, names
+    eng.set_option(OPT_CONV_PATH, 1)
+    b = eng.forward(x).copy()
+    assert "conv_tc" not in {k for _, k, _ in eng.profile_ops(1)}
+    eng.set_option(OPT_CONV_PATH, 0)
+    assert np.abs(a - b).max() <= 5e-3          # same 16-bit operands, different fp32 summation order
+
+
+def test_full_size_page_against_oracle(engines, oracles):
+    """BASELINE config 1: one 1024x768 page, separator net (the oracle needs a few seconds)."""
+    from aru_b200.synth import synth_page, page_to_net_input
+    x = page_to_net_input(synth_page(1024, 768, 0))
+    _check(engines("separator").forward(x)[0], oracles("separator").run(x)[0], "separator 1024x768")
+
+
+def test_benchmark_size_properties(engines):
+    """BASELINE config 3 shape (1856x1344): batch independence and determinism at full size."""
+    from aru_b200.synth import synth_page, page_to_net_input
+    eng = engines("separator")
+    xs = np.stack([page_to_net_input(synth_page(1856, 1344, s)) for s in range(3)]).astype(np.float32)
+    a = eng.forward(xs).copy()
+    b = eng.forward(xs[::-1].copy())
+    assert np.array_equal(a, b[::-1])             # page order does not matter
+    assert np.isfinite(a).all() and 0.0 <= a.min() and a.max() <= 1.0
+    np.testing.assert_allclose(a.sum(-1), 1.0, atol=1e-5)   # softmax over classes
+    frac = float(_mask(a).mean())
+    assert 0.001 < frac < 0.5, frac
