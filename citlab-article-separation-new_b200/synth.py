@@ -42,6 +42,8 @@ def synth_page(h: int, w: int, seed: int = 0) -> np.ndarray:
     """uint8 [h, w] newspaper-like page."""
     rng = np.random.default_rng(seed)
     img = np.clip(rng.normal(225.0, 6.0, size=(h, w)), 0, 255)
+    if min(h, w) < 8:                                       # too small for a layout: noise only
+        return img.astype(np.uint8)
     n_cols = int(rng.integers(2, 6))
     margin = max(1, min(max(4, w // 40), (min(h, w) - 1) // 2))
     n_cols = max(1, min(n_cols, (w - margin) // (margin + 8)))
