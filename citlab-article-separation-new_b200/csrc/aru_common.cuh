@@ -57,9 +57,10 @@ inline Geo make_geo(int N, int H, int W) {
   Geo g;
   g.N = N; g.H = H; g.W = W;
   g.Wp = W + 2; g.Hp = H + 2;
-  g.lead = ((long long)(g.Wp + 1 + 128 + 127) / 128) * 128;
+  // margins: conv_tc loads whole 512-position units around the first / last in-image position
+  g.lead = ((long long)(g.Wp + 1 + 1024 + 127) / 128) * 128;
   long long body = (long long)N * g.Hp * g.Wp;
-  g.plane = ((g.lead + body + 2LL * g.Wp + 640 + 127) / 128) * 128;
+  g.plane = ((g.lead + body + 2LL * g.Wp + 1280 + 127) / 128) * 128;
   return g;
 }
 

@@ -4,23 +4,28 @@
 // flattened padded chunk-planar layout of aru_common.cuh.  In that layout the convolution is a 1-D
 // correlation over positions:  out[p] = sum_{tap} W[tap] . in[p + off(tap)],  off = (ky-1)*Wp + (kx-1).
 //
-// GEMM view per tile:  D[128 positions, N=C_out] = sum over K-steps of A[128, 16] * B[16, N]
+// GEMM view per 128-position tile:  D[128, N=C_out] = sum over K-steps of A[128, 16] * B[16, N]
 //   * A (activations): for tap t and channel chunks (2c, 2c+1) the 128 x 16 operand is two contiguous
 //     runs of 128 x 16 B in shared memory -> canonical no-swizzle K-major core matrices,
 //     SBO = 128 B (next 8 positions), LBO = ring plane stride (next 8 channels).  For C_in = 8 two
 //     horizontally adjacent taps form one K=16 step (LBO = 16 B: the same run shifted by one position).
-//   * B (weights): pre-packed on the host into the exact shared-memory image, resident for the whole
-//     kernel (weight-stationary persistent CTAs).
-//   * D: fp32 in TMEM, n_stages accumulator stages so the epilogue of tile i overlaps the MMAs of i+1..
+//   * B (weights): pre-packed on the host into the exact shared-memory image.  Resident for the whole
+//     kernel when it fits (weight-stationary persistent CTAs), otherwise streamed per pass in groups of
+//     K-steps through a small ring (C >= 128 layers).
+//   * D: fp32 in TMEM; a *pass* is T consecutive tiles (T x N columns per accumulator stage), and there
+//     are 2 or 4 stages so the epilogue of pass i overlaps the MMAs of pass i+1.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over a contiguous range of tiles):
-//   warp 0 lane 0 : producer - streams the input as 2 KB bulk copies (TMA engine, cp.async.bulk) into a
-//                   ring of 128-position slots; slot 0 is mirrored behind the ring so that every
-//                   128(+1)-position operand run is contiguous even when it wraps
-//   warp 1 lane 0 : MMA issuer - tcgen05.mma.cta_group::1.kind::f16, commits free ring slots / publish D
+// Warp roles (384 threads, 1 CTA / SM, persistent over a contiguous range of passes):
+//   warp 0 lane 0 : producer - streams the input as bulk copies (TMA engine, cp.async.bulk) of one *unit*
+//                   (128*T positions x all input chunks) into a ring; the head of the ring is mirrored
+//                   behind its end so that every 128(+1)-position operand run is contiguous even when it
+//                   wraps.  Read amplification is ~1: every position is fetched once per CTA.
+//   warp 1 lane 0 : MMA issuer - tcgen05.mma.cta_group::1.kind::f16 from precomputed descriptor tables;
+//                   tcgen05.commit frees ring units / weight stages and publishes accumulators
 //   warp 2        : TMEM allocator
-//   warps 4..11   : two epilogue warpgroups (alternating tiles): tcgen05.ld -> +bias (+res) -> act ->
-//                   16-bit pack -> 16 B coalesced global stores (in-image positions only)
+//   warps 4..11   : two epilogue warpgroups (alternating passes): tcgen05.ld -> +bias (+res) -> act ->
+//                   16-bit pack -> 16 B coalesced global stores (in-image positions only; the zero frame of
+//                   the output tensor is never written)
 // All mbarrier waits are bounded: a protocol bug sets *err_flag and drains instead of hanging the GPU.
 #include <cstring>
 #include <vector>
@@ -34,18 +39,22 @@ namespace {
 
 constexpr int TILE = 128;
 constexpr int NUM_THREADS = 384;
-constexpr int MAX_SLOTS = 128;
+constexpr int MAX_UNITS = 96;
 constexpr int MAX_STEPS = 256;
-constexpr int PREFETCH_SLOTS = 3;
+constexpr int MIRROR = 136;          // positions mirrored behind the ring (129 needed, rounded up)
+constexpr int PREFETCH_UNITS = 2;
+constexpr int MAX_WSTAGES = 4;
 // shared-memory header layout (bytes)
-constexpr int OFF_FULL = 0;                       // uint64 full[MAX_SLOTS]
-constexpr int OFF_EMPTY = OFF_FULL + 8 * MAX_SLOTS;
-constexpr int OFF_TFULL = OFF_EMPTY + 8 * MAX_SLOTS;  // uint64 tmem_full[4]
-constexpr int OFF_TEMPTY = OFF_TFULL + 32;            // uint64 tmem_empty[4]
-constexpr int OFF_TMEMPTR = OFF_TEMPTY + 32;          // uint32 tmem base, uint32 abort flag
-constexpr int OFF_STEPOFF = OFF_TMEMPTR + 16;         // int step_off[MAX_STEPS]
-constexpr int OFF_STEPCH = OFF_STEPOFF + 4 * MAX_STEPS;  // int step_chunk[MAX_STEPS]
-constexpr int OFF_BIAS = OFF_STEPCH + 4 * MAX_STEPS;     // float bias[256]
+constexpr int OFF_FULL = 0;                                // uint64 full[MAX_UNITS]
+constexpr int OFF_EMPTY = OFF_FULL + 8 * MAX_UNITS;        // uint64 empty[MAX_UNITS]
+constexpr int OFF_TFULL = OFF_EMPTY + 8 * MAX_UNITS;       // uint64 tmem_full[4]
+constexpr int OFF_TEMPTY = OFF_TFULL + 32;                 // uint64 tmem_empty[4]
+constexpr int OFF_WFULL = OFF_TEMPTY + 32;                 // uint64 w_full[4]
+constexpr int OFF_WEMPTY = OFF_WFULL + 32;                 // uint64 w_empty[4]
+constexpr int OFF_TMEMPTR = OFF_WEMPTY + 32;               // uint32 tmem base, uint32 abort flag
+constexpr int OFF_STEPTAB = OFF_TMEMPTR + 16;              // int2 {A desc lo constant, window offset}[MAX_STEPS]
+constexpr int OFF_BTAB = OFF_STEPTAB + 8 * MAX_STEPS;      // uint32 B desc lo [MAX_STEPS]
+constexpr int OFF_BIAS = OFF_BTAB + 4 * MAX_STEPS;         // float bias[256]
 constexpr int HDR_BYTES = ((OFF_BIAS + 4 * 256 + 127) / 128) * 128;
 
 struct ConvTcArgs {
@@ -59,11 +68,14 @@ struct ConvTcArgs {
   long long res_plane;
   const act_t* wpack;
   const float* bias;
-  int ks, cin_chunks, cout_chunks, npad, n_steps, n_slots, n_stages, tmem_cols;
-  int N, H, W, Wp, Hp;
-  int lead;
-  int tile_begin, tile_end;
-  int dlo, dhi;
+  int ks, cin_chunks, cout_chunks, npad, n_steps;
+  int n_units, n_stages, tmem_cols;
+  int w_stream, w_group, n_wst;   // weight streaming: steps per group, stages
+  int W, H, Wp, Hp;
+  int lead, body_end, rel_bias;
+  int pass_begin, pass_end;
+  int dlo, dhi, min_off;
+  int dc128, dr128, dcT, drT;     // (col,row) advance of 128 and 128*T positions
   int act;
   int* err_flag;
 };
@@ -144,56 +156,73 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// shared-memory matrix descriptor, no swizzle, K-major: start / LBO / SBO in 16-byte units, version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+// High word of a shared-memory matrix descriptor (no swizzle, K-major): SBO in 16-byte units at bits 32..45,
+// descriptor version 1 (sm_100) at bits 46..47.  Low word = start address >> 4 | (LBO >> 4) << 16.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+__device__ __forceinline__ void walk_adv(int& col, int& rin, int dc, int dr, int Wp, int Hp) {
+  col += dc;
+  rin += dr;
+  if (col >= Wp) { col -= Wp; ++rin; }
+  if (rin >= Hp) {
+    rin -= Hp;
+    if (rin >= Hp) rin %= Hp;
+  }
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
+template <int T>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
+  // a previous launch hit a protocol timeout: do nothing (the host reports the error after the pass)
+  if (*reinterpret_cast<volatile int*>(a.err_flag) != 0) return;
+
+  constexpr int UNIT = TILE * T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_full = s_base + OFF_FULL, s_empty = s_base + OFF_EMPTY;
   const uint32_t s_tfull = s_base + OFF_TFULL, s_tempty = s_base + OFF_TEMPTY;
+  const uint32_t s_wfull = s_base + OFF_WFULL, s_wempty = s_base + OFF_WEMPTY;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
   volatile uint32_t* abort_smem = tmem_ptr + 1;
-  int* step_off = reinterpret_cast<int*>(smem + OFF_STEPOFF);
-  int* step_chunk = reinterpret_cast<int*>(smem + OFF_STEPCH);
+  int2* step_tab = reinterpret_cast<int2*>(smem + OFF_STEPTAB);
+  uint32_t* b_tab = reinterpret_cast<uint32_t*>(smem + OFF_BTAB);
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
-  const int wbytes = a.n_steps * 32 * a.npad;
+  const int step_bytes = 32 * a.npad;
+  const int w_smem_bytes = a.w_stream ? a.n_wst * a.w_group * step_bytes : a.n_steps * step_bytes;
   const uint32_t s_w = s_base + HDR_BYTES;
-  const uint32_t s_ring = s_w + ((wbytes + 127) / 128) * 128;
-  const int L = a.n_slots * TILE;        // ring length in positions
-  const int ring_plane = L + TILE;       // + mirror of slot 0
+  const uint32_t s_ring = s_w + ((w_smem_bytes + 127) / 128) * 128;
+  const int L = a.n_units * UNIT;        // ring length in positions
+  const int ring_plane = L + MIRROR;
 
-  // static partition of the tile range over the persistent CTAs
-  const int total_tiles = a.tile_end - a.tile_begin;
-  const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int t0 = a.tile_begin + (int)blockIdx.x * per_cta;
-  const int t1 = min(t0 + per_cta, a.tile_end);
-  const int n_tiles = max(t1 - t0, 0);
-  const int win = a.dhi - a.dlo + 1;     // chunks a tile reads
-
-  // a previous launch hit a protocol timeout: do nothing (the host reports the error after the pass)
-  if (*reinterpret_cast<volatile int*>(a.err_flag) != 0) return;
+  // static partition of the pass range over the persistent CTAs
+  const int total = a.pass_end - a.pass_begin;
+  const int per_cta = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int u0 = a.pass_begin + (int)blockIdx.x * per_cta;
+  const int n_pass = max(min(u0 + per_cta, a.pass_end) - u0, 0);
+  const int win = a.dhi - a.dlo + 1;     // units a pass reads
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     *abort_smem = 0;
-    for (int i = 0; i < a.n_slots; ++i) {
+    for (int i = 0; i < a.n_units; ++i) {
       mbar_init(s_full + 8 * i, 1);
       mbar_init(s_empty + 8 * i, 1);
     }
-    for (int i = 0; i < a.n_stages; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(s_tfull + 8 * i, 1);
       mbar_init(s_tempty + 8 * i, 4);
+      mbar_init(s_wfull + 8 * i, 1);
+      mbar_init(s_wempty + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  {  // K-step table: offset (positions) and first channel chunk of each step
+  {
+    // K-step tables: A descriptor constant + offset inside the pass window, B descriptor
     const int PB = (a.ks - 1) / 2;
+    const uint32_t a_lbo = a.cin_chunks == 1 ? 16u : (uint32_t)ring_plane * 16u;
+    const uint32_t b_lbo = (uint32_t)a.npad * 16u;
     for (int s = threadIdx.x; s < a.n_steps; s += NUM_THREADS) {
       int off, ch;
       if (a.cin_chunks == 1) {
@@ -207,15 +236,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
         off = (tap / a.ks - PB) * a.Wp + (tap % a.ks - PB);
         ch = 2 * (s % cp);
       }
-      step_off[s] = off;
-      step_chunk[s] = ch;
+      step_tab[s] = make_int2((int)(((s_ring >> 4) + (uint32_t)(ch * ring_plane)) | ((a_lbo >> 4) << 16)), off - a.min_off);
+      const int s_in = a.w_stream ? (s % a.w_group) : s;
+      b_tab[s] = ((s_w + (uint32_t)(s_in * step_bytes)) >> 4) | ((b_lbo >> 4) << 16);
     }
     for (int i = threadIdx.x; i < a.npad; i += NUM_THREADS) s_bias[i] = a.bias[i];
-    // resident B image
-    const uint4* wsrc = reinterpret_cast<const uint4*>(a.wpack);
-    uint4* wdst = reinterpret_cast<uint4*>(smem + HDR_BYTES);
-    for (int i = threadIdx.x; i < wbytes / 16; i += NUM_THREADS) wdst[i] = __ldg(wsrc + i);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA) reads
+    if (!a.w_stream) {  // resident B image
+      const uint4* wsrc = reinterpret_cast<const uint4*>(a.wpack);
+      uint4* wdst = reinterpret_cast<uint4*>(smem + HDR_BYTES);
+      for (int i = threadIdx.x; i < w_smem_bytes / 16; i += NUM_THREADS) wdst[i] = __ldg(wsrc + i);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA) reads
+    }
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr)),
@@ -227,115 +258,188 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int n_groups = a.w_stream ? (a.n_steps + a.w_group - 1) / a.w_group : 0;
 
-  if (n_tiles > 0) {
+  if (n_pass > 0) {
     if (warp == 0 && lane == 0) {
       // ================= producer =================
-      const int n_chunks = n_tiles + win - 1;
-      const long long first_pos = (long long)(t0 + a.dlo) * TILE;  // ring origin in plane positions
-      const uint32_t tx = (uint32_t)a.cin_chunks * TILE * 16;
-      for (int k = 0; k < n_chunks; ++k) {
-        const int slot = k % a.n_slots, use = k / a.n_slots;
-        if (!mbar_wait(s_empty + 8 * slot, (use & 1) ^ 1, abort_smem, a.err_flag, 1)) break;
+      const int n_load = n_pass + win - 1;
+      const long long first_pos = (long long)(u0 + a.dlo) * UNIT;  // ring origin in plane positions
+      const uint32_t tx = (uint32_t)a.cin_chunks * UNIT * 16;
+      const uint32_t tx_mirror = (uint32_t)a.cin_chunks * MIRROR * 16;
+      bool alive = true;
+      auto load_unit = [&](int k) {
+        const int slot = k % a.n_units, use = k / a.n_units;
+        if (!mbar_wait(s_empty + 8 * slot, (use & 1) ^ 1, abort_smem, a.err_flag, 1)) { alive = false; return; }
         const uint32_t bar = s_full + 8 * slot;
-        mbar_expect_tx(bar, slot == 0 ? 2 * tx : tx);
-        const act_t* src = a.in + (first_pos + (long long)k * TILE) * 8;
+        mbar_expect_tx(bar, slot == 0 ? tx + tx_mirror : tx);
+        const act_t* src = a.in + (first_pos + (long long)k * UNIT) * 8;
         for (int c = 0; c < a.cin_chunks; ++c) {
-          const uint32_t dst = s_ring + (uint32_t)(c * ring_plane + slot * TILE) * 16;
-          bulk_g2s(dst, src + c * a.in_plane * 8, TILE * 16, bar);
-          if (slot == 0) bulk_g2s(dst + (uint32_t)L * 16, src + c * a.in_plane * 8, TILE * 16, bar);
+          const uint32_t dst = s_ring + (uint32_t)(c * ring_plane + slot * UNIT) * 16;
+          bulk_g2s(dst, src + c * a.in_plane * 8, UNIT * 16, bar);
+          if (slot == 0) bulk_g2s(dst + (uint32_t)L * 16, src + c * a.in_plane * 8, MIRROR * 16, bar);
+        }
+      };
+      if (!a.w_stream) {
+        for (int k = 0; k < n_load && alive; ++k) load_unit(k);
+      } else {
+        // consumption order: window of pass 0 (+ prefetch), then per pass its weight groups and one more unit
+        int next = 0;
+        for (; next < min(n_load, a.n_units - 1) && alive; ++next) load_unit(next);
+        int wk = 0;  // running weight-group counter
+        for (int pi = 0; pi < n_pass && alive; ++pi) {
+          for (int g = 0; g < n_groups && alive; ++g, ++wk) {
+            const int ws = wk % a.n_wst, use = wk / a.n_wst;
+            if (!mbar_wait(s_wempty + 8 * ws, (use & 1) ^ 1, abort_smem, a.err_flag, 5)) { alive = false; break; }
+            const int steps = min(a.w_group, a.n_steps - g * a.w_group);
+            const uint32_t bytes = (uint32_t)(steps * step_bytes);
+            mbar_expect_tx(s_wfull + 8 * ws, bytes);
+            bulk_g2s(s_w + (uint32_t)(ws * a.w_group * step_bytes),
+                     reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)g * a.w_group * step_bytes, bytes, s_wfull + 8 * ws);
+          }
+          if (next < n_load && alive) load_unit(next++);
         }
       }
     } else if (warp == 1 && lane == 0) {
       // ================= MMA issuer =================
       const uint32_t idesc = (1u << 4) | (ARU_UMMA_FMT << 7) | (ARU_UMMA_FMT << 10) | ((uint32_t)(a.npad >> 3) << 17) |
                              ((uint32_t)(TILE >> 4) << 24);
-      const uint32_t a_lbo = a.cin_chunks == 1 ? 16u : (uint32_t)ring_plane * 16u;
-      const uint32_t b_lbo = (uint32_t)a.npad * 16u;
-      int tile_ring = (-a.dlo * TILE) % L;  // ring position of the tile's own position 0
+      const uint32_t hi = desc_hi(128);
+      const uint32_t uL = (uint32_t)L;
+      uint32_t ws = (uint32_t)(((-a.dlo) * UNIT + a.min_off) % L);  // ring position of the pass window start
+      const uint32_t wstage_units = (uint32_t)(a.w_group * step_bytes) >> 4;
+      int wk = 0;
       bool alive = true;
-      for (int ti = 0; ti < n_tiles && alive; ++ti) {
-        const int stage = ti % a.n_stages;
-        alive = mbar_wait(s_tempty + 8 * stage, ((ti / a.n_stages) & 1) ^ 1, abort_smem, a.err_flag, 2);
-        if (!alive) break;
-        // operands: tile ti reads chunks ti .. ti+win-1 (the first tile waits for its whole window)
-        for (int k = (ti == 0 ? 0 : ti + win - 1); k <= ti + win - 1; ++k) {
-          alive = mbar_wait(s_full + 8 * (k % a.n_slots), (k / a.n_slots) & 1, abort_smem, a.err_flag, 3);
-          if (!alive) break;
-        }
+      for (int pi = 0; pi < n_pass && alive; ++pi) {
+        const int stage = pi % a.n_stages;
+        alive = mbar_wait(s_tempty + 8 * stage, ((pi / a.n_stages) & 1) ^ 1, abort_smem, a.err_flag, 2);
+        // operands: pass pi reads units pi .. pi+win-1 (the first pass waits for its whole window)
+        for (int k = (pi == 0 ? 0 : pi + win - 1); k <= pi + win - 1 && alive; ++k)
+          alive = mbar_wait(s_full + 8 * (k % a.n_units), (k / a.n_units) & 1, abort_smem, a.err_flag, 3);
         if (!alive) break;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(stage * a.npad);
-        for (int s = 0; s < a.n_steps; ++s) {
-          int rp = tile_ring + step_off[s];
-          rp += (rp < 0) ? L : 0;
-          rp -= (rp >= L) ? L : 0;
-          const uint32_t a_addr = s_ring + (uint32_t)(step_chunk[s] * ring_plane + rp) * 16u;
-          const uint32_t b_addr = s_w + (uint32_t)s * 32u * (uint32_t)a.npad;
-          umma_f16(d_tmem, make_desc(a_addr, a_lbo, 128), make_desc(b_addr, b_lbo, 128), idesc, s > 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(stage * T * a.npad);
+        if (!a.w_stream) {
+#pragma unroll 2
+          for (int s = 0; s < a.n_steps; ++s) {
+            const int2 e = step_tab[s];
+            const uint64_t bdesc = desc64(hi, b_tab[s]);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              uint32_t pos = ws + (uint32_t)e.y + (uint32_t)(t * TILE);
+              pos = min(pos, pos - uL);  // wrap (unsigned): pos < 2L
+              umma_f16(d_tmem + (uint32_t)(t * a.npad), desc64(hi, (uint32_t)e.x + pos), bdesc, idesc, s > 0 ? 1u : 0u);
+            }
+          }
+        } else {
+          for (int g = 0, s = 0; g < n_groups && alive; ++g, ++wk) {
+            const int wst = wk % a.n_wst;
+            alive = mbar_wait(s_wfull + 8 * wst, (wk / a.n_wst) & 1, abort_smem, a.err_flag, 6);
+            if (!alive) break;
+            tc_fence_after();
+            const int s_end = min(s + a.w_group, a.n_steps);
+            for (; s < s_end; ++s) {
+              const int2 e = step_tab[s];
+              const uint64_t bdesc = desc64(hi, b_tab[s] + (uint32_t)wst * wstage_units);
+#pragma unroll
+              for (int t = 0; t < T; ++t) {
+                uint32_t pos = ws + (uint32_t)e.y + (uint32_t)(t * TILE);
+                pos = min(pos, pos - uL);
+                umma_f16(d_tmem + (uint32_t)(t * a.npad), desc64(hi, (uint32_t)e.x + pos), bdesc, idesc, s > 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(s_wempty + 8 * wst);  // weight stage may be refilled once these MMAs retire
+          }
+          if (!alive) break;
         }
-        umma_commit(s_empty + 8 * (ti % a.n_slots));  // chunk ti is not needed by later tiles
-        umma_commit(s_tfull + 8 * stage);             // accumulator ready for the epilogue
-        tile_ring += TILE;
-        tile_ring -= (tile_ring >= L) ? L : 0;
+        umma_commit(s_empty + 8 * (pi % a.n_units));  // unit pi is not needed by later passes
+        umma_commit(s_tfull + 8 * stage);             // accumulators ready for the epilogue
+        ws += UNIT;
+        ws -= (ws >= uL) ? uL : 0u;
       }
     } else if (warp >= 4) {
       // ================= epilogue =================
-      const int wg = (warp - 4) >> 2;  // warpgroup 0/1 -> even/odd tiles
+      const int wg = (warp - 4) >> 2;  // warpgroup 0/1 -> even/odd passes
       const int q = warp & 3;          // TMEM lane quarter this warp may access
       const int m = q * 32 + lane;
-      const int body_rows = a.N * a.Hp;
+      // (col, rin) of this lane's position in tile 0 of its first pass; rel_bias makes the numerator non-negative
+      int p = (u0 + wg) * UNIT + m;
+      int col, rin;
+      {
+        const int rel = p - a.lead + a.rel_bias;
+        const int row = rel / a.Wp;
+        col = rel - row * a.Wp;
+        rin = row % a.Hp;
+      }
       bool alive = true;
-      for (int ti = wg; ti < n_tiles && alive; ti += 2) {
-        const int stage = ti % a.n_stages;
-        const int p = (t0 + ti) * TILE + m;
-        const int rel = p - a.lead;
-        bool valid = false;
-        if (rel >= 0) {
-          const int row = rel / a.Wp, col = rel - row * a.Wp;
-          const int rin = row % a.Hp;
-          valid = (col >= 1) && (col <= a.W) && (rin >= 1) && (rin <= a.H) && (row < body_rows);
+      for (int pi = wg; pi < n_pass && alive; pi += 2) {
+        const int stage = pi % a.n_stages;
+        uint4 res0[T];
+        bool valid[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) res0[t] = make_uint4(0, 0, 0, 0);
+        {  // validity of the T positions of this pass + early residual fetch (chunk 0)
+          int c2 = col, r2 = rin;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int pt = p + t * TILE;
+            valid[t] = (c2 >= 1) && (c2 <= a.W) && (r2 >= 1) && (r2 <= a.H) && (pt >= a.lead) && (pt < a.body_end);
+            if (a.res && valid[t]) res0[t] = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)pt * 8));
+            walk_adv(c2, r2, a.dc128, a.dr128, a.Wp, a.Hp);
+          }
+          col = c2; rin = r2;                                // now at tile 0 of the next pass (other warpgroup's)
+          walk_adv(col, rin, a.dcT, a.drT, a.Wp, a.Hp);      // skip it
         }
-        alive = mbar_wait(s_tfull + 8 * stage, (ti / a.n_stages) & 1, abort_smem, a.err_flag, 4);
+        alive = mbar_wait(s_tfull + 8 * stage, (pi / a.n_stages) & 1, abort_smem, a.err_flag, 4);
         alive = __shfl_sync(0xffffffffu, alive ? 1 : 0, 0) != 0;
         if (!alive) break;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * a.npad);
-        for (int c0 = 0; c0 < a.cout_chunks; c0 += 2) {
-          uint32_t v0[8], v1[8];
-          const bool two = (c0 + 1 < a.cout_chunks);
-          tmem_ld8(taddr + c0 * 8, v0);
-          if (two) tmem_ld8(taddr + c0 * 8 + 8, v1);
-          tmem_ld_wait();
-          if (c0 + 2 >= a.cout_chunks) {  // last TMEM read of this stage: hand the accumulator back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
-          }
-          if (valid) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (h == 1 && !two) break;
-              const int c = c0 + h;
-              float acc[8];
+        for (int t = 0; t < T; ++t) {
+          const int pt = p + t * TILE;
+          for (int c0 = 0; c0 < a.cout_chunks; c0 += 2) {
+            uint32_t v0[8], v1[8];
+            const bool two = (c0 + 1 < a.cout_chunks);
+            tmem_ld8(taddr + t * a.npad + c0 * 8, v0);
+            if (two) tmem_ld8(taddr + t * a.npad + c0 * 8 + 8, v1);
+            uint4 r0 = res0[t], r1 = make_uint4(0, 0, 0, 0);
+            if (a.res && valid[t]) {
+              if (c0 > 0) r0 = __ldg(reinterpret_cast<const uint4*>(a.res + ((long long)c0 * a.res_plane + pt) * 8));
+              if (two) r1 = __ldg(reinterpret_cast<const uint4*>(a.res + ((long long)(c0 + 1) * a.res_plane + pt) * 8));
+            }
+            tmem_ld_wait();
+            if (t == T - 1 && c0 + 2 >= a.cout_chunks) {  // last TMEM read of this stage: hand the accumulators back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
+            }
+            if (valid[t]) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(h ? v1[j] : v0[j]) + s_bias[c * 8 + j];
-              if (a.res) {
-                float r[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(a.res + ((long long)c * a.res_plane + p) * 8)), r);
+              for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !two) break;
+                const int c = c0 + h;
+                float acc[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += r[j];
+                for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(h ? v1[j] : v0[j]) + s_bias[c * 8 + j];
+                if (a.res) {
+                  float r[8];
+                  unpack8(h ? r1 : r0, r);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[j] += r[j];
+                }
+                if (a.out_pre)
+                  *reinterpret_cast<uint4*>(a.out_pre + ((long long)c * a.pre_plane + pt) * 8) = pack8(acc);
+                if (a.act == 1) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+                }
+                *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + pt) * 8) = pack8(acc);
               }
-              if (a.out_pre)
-                *reinterpret_cast<uint4*>(a.out_pre + ((long long)c * a.pre_plane + p) * 8) = pack8(acc);
-              if (a.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-              }
-              *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + p) * 8) = pack8(acc);
             }
           }
         }
+        p += 2 * UNIT;
       }
     }
   }
@@ -348,6 +452,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
                  : "memory");
   }
+}
+
+struct Window {
+  int min_off, max_off, dlo, dhi, win;
+};
+
+Window make_window(int ks, int cin_chunks, int Wp, int unit) {
+  Window w;
+  const int PB = (ks - 1) / 2;
+  w.min_off = -PB * (Wp + 1);
+  w.max_off = (ks - 1 - PB) * (Wp + 1);
+  if (cin_chunks == 1) w.max_off += 1;  // paired taps read one position further
+  w.dlo = -cdiv(-w.min_off, unit);
+  w.dhi = (unit - 1 + w.max_off) / unit;
+  w.win = w.dhi - w.dlo + 1;
+  return w;
 }
 
 }  // namespace
@@ -380,36 +500,51 @@ ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, si
   if (p.cin_chunks != 1 && (p.cin_chunks & 1)) { p.why = "odd number of input chunks"; return p; }
   if (p.npad > 256) { p.why = "C_out > 256"; return p; }
   if (g.plane >= (1LL << 31) / 16) { p.why = "plane too large for 32-bit positions"; return p; }
-  const int PB = (ks - 1) / 2;
-  const int min_off = -PB * (g.Wp + 1);
-  int max_off = (ks - 1 - PB) * (g.Wp + 1);
-  if (p.cin_chunks == 1) max_off += 1;  // paired taps read one position further
-  const int dlo = -cdiv(-min_off, TILE);
-  const int dhi = (TILE - 1 + max_off) / TILE;
-  const int win = dhi - dlo + 1;
-  p.n_slots = win + PREFETCH_SLOTS;
-  if (p.n_slots > MAX_SLOTS) { p.why = "row pitch too large for the operand ring"; return p; }
   p.n_steps = p.cin_chunks == 1 ? ks * ((ks + 1) / 2) : ks * ks * (p.cin_chunks / 2);
   if (p.n_steps > MAX_STEPS) { p.why = "too many K steps"; return p; }
-  p.n_stages = p.npad <= 64 ? 4 : 2;
   p.wpack_bytes = (size_t)p.n_steps * 32 * p.npad;
-  const size_t ring = (size_t)p.cin_chunks * (p.n_slots * TILE + TILE) * 16;
-  p.smem_bytes = HDR_BYTES + ((p.wpack_bytes + 127) / 128) * 128 + ring;
-  if (p.smem_bytes > max_smem) { p.why = "weights + operand ring exceed shared memory"; return p; }
-  p.tile_begin = g.pos(0, 0, 0) / TILE;
-  p.tile_end = g.pos(g.N - 1, g.H - 1, g.W - 1) / TILE + 1;
-  const long long tiles = p.tile_end - p.tile_begin;
-  p.grid = (int)(tiles < num_sms ? tiles : num_sms);
-  p.ok = true;
+  const size_t w_resident = ((p.wpack_bytes + 127) / 128) * 128;
+  p.w_group = std::max(1, 16384 / (32 * p.npad));
+  p.n_wst = 3;
+  const size_t w_streamed = (((size_t)p.n_wst * p.w_group * 32 * p.npad) + 127) / 128 * 128;
+  p.why = "weights + operand ring exceed shared memory";
+  const int combos[3][2] = {{0, PREFETCH_UNITS}, {1, PREFETCH_UNITS}, {1, 1}};  // {stream weights, prefetch units}
+  for (int ci = 0; ci < 3 && !p.ok; ++ci) {
+    const int stream = combos[ci][0], pf = combos[ci][1];
+    for (int T = 4; T >= 1 && !p.ok; T >>= 1) {
+      if (T * p.npad * 2 > 512) continue;  // at least two accumulator stages
+      if (stream && T > 2) continue;
+      const Window w = make_window(ks, p.cin_chunks, g.Wp, TILE * T);
+      const int n_units = w.win + pf;
+      if (n_units > MAX_UNITS) continue;
+      const size_t ring = (size_t)p.cin_chunks * (n_units * TILE * T + MIRROR) * 16;
+      const size_t smem = HDR_BYTES + (stream ? w_streamed : w_resident) + ring;
+      if (smem > max_smem) continue;
+      p.ok = true;
+      p.T = T;
+      p.w_stream = stream;
+      p.n_slots = n_units;
+      p.smem_bytes = smem;
+      p.n_stages = (T * p.npad * 4 <= 512) ? 4 : 2;
+    }
+  }
+  if (!p.ok) return p;
+  p.why = "";
+  const long long unit = TILE * p.T;
+  p.tile_begin = g.pos(0, 0, 0) / unit;                          // in passes
+  p.tile_end = g.pos(g.N - 1, g.H - 1, g.W - 1) / unit + 1;
+  const long long passes = p.tile_end - p.tile_begin;
+  p.grid = (int)(passes < num_sms ? passes : num_sms);
   return p;
 }
 
-void conv_tc_pack_weights(const ConvTcPlan& p, const float* w, int cin, int cout, uint16_t* dst) {
+void conv_tc_pack_weights(const ConvTcPlan& p, const float* w, int cin, int cout, int ci_begin, uint16_t* dst) {
   const int ks = p.ks;
   memset(dst, 0, p.wpack_bytes);
   auto W = [&](int ky, int kx, int ci, int co) -> float {
-    if (kx >= ks || ci >= cin || co >= cout) return 0.f;
-    return w[(((size_t)ky * ks + kx) * cin + ci) * cout + co];
+    // ci is local to this K-part: channels [ci_begin, ci_begin + 8*cin_chunks) of the full filter
+    if (kx >= ks || ci >= p.cin_chunks * 8 || ci_begin + ci >= cin || co >= cout) return 0.f;
+    return w[(((size_t)ky * ks + kx) * cin + ci_begin + ci) * cout + co];
   };
   for (int s = 0; s < p.n_steps; ++s)
     for (int h = 0; h < 2; ++h)
@@ -438,28 +573,39 @@ cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& p, PV in, PV out, 
   a.res = res.p; a.res_plane = res.plane;
   a.wpack = wpack; a.bias = bias_pad;
   a.ks = p.ks; a.cin_chunks = p.cin_chunks; a.cout_chunks = p.cout_chunks; a.npad = p.npad;
-  a.n_steps = p.n_steps; a.n_slots = p.n_slots; a.n_stages = p.n_stages;
-  int cols = p.n_stages * p.npad;
+  a.n_steps = p.n_steps; a.n_units = p.n_slots; a.n_stages = p.n_stages;
+  a.w_stream = p.w_stream; a.w_group = p.w_group; a.n_wst = p.n_wst;
+  int cols = p.n_stages * p.T * p.npad;
   int pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   a.tmem_cols = pow2;
-  a.N = g.N; a.H = g.H; a.W = g.W; a.Wp = g.Wp; a.Hp = g.Hp; a.lead = (int)g.lead;
-  a.tile_begin = (int)p.tile_begin; a.tile_end = (int)p.tile_end;
-  const int PB = (p.ks - 1) / 2;
-  const int min_off = -PB * (g.Wp + 1);
-  int max_off = (p.ks - 1 - PB) * (g.Wp + 1);
-  if (p.cin_chunks == 1) max_off += 1;
-  a.dlo = -cdiv(-min_off, TILE);
-  a.dhi = (TILE - 1 + max_off) / TILE;
+  a.W = g.W; a.H = g.H; a.Wp = g.Wp; a.Hp = g.Hp;
+  a.lead = (int)g.lead;
+  a.body_end = (int)(g.lead + (long long)g.N * g.Hp * g.Wp);
+  const long long page = (long long)g.Wp * g.Hp;
+  a.rel_bias = (int)(((g.lead + page - 1) / page) * page);
+  a.pass_begin = (int)p.tile_begin; a.pass_end = (int)p.tile_end;
+  const int unit = TILE * p.T;
+  const Window w = make_window(p.ks, p.cin_chunks, g.Wp, unit);
+  a.dlo = w.dlo; a.dhi = w.dhi; a.min_off = w.min_off;
+  a.dc128 = TILE % g.Wp; a.dr128 = TILE / g.Wp;
+  a.dcT = unit % g.Wp; a.drT = unit / g.Wp;
   a.act = act;
   a.err_flag = err_flag;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_conv_tc<<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
+  if (p.T == 4)
+    k_conv_tc<4><<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
+  else if (p.T == 2)
+    k_conv_tc<2><<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
+  else
+    k_conv_tc<1><<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
   return cudaGetLastError();
 }
 

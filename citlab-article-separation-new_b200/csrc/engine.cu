@@ -29,11 +29,13 @@ enum BufKind { KIND_PLANAR = 0, KIND_F32 = 1, KIND_OUT = 2 };
 
 struct OpWeights {
   act_t* w16 = nullptr;     // direct conv / deconv pack [tap][cin_chunk][cout_chunk][8][8]
-  act_t* w_tc = nullptr;    // tcgen05 B image
+  // tcgen05 B images, keyed by (first input chunk, number of input chunks): the whole filter, or the
+  // K-parts of a split launch (built lazily at plan time)
+  struct TcImage { int ci_chunk_begin, ci_chunks; act_t* w; };
+  std::vector<TcImage> tc_images;
   float* w32 = nullptr;     // stem [tap][cpad] / small [tap][cin_pad][cout]
   float* bias = nullptr;    // zero-padded to a multiple of 16
   int cin = 0, cout = 0;
-  bool tc_shape_ok = false;
 };
 
 struct BufPlan {
@@ -46,10 +48,18 @@ struct BufPlan {
   size_t bytes = 0;
 };
 
+struct TcPart {
+  ConvTcPlan plan;
+  int ci_chunk_begin = 0, ci_chunks = 0;
+  const act_t* w = nullptr;
+};
+
 struct Plan {
   int n = 0, h = 0, w = 0;
   std::vector<BufPlan> bufs;
-  std::vector<ConvTcPlan> tc;        // per op (ok == false when the op does not use the tensor-core kernel)
+  std::vector<std::vector<TcPart>> tc;  // per op: K-parts of the tensor-core launch (empty: other kernel)
+  act_t* scratch = nullptr;             // partial sums of split-K launches
+  size_t scratch_bytes = 0;
   std::vector<const char*> kernel;   // per op label
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
@@ -79,6 +89,7 @@ struct aru_engine {
   int conv_path = 0, use_graph = 1, micro_batch = 0;
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   int* err_flag = nullptr;
+  float* zero_bias = nullptr;
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* cur = nullptr;
   uint64_t tick = 0;
@@ -165,17 +176,22 @@ int pack_op_weights(aru_engine* e, int oi) {
       }
   rc = upload(e, p, reinterpret_cast<uint16_t**>(&ow.w16));
   if (rc) return rc;
-  if (op.kind == ARU_OP_CONV) {
-    const Geo dummy = make_geo(1, 8, 8);
-    ConvTcPlan tp = conv_tc_plan(ks, cin, cout, dummy, e->num_sms, e->max_smem);
-    if (tp.ok) {
-      std::vector<uint16_t> img(tp.wpack_bytes / 2);
-      conv_tc_pack_weights(tp, w, cin, cout, img.data());
-      rc = upload(e, img, reinterpret_cast<uint16_t**>(&ow.w_tc));
-      if (rc) return rc;
-      ow.tc_shape_ok = true;
-    }
-  }
+  return ARU_OK;
+}
+
+// B image of input chunks [begin, begin+chunks) of op oi for the tensor-core kernel (cached per engine)
+int get_tc_image(aru_engine* e, int oi, const ConvTcPlan& tp, int begin, int chunks, const act_t** out) {
+  OpWeights& ow = e->opw[oi];
+  for (auto& im : ow.tc_images)
+    if (im.ci_chunk_begin == begin && im.ci_chunks == chunks) { *out = im.w; return ARU_OK; }
+  const aru_op& op = e->ops[oi];
+  std::vector<uint16_t> img(tp.wpack_bytes / 2);
+  conv_tc_pack_weights(tp, e->weights.data() + op.w_off, op.in.ch, op.out.ch, begin * 8, img.data());
+  uint16_t* dev = nullptr;
+  int rc = upload(e, img, &dev);
+  if (rc) return rc;
+  ow.tc_images.push_back({begin, chunks, reinterpret_cast<act_t*>(dev)});
+  *out = reinterpret_cast<act_t*>(dev);
   return ARU_OK;
 }
 
@@ -193,6 +209,7 @@ void free_plan(Plan* p) {
     if (p->ev_d2h[i]) cudaEventDestroy(p->ev_d2h[i]);
   }
   if (p->arena) cudaFree(p->arena);
+  if (p->scratch) cudaFree(p->scratch);
 }
 
 int set_dims(aru_engine* e, Plan* p, int buf, int h, int w, int op) {
@@ -241,10 +258,22 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
         label = "conv_small";
         err = launch_conv_small(st, op.ksize, op.out.ch, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), ow.w32,
                                 ow.bias, bi.geo, op.act);
-      } else if (p->tc[oi].ok) {
-        label = "conv_tc";
-        err = launch_conv_tc(st, p->tc[oi], make_pv(e, p, op.in), make_pv(e, p, op.out), make_pv(e, p, op.out_pre),
-                             make_pv(e, p, op.res), ow.w_tc, ow.bias, bo.geo, op.act, e->err_flag);
+      } else if (!p->tc[oi].empty()) {
+        // K-parts chain through the scratch buffer: part 0 adds the op's residual, the last part adds the
+        // bias, applies the activation and writes the real outputs
+        const auto& parts = p->tc[oi];
+        label = parts.size() == 1 ? (parts[0].plan.w_stream ? "conv_tc_ws" : "conv_tc") : "conv_tc_splitk";
+        PV scratch;
+        scratch.p = p->scratch; scratch.plane = bo.geo.plane; scratch.chunks = cdiv(op.out.ch, 8); scratch.C = op.out.ch;
+        for (size_t k = 0; k < parts.size() && err == cudaSuccess; ++k) {
+          const bool first = k == 0, last = k + 1 == parts.size();
+          PV in = make_pv(e, p, op.in);
+          in.p += (long long)parts[k].ci_chunk_begin * in.plane * 8;
+          in.chunks = parts[k].ci_chunks;
+          err = launch_conv_tc(st, parts[k].plan, in, last ? make_pv(e, p, op.out) : scratch,
+                               last ? make_pv(e, p, op.out_pre) : PV(), first ? make_pv(e, p, op.res) : scratch,
+                               parts[k].w, last ? ow.bias : e->zero_bias, bo.geo, last ? op.act : ARU_ACT_NONE, e->err_flag);
+        }
       } else {
         label = "conv_direct";
         err = launch_conv_direct(st, op.ksize, make_pv(e, p, op.in), make_pv(e, p, op.out), make_pv(e, p, op.out_pre),
@@ -444,9 +473,26 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     const aru_op& op = e->ops[i];
     if (op.kind != ARU_OP_CONV) continue;
     if (p->bufs[op.in.buf].kind != KIND_PLANAR || p->bufs[op.out.buf].kind != KIND_PLANAR) continue;
-    if (e->conv_path == 1 || !e->opw[i].tc_shape_ok) continue;
-    p->tc[i] = conv_tc_plan(op.ksize, op.in.ch, op.out.ch, p->bufs[op.out.buf].geo, e->num_sms, e->max_smem);
+    if (e->conv_path == 1) continue;
+    const Geo& geo = p->bufs[op.out.buf].geo;
+    const int cin_chunks = cdiv(op.in.ch, 8);
+    for (int parts = 1; parts <= 4 && p->tc[i].empty(); parts *= 2) {
+      if (cin_chunks % parts || (parts > 1 && (cin_chunks / parts) % 2)) break;
+      const int pc = cin_chunks / parts;
+      ConvTcPlan tp = conv_tc_plan(op.ksize, parts == 1 ? op.in.ch : pc * 8, op.out.ch, geo, e->num_sms, e->max_smem);
+      if (!tp.ok) continue;
+      for (int k = 0; k < parts; ++k) {
+        TcPart part;
+        part.plan = tp;
+        part.ci_chunk_begin = k * pc;
+        part.ci_chunks = pc;
+        if ((rc = get_tc_image(e, i, tp, part.ci_chunk_begin, pc, &part.w))) { free_plan(p.get()); return rc; }
+        p->tc[i].push_back(part);
+      }
+      if (parts > 1) p->scratch_bytes = std::max<size_t>(p->scratch_bytes, (size_t)cdiv(op.out.ch, 8) * (size_t)geo.plane * 16);
+    }
   }
+  if (p->scratch_bytes) CU(e, cudaMalloc((void**)&p->scratch, p->scratch_bytes));
   // one eager pass (sets function attributes, validates every launch), then capture
   rc = run_all(e, p.get(), 0, e->s_comp);
   if (rc) { free_plan(p.get()); return rc; }
@@ -461,6 +507,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   p->launches = no;
   for (int i = 0; i < no; ++i)
     if (e->ops[i].kind == ARU_OP_COPY) p->launches += cdiv(e->ops[i].in.ch, 8) - 1;
+    else if (p->tc[i].size() > 1) p->launches += (int)p->tc[i].size() - 1;
   if (e->use_graph) {
     for (int par = 0; par < 2; ++par) {
       cudaGraph_t g = nullptr;
@@ -660,6 +707,8 @@ int aru_create(const aru_graph_desc* g, int device, aru_engine** out) {
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaMalloc((void**)&e->err_flag, sizeof(int));
   if (err == cudaSuccess) err = cudaMemset(e->err_flag, 0, sizeof(int));
+  if (err == cudaSuccess) err = cudaMalloc((void**)&e->zero_bias, 256 * sizeof(float));
+  if (err == cudaSuccess) err = cudaMemset(e->zero_bias, 0, 256 * sizeof(float));
   if (err != cudaSuccess) return fail(nullptr, ARU_ECUDA, "stream / flag setup: %s", cudaGetErrorString(err));
   e->opw.resize(g->n_ops);
   for (int i = 0; i < g->n_ops; ++i) {
@@ -681,11 +730,12 @@ void aru_destroy(aru_engine* e) {
   for (auto& p : e->plans) free_plan(p.get());
   for (auto& w : e->opw) {
     if (w.w16) cudaFree(w.w16);
-    if (w.w_tc) cudaFree(w.w_tc);
+    for (auto& im : w.tc_images) cudaFree(im.w);
     if (w.w32) cudaFree(w.w32);
     if (w.bias) cudaFree(w.bias);
   }
   if (e->err_flag) cudaFree(e->err_flag);
+  if (e->zero_bias) cudaFree(e->zero_bias);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);

@@ -56,19 +56,24 @@ struct ConvTcPlan {
   int cout_chunks = 0;   // real output planes
   int npad = 0;          // UMMA N (multiple of 16)
   int n_steps = 0;       // K=16 MMA steps per tile
-  int n_slots = 0;       // ring slots (128 positions each)
+  int T = 1;             // 128-position tiles per pass
+  int n_slots = 0;       // ring units (128*T positions each)
   int n_stages = 0;      // TMEM accumulator stages
+  int w_stream = 0;      // 1: filters do not fit next to the operand ring and are streamed per pass
+  int w_group = 0;       // K-steps per streamed weight group
+  int n_wst = 0;         // weight ring stages
   int grid = 0;
   size_t smem_bytes = 0;
   size_t wpack_bytes = 0;  // packed B image (16-bit elements)
-  long long tile_begin = 0, tile_end = 0;
+  long long tile_begin = 0, tile_end = 0;  // pass range [begin, end) in units of 128*T positions
   const char* why = "";
 };
 
 // Decide whether / how the tcgen05 kernel runs conv (ks x ks, cin -> cout) on geometry g.
 ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, size_t max_smem);
-// Pack a TF-layout filter [ks][ks][cin][cout] (float32) into the kernel's shared-memory B image.
-void conv_tc_pack_weights(const ConvTcPlan& plan, const float* w_tf, int cin, int cout, uint16_t* dst);
+// Pack input channels [ci_begin, ci_begin + 8*plan.cin_chunks) of a TF-layout filter [ks][ks][cin][cout]
+// (float32) into the kernel's shared-memory B image.
+void conv_tc_pack_weights(const ConvTcPlan& plan, const float* w_tf, int cin, int cout, int ci_begin, uint16_t* dst);
 cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& plan, PV in, PV out, PV out_pre, PV res,
                            const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag);
 

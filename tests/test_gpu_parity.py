@@ -91,6 +91,7 @@ def test_golden_fixtures(engines, fixture, path, pname):
     ("separator", 128, 96),      # /32 in both dims
     ("separator", 150, 113),     # odd at every level (the CLI default 1500x1125, scaled down)
     ("separator", 257, 130),     # W+2 spans several 128-position tiles; odd H
+    ("separator", 40, 1250),     # wide page: the 128-channel layers take the split-K / weight-streaming launches
     ("heading", 90, 68),         # heading default height 900, scaled down
     ("ru", 77, 101),
     ("aru_s6a5", 129, 97),
@@ -175,10 +176,10 @@ def test_tensor_core_and_cuda_core_paths_agree(engines):
     eng.set_option(OPT_CONV_PATH, 0)
     a = eng.forward(x).copy()
     names = {k for _, k, _ in eng.profile_ops(1)}
-    assert "conv_tc" in names, names
+    assert any(k.startswith("conv_tc") for k in names), names
     eng.set_option(OPT_CONV_PATH, 1)
     b = eng.forward(x).copy()
-    assert "conv_tc" not in {k for _, k, _ in eng.profile_ops(1)}
+    assert not any(k.startswith("conv_tc") for _, k, _ in eng.profile_ops(1))
     eng.set_option(OPT_CONV_PATH, 0)
     assert np.abs(a - b).max() <= 5e-3          # same 16-bit operands, different fp32 summation order
 

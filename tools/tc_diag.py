@@ -47,7 +47,7 @@ def diag(net, h, w, n=1, max_report=4):
     bad = 0
     for op in eng.program.ops:
         k = vals[0]["kernels"].get(op.name)
-        if k != "conv_tc":
+        if not (k or "").startswith("conv_tc"):
             continue
         # the op's output node: find by view
         for node, v in eng.program.tensor_of_node.items():
@@ -67,6 +67,8 @@ def diag(net, h, w, n=1, max_report=4):
                         print(f"     rows {ys.min()}..{ys.max()} cols {xs.min()}..{xs.max()} chans {sorted(set(cs.tolist()))[:16]}")
                         print(f"     tc[0,:4,0]={a[0,:4,0]} direct={b[0,:4,0]}  tc nonfinite={np.isnan(a).sum()} tc zeros={np.mean(a==0):.3f} direct zeros={np.mean(b==0):.3f}")
                 break
+    from collections import Counter
+    print("  kernels:", dict(Counter(vals[0]["kernels"].values())))
     print(f"  conv_tc ops mismatching direct path: {bad}", flush=True)
     eng.close()
     return bad == 0
@@ -75,6 +77,6 @@ def diag(net, h, w, n=1, max_report=4):
 if __name__ == "__main__":
     ok = True
     for net, h, w, n in [("tiny", 32, 32, 1), ("tiny", 45, 39, 2), ("tiny", 20, 300, 1), ("separator", 128, 96, 1),
-                         ("separator", 150, 113, 2)]:
+                         ("separator", 150, 113, 2), ("separator", 40, 1250, 1), ("separator", 300, 420, 3)]:
         ok = diag(net, h, w, n) and ok
     print("TC_DIAG", "PASS" if ok else "FAIL")
