@@ -15,14 +15,17 @@
 //   * D: fp32 in TMEM; a *pass* is T consecutive tiles (T x N columns per accumulator stage), and there
 //     are 2 or 4 stages so the epilogue of pass i overlaps the MMAs of pass i+1.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over a contiguous range of passes):
-//   warp 0 lane 0 : producer - streams the input as bulk copies (TMA engine, cp.async.bulk) of one *unit*
+// Warp roles (416 threads, 1 CTA / SM, persistent over a contiguous range of passes):
+//   warp 12 lane 0: producer - streams the input as bulk copies (TMA engine, cp.async.bulk) of one *unit*
 //                   (128*T positions x all input chunks) into a ring; the head of the ring is mirrored
 //                   behind its end so that every 128(+1)-position operand run is contiguous even when it
 //                   wraps.  Read amplification is ~1: every position is fetched once per CTA.
-//   warp 1 lane 0 : MMA issuer - tcgen05.mma.cta_group::1.kind::f16 from precomputed descriptor tables;
-//                   tcgen05.commit frees ring units / weight stages and publishes accumulators
-//   warp 2        : TMEM allocator
+//                   (warp 12 also allocates / frees TMEM)
+//   warps 0..T-1  : MMA issuers (lane 0) - warp t issues tcgen05.mma.cta_group::1.kind::f16 for tile t of every
+//                   pass, on its own scheduler partition: with N = 16..64 an MMA is far cheaper than the
+//                   instruction sequence that launches it, so issue bandwidth, not the tensor pipe, is the
+//                   limit and it is spread over up to four warps.  tcgen05.commit (one per issuer) frees ring
+//                   units / weight stages and publishes accumulators
 //   warps 4..11   : two epilogue warpgroups (alternating passes): tcgen05.ld -> +bias (+res) -> act ->
 //                   16-bit pack -> 16 B coalesced global stores (in-image positions only; the zero frame of
 //                   the output tensor is never written)
@@ -38,7 +41,7 @@ namespace aru {
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 416;      // warps 0-3 MMA issuers, 4-11 epilogue, 12 producer / TMEM allocator
 constexpr int MAX_UNITS = 96;
 constexpr int MAX_STEPS = 256;
 constexpr int MIRROR = 136;          // positions mirrored behind the ring (129 needed, rounded up)
@@ -156,6 +159,19 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp (the same lane every time for a full mask).  Issuing the TMA / UMMA
+// instructions under this predicate from warp-uniform control flow lets the compiler keep descriptors
+// in uniform registers instead of emitting a per-lane "waterfall" loop around every instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // High word of a shared-memory matrix descriptor (no swizzle, K-major): SBO in 16-byte units at bits 32..45,
 // descriptor version 1 (sm_100) at bits 46..47.  Low word = start address >> 4 | (LBO >> 4) << 16.
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
@@ -186,8 +202,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
   const uint32_t s_wfull = s_base + OFF_WFULL, s_wempty = s_base + OFF_WEMPTY;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
   volatile uint32_t* abort_smem = tmem_ptr + 1;
-  int2* step_tab = reinterpret_cast<int2*>(smem + OFF_STEPTAB);
-  uint32_t* b_tab = reinterpret_cast<uint32_t*>(smem + OFF_BTAB);
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
   const int step_bytes = 32 * a.npad;
   const int w_smem_bytes = a.w_stream ? a.n_wst * a.w_group * step_bytes : a.n_steps * step_bytes;
@@ -208,38 +222,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
     *abort_smem = 0;
     for (int i = 0; i < a.n_units; ++i) {
       mbar_init(s_full + 8 * i, 1);
-      mbar_init(s_empty + 8 * i, 1);
+      mbar_init(s_empty + 8 * i, T);   // one tcgen05.commit per MMA issuer
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(s_tfull + 8 * i, 1);
+      mbar_init(s_tfull + 8 * i, T);
       mbar_init(s_tempty + 8 * i, 4);
       mbar_init(s_wfull + 8 * i, 1);
-      mbar_init(s_wempty + 8 * i, 1);
+      mbar_init(s_wempty + 8 * i, T);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
-    // K-step tables: A descriptor constant + offset inside the pass window, B descriptor
-    const int PB = (a.ks - 1) / 2;
-    const uint32_t a_lbo = a.cin_chunks == 1 ? 16u : (uint32_t)ring_plane * 16u;
-    const uint32_t b_lbo = (uint32_t)a.npad * 16u;
-    for (int s = threadIdx.x; s < a.n_steps; s += NUM_THREADS) {
-      int off, ch;
-      if (a.cin_chunks == 1) {
-        const int npairs = (a.ks + 1) / 2;
-        const int ky = s / npairs, pi = s % npairs;
-        off = (ky - PB) * a.Wp + (2 * pi - PB);
-        ch = 0;
-      } else {
-        const int cp = a.cin_chunks / 2;
-        const int tap = s / cp;
-        off = (tap / a.ks - PB) * a.Wp + (tap % a.ks - PB);
-        ch = 2 * (s % cp);
-      }
-      step_tab[s] = make_int2((int)(((s_ring >> 4) + (uint32_t)(ch * ring_plane)) | ((a_lbo >> 4) << 16)), off - a.min_off);
-      const int s_in = a.w_stream ? (s % a.w_group) : s;
-      b_tab[s] = ((s_w + (uint32_t)(s_in * step_bytes)) >> 4) | ((b_lbo >> 4) << 16);
-    }
     for (int i = threadIdx.x; i < a.npad; i += NUM_THREADS) s_bias[i] = a.bias[i];
     if (!a.w_stream) {  // resident B image
       const uint4* wsrc = reinterpret_cast<const uint4*>(a.wpack);
@@ -248,7 +241,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA) reads
     }
   }
-  if (warp == 2) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr)),
                  "r"((uint32_t)a.tmem_cols)
                  : "memory");
@@ -261,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
   const int n_groups = a.w_stream ? (a.n_steps + a.w_group - 1) / a.w_group : 0;
 
   if (n_pass > 0) {
-    if (warp == 0 && lane == 0) {
+    if (warp == 12 && lane == 0) {
       // ================= producer =================
       const int n_load = n_pass + win - 1;
       const long long first_pos = (long long)(u0 + a.dlo) * UNIT;  // ring origin in plane positions
@@ -272,8 +265,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
         const int slot = k % a.n_units, use = k / a.n_units;
         if (!mbar_wait(s_empty + 8 * slot, (use & 1) ^ 1, abort_smem, a.err_flag, 1)) { alive = false; return; }
         const uint32_t bar = s_full + 8 * slot;
-        mbar_expect_tx(bar, slot == 0 ? tx + tx_mirror : tx);
         const act_t* src = a.in + (first_pos + (long long)k * UNIT) * 8;
+        mbar_expect_tx(bar, slot == 0 ? tx + tx_mirror : tx);
         for (int c = 0; c < a.cin_chunks; ++c) {
           const uint32_t dst = s_ring + (uint32_t)(c * ring_plane + slot * UNIT) * 16;
           bulk_g2s(dst, src + c * a.in_plane * 8, UNIT * 16, bar);
@@ -300,64 +293,80 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
           if (next < n_load && alive) load_unit(next++);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ================= MMA issuer =================
+    } else if (warp < T && lane == 0) {
+      // ================= MMA issuers: warp t issues the MMAs of tile t of every pass =================
+      const int t = warp;
       const uint32_t idesc = (1u << 4) | (ARU_UMMA_FMT << 7) | (ARU_UMMA_FMT << 10) | ((uint32_t)(a.npad >> 3) << 17) |
                              ((uint32_t)(TILE >> 4) << 24);
       const uint32_t hi = desc_hi(128);
       const uint32_t uL = (uint32_t)L;
       uint32_t ws = (uint32_t)(((-a.dlo) * UNIT + a.min_off) % L);  // ring position of the pass window start
       const uint32_t wstage_units = (uint32_t)(a.w_group * step_bytes) >> 4;
+      const uint32_t step_units = (uint32_t)step_bytes >> 4;
+      const uint32_t a_lbo = a.cin_chunks == 1 ? 16u : (uint32_t)ring_plane * 16u;
+      const uint32_t a_lo0 = (s_ring >> 4) | ((a_lbo >> 4) << 16);
+      const uint32_t b_lo0 = (s_w >> 4) | ((((uint32_t)a.npad * 16u) >> 4) << 16);
+      // C_in = 8: horizontally adjacent taps are paired into one K=16 step (the B image holds zeros for
+      // the non-existent partner of the last tap of an odd-width kernel)
+      const int kx_step = a.cin_chunks == 1 ? 2 : 1;
+      const int kx_end = a.ks;
+      const int n_cp = a.cin_chunks == 1 ? 1 : a.cin_chunks / 2;
       int wk = 0;
       bool alive = true;
+      auto wait_u = [&](uint32_t bar, uint32_t parity, int code) -> bool {
+        return mbar_wait(bar, parity, abort_smem, a.err_flag, code);
+      };
       for (int pi = 0; pi < n_pass && alive; ++pi) {
         const int stage = pi % a.n_stages;
-        alive = mbar_wait(s_tempty + 8 * stage, ((pi / a.n_stages) & 1) ^ 1, abort_smem, a.err_flag, 2);
+        alive = wait_u(s_tempty + 8 * stage, ((pi / a.n_stages) & 1) ^ 1, 2);
         // operands: pass pi reads units pi .. pi+win-1 (the first pass waits for its whole window)
         for (int k = (pi == 0 ? 0 : pi + win - 1); k <= pi + win - 1 && alive; ++k)
-          alive = mbar_wait(s_full + 8 * (k % a.n_units), (k / a.n_units) & 1, abort_smem, a.err_flag, 3);
+          alive = wait_u(s_full + 8 * (k % a.n_units), (k / a.n_units) & 1, 3);
         if (!alive) break;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(stage * T * a.npad);
-        if (!a.w_stream) {
-#pragma unroll 2
-          for (int s = 0; s < a.n_steps; ++s) {
-            const int2 e = step_tab[s];
-            const uint64_t bdesc = desc64(hi, b_tab[s]);
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-              uint32_t pos = ws + (uint32_t)e.y + (uint32_t)(t * TILE);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((stage * T + t) * a.npad);
+        // K loop: (ky, kx[, channel-chunk pair]) in the order the B image was packed.  Everything below is
+        // warp-uniform integer arithmetic (no table lookups), so descriptors stay in uniform registers.
+        uint32_t b_lo = b_lo0;
+        int in_group = 0, wst = 0;
+        uint32_t acc = 0;
+        for (int ky = 0; ky < a.ks && alive; ++ky) {
+          for (int kx = 0; kx < kx_end && alive; kx += kx_step) {
+            const uint32_t dwin = (uint32_t)(ky * a.Wp + kx);  // tap offset inside the pass window
+            for (int cp = 0; cp < n_cp; ++cp) {
+              if (a.w_stream && in_group == 0) {  // next streamed weight group
+                wst = wk % a.n_wst;
+                alive = wait_u(s_wfull + 8 * wst, (wk / a.n_wst) & 1, 6);
+                if (!alive) break;
+                tc_fence_after();
+                b_lo = b_lo0 + (uint32_t)wst * wstage_units;
+              }
+              const uint32_t a_c = a_lo0 + (uint32_t)(cp * 2 * ring_plane);
+              const uint64_t bdesc = desc64(hi, b_lo);
+              uint32_t pos = ws + dwin + (uint32_t)(t * TILE);
               pos = min(pos, pos - uL);  // wrap (unsigned): pos < 2L
-              umma_f16(d_tmem + (uint32_t)(t * a.npad), desc64(hi, (uint32_t)e.x + pos), bdesc, idesc, s > 0 ? 1u : 0u);
-            }
-          }
-        } else {
-          for (int g = 0, s = 0; g < n_groups && alive; ++g, ++wk) {
-            const int wst = wk % a.n_wst;
-            alive = mbar_wait(s_wfull + 8 * wst, (wk / a.n_wst) & 1, abort_smem, a.err_flag, 6);
-            if (!alive) break;
-            tc_fence_after();
-            const int s_end = min(s + a.w_group, a.n_steps);
-            for (; s < s_end; ++s) {
-              const int2 e = step_tab[s];
-              const uint64_t bdesc = desc64(hi, b_tab[s] + (uint32_t)wst * wstage_units);
-#pragma unroll
-              for (int t = 0; t < T; ++t) {
-                uint32_t pos = ws + (uint32_t)e.y + (uint32_t)(t * TILE);
-                pos = min(pos, pos - uL);
-                umma_f16(d_tmem + (uint32_t)(t * a.npad), desc64(hi, (uint32_t)e.x + pos), bdesc, idesc, s > 0 ? 1u : 0u);
+              umma_f16(d_tmem, desc64(hi, a_c + pos), bdesc, idesc, acc);
+              acc = 1;
+              b_lo += step_units;
+              if (a.w_stream && ++in_group == a.w_group) {
+                umma_commit(s_wempty + 8 * wst);  // stage may be refilled once every issuer's MMAs retire
+                in_group = 0;
+                ++wk;
               }
             }
-            umma_commit(s_wempty + 8 * wst);  // weight stage may be refilled once these MMAs retire
           }
-          if (!alive) break;
+        }
+        if (!alive) break;
+        if (a.w_stream && in_group != 0) {  // last (short) group of the pass
+          umma_commit(s_wempty + 8 * wst);
+          ++wk;
         }
         umma_commit(s_empty + 8 * (pi % a.n_units));  // unit pi is not needed by later passes
-        umma_commit(s_tfull + 8 * stage);             // accumulators ready for the epilogue
+        umma_commit(s_tfull + 8 * stage);             // this tile's accumulator is ready for the epilogue
         ws += UNIT;
         ws -= (ws >= uL) ? uL : 0u;
       }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
       // ================= epilogue =================
       const int wg = (warp - 4) >> 2;  // warpgroup 0/1 -> even/odd passes
       const int q = warp & 3;          // TMEM lane quarter this warp may access
@@ -447,7 +456,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 12) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
                  : "memory");
