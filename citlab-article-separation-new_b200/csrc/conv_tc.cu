@@ -15,17 +15,19 @@
 //   * D: fp32 in TMEM; a *pass* is T consecutive tiles (T x N columns per accumulator stage), and there
 //     are 2 or 4 stages so the epilogue of pass i overlaps the MMAs of pass i+1.
 //
-// Warp roles (416 threads, 1 CTA / SM, persistent over a contiguous range of passes):
-//   warp 12 lane 0: producer - streams the input as bulk copies (TMA engine, cp.async.bulk) of one *unit*
+// Warp roles (384 threads, 1 CTA / SM, persistent over a contiguous range of passes):
+//   warp 1 lane 0 : producer - streams the input as bulk copies (TMA engine, cp.async.bulk) of one *unit*
 //                   (128*T positions x all input chunks) into a ring; the head of the ring is mirrored
 //                   behind its end so that every 128(+1)-position operand run is contiguous even when it
 //                   wraps.  Read amplification is ~1: every position is fetched once per CTA.
-//                   (warp 12 also allocates / frees TMEM)
-//   warps 0..T-1  : MMA issuers (lane 0) - warp t issues tcgen05.mma.cta_group::1.kind::f16 for tile t of every
-//                   pass, on its own scheduler partition: with N = 16..64 an MMA is far cheaper than the
-//                   instruction sequence that launches it, so issue bandwidth, not the tensor pipe, is the
-//                   limit and it is spread over up to four warps.  tcgen05.commit (one per issuer) frees ring
-//                   units / weight stages and publishes accumulators
+//   warp 0 lane 0 : MMA issuer - tcgen05.mma.cta_group::1.kind::f16.  tools/mma_issue_bench.cu measured the
+//                   issue side on B200: an M=128,K=16 MMA with N <= 64 occupies the pipe for 39-48 cycles
+//                   (the 4 KB shared-memory A read), one thread reaches ~50 cycles/MMA with straight-line
+//                   code and arithmetic descriptors, table look-ups or rolled loops cost 2-3x and extra
+//                   issuer warps do not help.  Hence the kernel is templated on the filter size so the tap
+//                   loops unroll completely and descriptors are base + compile-time-shaped offsets.
+//                   tcgen05.commit frees ring units / weight stages and publishes accumulators
+//   warp 2        : TMEM allocator
 //   warps 4..11   : two epilogue warpgroups (alternating passes): tcgen05.ld -> +bias (+res) -> act ->
 //                   16-bit pack -> 16 B coalesced global stores (in-image positions only; the zero frame of
 //                   the output tensor is never written)
@@ -41,7 +43,7 @@ namespace aru {
 namespace {
 
 constexpr int TILE = 128;
-constexpr int NUM_THREADS = 416;      // warps 0-3 MMA issuers, 4-11 epilogue, 12 producer / TMEM allocator
+constexpr int NUM_THREADS = 384;
 constexpr int MAX_UNITS = 96;
 constexpr int MAX_STEPS = 256;
 constexpr int MIRROR = 136;          // positions mirrored behind the ring (129 needed, rounded up)
@@ -188,8 +190,10 @@ __device__ __forceinline__ void walk_adv(int& col, int& rin, int dc, int dr, int
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int T>
+// MODE 0: C_in = 8 (paired taps)   1: resident weights, >= 2 input chunks   2: streamed weights
+template <int T, int KS, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) {
+  constexpr bool CIN1 = (MODE == 0);
   extern __shared__ __align__(128) uint8_t smem[];
   // a previous launch hit a protocol timeout: do nothing (the host reports the error after the pass)
   if (*reinterpret_cast<volatile int*>(a.err_flag) != 0) return;
@@ -222,13 +226,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
     *abort_smem = 0;
     for (int i = 0; i < a.n_units; ++i) {
       mbar_init(s_full + 8 * i, 1);
-      mbar_init(s_empty + 8 * i, T);   // one tcgen05.commit per MMA issuer
+      mbar_init(s_empty + 8 * i, 1);
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(s_tfull + 8 * i, T);
+      mbar_init(s_tfull + 8 * i, 1);
       mbar_init(s_tempty + 8 * i, 4);
       mbar_init(s_wfull + 8 * i, 1);
-      mbar_init(s_wempty + 8 * i, T);
+      mbar_init(s_wempty + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA) reads
     }
   }
-  if (warp == 12) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr)),
                  "r"((uint32_t)a.tmem_cols)
                  : "memory");
@@ -254,16 +258,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
   const int n_groups = a.w_stream ? (a.n_steps + a.w_group - 1) / a.w_group : 0;
 
   if (n_pass > 0) {
-    if (warp == 12 && lane == 0) {
+    if (warp == 1 && lane == 0) {
       // ================= producer =================
       const int n_load = n_pass + win - 1;
       const long long first_pos = (long long)(u0 + a.dlo) * UNIT;  // ring origin in plane positions
       const uint32_t tx = (uint32_t)a.cin_chunks * UNIT * 16;
       const uint32_t tx_mirror = (uint32_t)a.cin_chunks * MIRROR * 16;
       bool alive = true;
+      int slot = 0;            // k % n_units and the parity of k / n_units, kept incrementally (no divisions
+      uint32_t use_par = 0;    // in the steady-state loops of any role)
       auto load_unit = [&](int k) {
-        const int slot = k % a.n_units, use = k / a.n_units;
-        if (!mbar_wait(s_empty + 8 * slot, (use & 1) ^ 1, abort_smem, a.err_flag, 1)) { alive = false; return; }
+        if (!mbar_wait(s_empty + 8 * slot, use_par ^ 1, abort_smem, a.err_flag, 1)) { alive = false; return; }
         const uint32_t bar = s_full + 8 * slot;
         const act_t* src = a.in + (first_pos + (long long)k * UNIT) * 8;
         mbar_expect_tx(bar, slot == 0 ? tx + tx_mirror : tx);
@@ -272,6 +277,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
           bulk_g2s(dst, src + c * a.in_plane * 8, UNIT * 16, bar);
           if (slot == 0) bulk_g2s(dst + (uint32_t)L * 16, src + c * a.in_plane * 8, MIRROR * 16, bar);
         }
+        if (++slot == a.n_units) { slot = 0; use_par ^= 1; }
       };
       if (!a.w_stream) {
         for (int k = 0; k < n_load && alive; ++k) load_unit(k);
@@ -279,23 +285,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
         // consumption order: window of pass 0 (+ prefetch), then per pass its weight groups and one more unit
         int next = 0;
         for (; next < min(n_load, a.n_units - 1) && alive; ++next) load_unit(next);
-        int wk = 0;  // running weight-group counter
+        int ws = 0;            // weight stage and its use parity
+        uint32_t w_par = 0;
         for (int pi = 0; pi < n_pass && alive; ++pi) {
-          for (int g = 0; g < n_groups && alive; ++g, ++wk) {
-            const int ws = wk % a.n_wst, use = wk / a.n_wst;
-            if (!mbar_wait(s_wempty + 8 * ws, (use & 1) ^ 1, abort_smem, a.err_flag, 5)) { alive = false; break; }
+          for (int g = 0; g < n_groups && alive; ++g) {
+            if (!mbar_wait(s_wempty + 8 * ws, w_par ^ 1, abort_smem, a.err_flag, 5)) { alive = false; break; }
             const int steps = min(a.w_group, a.n_steps - g * a.w_group);
             const uint32_t bytes = (uint32_t)(steps * step_bytes);
             mbar_expect_tx(s_wfull + 8 * ws, bytes);
             bulk_g2s(s_w + (uint32_t)(ws * a.w_group * step_bytes),
                      reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)g * a.w_group * step_bytes, bytes, s_wfull + 8 * ws);
+            if (++ws == a.n_wst) { ws = 0; w_par ^= 1; }
           }
           if (next < n_load && alive) load_unit(next++);
         }
       }
-    } else if (warp < T && lane == 0) {
-      // ================= MMA issuers: warp t issues the MMAs of tile t of every pass =================
-      const int t = warp;
+    } else if (warp == 0 && lane == 0) {
+      // ================= MMA issuer =================
       const uint32_t idesc = (1u << 4) | (ARU_UMMA_FMT << 7) | (ARU_UMMA_FMT << 10) | ((uint32_t)(a.npad >> 3) << 17) |
                              ((uint32_t)(TILE >> 4) << 24);
       const uint32_t hi = desc_hi(128);
@@ -303,71 +309,99 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
       uint32_t ws = (uint32_t)(((-a.dlo) * UNIT + a.min_off) % L);  // ring position of the pass window start
       const uint32_t wstage_units = (uint32_t)(a.w_group * step_bytes) >> 4;
       const uint32_t step_units = (uint32_t)step_bytes >> 4;
-      const uint32_t a_lbo = a.cin_chunks == 1 ? 16u : (uint32_t)ring_plane * 16u;
+      const uint32_t a_lbo = CIN1 ? 16u : (uint32_t)ring_plane * 16u;
       const uint32_t a_lo0 = (s_ring >> 4) | ((a_lbo >> 4) << 16);
       const uint32_t b_lo0 = (s_w >> 4) | ((((uint32_t)a.npad * 16u) >> 4) << 16);
-      // C_in = 8: horizontally adjacent taps are paired into one K=16 step (the B image holds zeros for
-      // the non-existent partner of the last tap of an odd-width kernel)
-      const int kx_step = a.cin_chunks == 1 ? 2 : 1;
-      const int kx_end = a.ks;
-      const int n_cp = a.cin_chunks == 1 ? 1 : a.cin_chunks / 2;
-      int wk = 0;
+      const uint32_t cp_stride = (uint32_t)(2 * ring_plane);  // descriptor units between channel-chunk pairs
+      const int n_cp = CIN1 ? 1 : a.cin_chunks / 2;
+      const uint32_t uWp = (uint32_t)a.Wp, npad = (uint32_t)a.npad;
       bool alive = true;
-      auto wait_u = [&](uint32_t bar, uint32_t parity, int code) -> bool {
-        return mbar_wait(bar, parity, abort_smem, a.err_flag, code);
-      };
+      // incremental ring bookkeeping (no divisions in the loop)
+      int stage = 0, f_slot = 0, e_slot = 0, wst = 0;
+      uint32_t stage_par = 0, f_par = 0, w_par = 0;
       for (int pi = 0; pi < n_pass && alive; ++pi) {
-        const int stage = pi % a.n_stages;
-        alive = wait_u(s_tempty + 8 * stage, ((pi / a.n_stages) & 1) ^ 1, 2);
+        alive = mbar_wait(s_tempty + 8 * stage, stage_par ^ 1, abort_smem, a.err_flag, 2);
         // operands: pass pi reads units pi .. pi+win-1 (the first pass waits for its whole window)
-        for (int k = (pi == 0 ? 0 : pi + win - 1); k <= pi + win - 1 && alive; ++k)
-          alive = wait_u(s_full + 8 * (k % a.n_units), (k / a.n_units) & 1, 3);
+        for (int k = (pi == 0 ? 0 : win - 1); k < win && alive; ++k) {
+          alive = mbar_wait(s_full + 8 * f_slot, f_par, abort_smem, a.err_flag, 3);
+          if (++f_slot == a.n_units) { f_slot = 0; f_par ^= 1; }
+        }
         if (!alive) break;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)((stage * T + t) * a.npad);
-        // K loop: (ky, kx[, channel-chunk pair]) in the order the B image was packed.  Everything below is
-        // warp-uniform integer arithmetic (no table lookups), so descriptors stay in uniform registers.
+        const uint32_t d_tmem = tmem_base + (uint32_t)(stage * T) * npad;
+        // K loop in the order the B image was packed: taps (ky, kx) unrolled at compile time, channel-chunk
+        // pairs inside.  C_in = 8 (CIN1): horizontally adjacent taps are paired into one K=16 step (the B
+        // image holds zeros for the missing partner of the last tap of an odd-width kernel).
         uint32_t b_lo = b_lo0;
-        int in_group = 0, wst = 0;
-        uint32_t acc = 0;
-        for (int ky = 0; ky < a.ks && alive; ++ky) {
-          for (int kx = 0; kx < kx_end && alive; kx += kx_step) {
-            const uint32_t dwin = (uint32_t)(ky * a.Wp + kx);  // tap offset inside the pass window
-            for (int cp = 0; cp < n_cp; ++cp) {
-              if (a.w_stream && in_group == 0) {  // next streamed weight group
-                wst = wk % a.n_wst;
-                alive = wait_u(s_wfull + 8 * wst, (wk / a.n_wst) & 1, 6);
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < KS; kx += (CIN1 ? 2 : 1)) {
+            uint32_t a_pos[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              uint32_t pos = ws + (uint32_t)ky * uWp + (uint32_t)(kx + t * TILE);  // position inside the ring
+              pos = min(pos, pos - uL);                                             // wrap (unsigned): pos < 2L
+              a_pos[t] = a_lo0 + pos;
+            }
+            if constexpr (MODE == 0) {
+#pragma unroll
+              for (int t = 0; t < T; ++t)
+                umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_pos[t]), desc64(hi, b_lo), idesc, (ky | kx) ? 1u : 0u);
+              b_lo += step_units;
+            } else if constexpr (MODE == 1) {
+              // rolled over the channel-chunk pairs (keeps the kernel small enough for the instruction cache);
+              // with one tile per pass two pairs are issued per iteration to amortise the loop overhead
+              int cp = 0;
+              if constexpr (T == 1) {
+                for (; cp + 1 < n_cp; cp += 2) {
+                  umma_f16(d_tmem, desc64(hi, a_pos[0] + (uint32_t)cp * cp_stride), desc64(hi, b_lo), idesc, (ky | kx | cp) ? 1u : 0u);
+                  umma_f16(d_tmem, desc64(hi, a_pos[0] + (uint32_t)(cp + 1) * cp_stride), desc64(hi, b_lo + step_units), idesc, 1u);
+                  b_lo += 2 * step_units;
+                }
+              }
+#pragma unroll 1
+              for (; cp < n_cp; ++cp) {
+                const uint32_t acc = (ky | kx | cp) ? 1u : 0u;
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                  umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_pos[t] + (uint32_t)cp * cp_stride), desc64(hi, b_lo), idesc, acc);
+                b_lo += step_units;
+              }
+            } else {
+              // streamed weights: groups of w_group steps (w_group divides n_cp, so a group never straddles taps)
+#pragma unroll 1
+              for (int cp0 = 0; cp0 < n_cp && alive; cp0 += a.w_group) {
+                alive = mbar_wait(s_wfull + 8 * wst, w_par, abort_smem, a.err_flag, 6);
                 if (!alive) break;
                 tc_fence_after();
                 b_lo = b_lo0 + (uint32_t)wst * wstage_units;
-              }
-              const uint32_t a_c = a_lo0 + (uint32_t)(cp * 2 * ring_plane);
-              const uint64_t bdesc = desc64(hi, b_lo);
-              uint32_t pos = ws + dwin + (uint32_t)(t * TILE);
-              pos = min(pos, pos - uL);  // wrap (unsigned): pos < 2L
-              umma_f16(d_tmem, desc64(hi, a_c + pos), bdesc, idesc, acc);
-              acc = 1;
-              b_lo += step_units;
-              if (a.w_stream && ++in_group == a.w_group) {
-                umma_commit(s_wempty + 8 * wst);  // stage may be refilled once every issuer's MMAs retire
-                in_group = 0;
-                ++wk;
+#pragma unroll 1
+                for (int cp = cp0; cp < cp0 + a.w_group; ++cp) {
+                  const uint32_t acc = (ky | kx | cp) ? 1u : 0u;
+#pragma unroll
+                  for (int t = 0; t < T; ++t)
+                    umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_pos[t] + (uint32_t)cp * cp_stride), desc64(hi, b_lo), idesc, acc);
+                  b_lo += step_units;
+                }
+                umma_commit(s_wempty + 8 * wst);  // stage may be refilled once these MMAs retire
+                if (++wst == a.n_wst) { wst = 0; w_par ^= 1; }
               }
             }
           }
         }
         if (!alive) break;
-        if (a.w_stream && in_group != 0) {  // last (short) group of the pass
-          umma_commit(s_wempty + 8 * wst);
-          ++wk;
-        }
-        umma_commit(s_empty + 8 * (pi % a.n_units));  // unit pi is not needed by later passes
-        umma_commit(s_tfull + 8 * stage);             // this tile's accumulator is ready for the epilogue
+        umma_commit(s_empty + 8 * e_slot);  // unit pi is not needed by later passes
+        umma_commit(s_tfull + 8 * stage);   // accumulators ready for the epilogue
+        if (++e_slot == a.n_units) e_slot = 0;
+        if (++stage == a.n_stages) { stage = 0; stage_par ^= 1; }
         ws += UNIT;
         ws -= (ws >= uL) ? uL : 0u;
       }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4) {
       // ================= epilogue =================
+      // Deliberately compact (rolled loops): ten warps run four different code regions of this kernel, and an
+      // unrolled epilogue made instruction-cache misses (stall_no_inst) its dominant stall.
       const int wg = (warp - 4) >> 2;  // warpgroup 0/1 -> even/odd passes
       const int q = warp & 3;          // TMEM lane quarter this warp may access
       const int m = q * 32 + lane;
@@ -380,75 +414,71 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
         col = rel - row * a.Wp;
         rin = row % a.Hp;
       }
+      auto in_image = [&](int pp, int c, int r) {
+        return (c >= 1) && (c <= a.W) && (r >= 1) && (r <= a.H) && (pp >= a.lead) && (pp < a.body_end);
+      };
+      // residual operand of the *next* tile is fetched one tile ahead (chunk 0) / one chunk ahead (others)
+      bool v_next = in_image(p, col, rin);
+      uint4 r_next = make_uint4(0, 0, 0, 0);
+      if (a.res && v_next) r_next = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)p * 8));
       bool alive = true;
+      int stage = wg;             // pi % n_stages and the parity of pi / n_stages (n_stages is 2 or 4)
+      uint32_t stage_par = 0;
       for (int pi = wg; pi < n_pass && alive; pi += 2) {
-        const int stage = pi % a.n_stages;
-        uint4 res0[T];
-        bool valid[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) res0[t] = make_uint4(0, 0, 0, 0);
-        {  // validity of the T positions of this pass + early residual fetch (chunk 0)
-          int c2 = col, r2 = rin;
-#pragma unroll
-          for (int t = 0; t < T; ++t) {
-            const int pt = p + t * TILE;
-            valid[t] = (c2 >= 1) && (c2 <= a.W) && (r2 >= 1) && (r2 <= a.H) && (pt >= a.lead) && (pt < a.body_end);
-            if (a.res && valid[t]) res0[t] = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)pt * 8));
-            walk_adv(c2, r2, a.dc128, a.dr128, a.Wp, a.Hp);
-          }
-          col = c2; rin = r2;                                // now at tile 0 of the next pass (other warpgroup's)
-          walk_adv(col, rin, a.dcT, a.drT, a.Wp, a.Hp);      // skip it
-        }
-        alive = mbar_wait(s_tfull + 8 * stage, (pi / a.n_stages) & 1, abort_smem, a.err_flag, 4);
+        alive = mbar_wait(s_tfull + 8 * stage, stage_par, abort_smem, a.err_flag, 4);
         alive = __shfl_sync(0xffffffffu, alive ? 1 : 0, 0) != 0;
         if (!alive) break;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < T; ++t) {
-          const int pt = p + t * TILE;
-          for (int c0 = 0; c0 < a.cout_chunks; c0 += 2) {
-            uint32_t v0[8], v1[8];
-            const bool two = (c0 + 1 < a.cout_chunks);
-            tmem_ld8(taddr + t * a.npad + c0 * 8, v0);
-            if (two) tmem_ld8(taddr + t * a.npad + c0 * 8 + 8, v1);
-            uint4 r0 = res0[t], r1 = make_uint4(0, 0, 0, 0);
-            if (a.res && valid[t]) {
-              if (c0 > 0) r0 = __ldg(reinterpret_cast<const uint4*>(a.res + ((long long)c0 * a.res_plane + pt) * 8));
-              if (two) r1 = __ldg(reinterpret_cast<const uint4*>(a.res + ((long long)(c0 + 1) * a.res_plane + pt) * 8));
-            }
+          const int pt = p;
+          const bool valid = v_next;
+          uint4 r_cur = r_next;
+          // step to the next tile of this warpgroup (the other warpgroup's pass is skipped after tile T-1)
+          walk_adv(col, rin, a.dc128, a.dr128, a.Wp, a.Hp);
+          p += TILE;
+          if (t == T - 1) {
+            walk_adv(col, rin, a.dcT, a.drT, a.Wp, a.Hp);
+            p += UNIT;
+          }
+          v_next = in_image(p, col, rin);
+          if (a.res && v_next) r_next = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)p * 8));
+#pragma unroll 1
+          for (int c = 0; c < a.cout_chunks; ++c) {
+            uint32_t v[8];
+            tmem_ld8(taddr + (uint32_t)(t * a.npad + c * 8), v);
+            uint4 r_c1 = make_uint4(0, 0, 0, 0);
+            if (a.res && valid && c + 1 < a.cout_chunks)
+              r_c1 = __ldg(reinterpret_cast<const uint4*>(a.res + ((long long)(c + 1) * a.res_plane + pt) * 8));
             tmem_ld_wait();
-            if (t == T - 1 && c0 + 2 >= a.cout_chunks) {  // last TMEM read of this stage: hand the accumulators back
+            if (t == T - 1 && c == a.cout_chunks - 1) {  // last TMEM read of this stage: hand the accumulators back
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
             }
-            if (valid[t]) {
+            if (valid) {
+              float acc[8];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (h == 1 && !two) break;
-                const int c = c0 + h;
-                float acc[8];
+              for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(v[j]) + s_bias[c * 8 + j];
+              if (a.res) {
+                float r[8];
+                unpack8(r_cur, r);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(h ? v1[j] : v0[j]) + s_bias[c * 8 + j];
-                if (a.res) {
-                  float r[8];
-                  unpack8(h ? r1 : r0, r);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) acc[j] += r[j];
-                }
-                if (a.out_pre)
-                  *reinterpret_cast<uint4*>(a.out_pre + ((long long)c * a.pre_plane + pt) * 8) = pack8(acc);
-                if (a.act == 1) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-                }
-                *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + pt) * 8) = pack8(acc);
+                for (int j = 0; j < 8; ++j) acc[j] += r[j];
               }
+              if (a.out_pre) *reinterpret_cast<uint4*>(a.out_pre + ((long long)c * a.pre_plane + pt) * 8) = pack8(acc);
+              if (a.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+              }
+              *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + pt) * 8) = pack8(acc);
             }
+            r_cur = r_c1;
           }
         }
-        p += 2 * UNIT;
+        stage += 2;
+        if (stage >= a.n_stages) { stage -= a.n_stages; stage_par ^= 1; }
       }
     }
   }
@@ -456,7 +486,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
                  : "memory");
@@ -513,7 +543,10 @@ ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, si
   if (p.n_steps > MAX_STEPS) { p.why = "too many K steps"; return p; }
   p.wpack_bytes = (size_t)p.n_steps * 32 * p.npad;
   const size_t w_resident = ((p.wpack_bytes + 127) / 128) * 128;
-  p.w_group = std::max(1, 16384 / (32 * p.npad));
+  // streamed weight groups: about 16 KB, a divisor of the channel-chunk pairs per tap
+  const int n_cp = p.cin_chunks == 1 ? 1 : p.cin_chunks / 2;
+  p.w_group = std::max(1, std::min(n_cp, 16384 / (32 * p.npad)));
+  while (n_cp % p.w_group) --p.w_group;
   p.n_wst = 3;
   const size_t w_streamed = (((size_t)p.n_wst * p.w_group * 32 * p.npad) + 127) / 128 * 128;
   p.why = "weights + operand ring exceed shared memory";
@@ -535,6 +568,14 @@ ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, si
       p.n_slots = n_units;
       p.smem_bytes = smem;
       p.n_stages = (T * p.npad * 4 <= 512) ? 4 : 2;
+      // Deepen the prefetch with whatever shared memory is left: HBM latency under load is ~1-2 us, so a
+      // CTA needs tens of KB of loads in flight to sustain its share (~45 GB/s) of the memory bandwidth.
+      const size_t unit_bytes = (size_t)p.cin_chunks * TILE * T * 16;
+      while (p.n_slots < MAX_UNITS && p.smem_bytes + unit_bytes <= max_smem &&
+             (size_t)(p.n_slots + 1 - w.win) * unit_bytes <= 96 * 1024) {
+        ++p.n_slots;
+        p.smem_bytes += unit_bytes;
+      }
     }
   }
   if (!p.ok) return p;
@@ -601,20 +642,28 @@ cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& p, PV in, PV out, 
   a.dcT = unit % g.Wp; a.drT = unit / g.Wp;
   a.act = act;
   a.err_flag = err_flag;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  using Kern = void (*)(const ConvTcArgs);
+  Kern k = nullptr;
+  const int mode = p.cin_chunks == 1 ? 0 : (p.w_stream ? 2 : 1);
+#define ARU_TC_PICK(TT, KK, MM) if (p.T == TT && p.ks == KK && mode == MM) k = k_conv_tc<TT, KK, MM>;
+  ARU_TC_PICK(1, 3, 0) ARU_TC_PICK(2, 3, 0) ARU_TC_PICK(4, 3, 0)
+  ARU_TC_PICK(1, 3, 1) ARU_TC_PICK(2, 3, 1) ARU_TC_PICK(4, 3, 1)
+  ARU_TC_PICK(1, 3, 2) ARU_TC_PICK(2, 3, 2)
+  ARU_TC_PICK(1, 4, 0) ARU_TC_PICK(2, 4, 0) ARU_TC_PICK(4, 4, 0)
+  ARU_TC_PICK(1, 4, 1) ARU_TC_PICK(2, 4, 1) ARU_TC_PICK(4, 4, 1)
+  ARU_TC_PICK(1, 4, 2) ARU_TC_PICK(2, 4, 2)
+#undef ARU_TC_PICK
+  if (!k) return cudaErrorInvalidValue;
+  static Kern configured[24];
+  static int n_configured = 0;
+  bool done = false;
+  for (int i = 0; i < n_configured; ++i) done = done || configured[i] == k;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (n_configured < 24) configured[n_configured++] = k;
   }
-  if (p.T == 4)
-    k_conv_tc<4><<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
-  else if (p.T == 2)
-    k_conv_tc<2><<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
-  else
-    k_conv_tc<1><<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
+  k<<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
   return cudaGetLastError();
 }
 
