@@ -82,6 +82,9 @@ struct ConvTcArgs {
   int dlo, dhi, min_off;
   int dc128, dr128, dcT, drT;     // (col,row) advance of 128 and 128*T positions
   int act;
+  // transposed convolution (3x3 stride 2 as a 2x2 correlation with four output-parity classes in N)
+  int deconv, cls_chunks, bias_pages;
+  int Wo, Ho, Wpo, Hpo, lead_o, offy, offx;
   int* err_flag;
 };
 
@@ -179,13 +182,14 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
-__device__ __forceinline__ void walk_adv(int& col, int& rin, int dc, int dr, int Wp, int Hp) {
+__device__ __forceinline__ void walk_adv(int& col, int& rin, int& pg, int dc, int dr, int Wp, int Hp) {
   col += dc;
   rin += dr;
   if (col >= Wp) { col -= Wp; ++rin; }
   if (rin >= Hp) {
     rin -= Hp;
-    if (rin >= Hp) rin %= Hp;
+    ++pg;
+    if (rin >= Hp) { pg += rin / Hp; rin %= Hp; }
   }
 }
 
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
-    for (int i = threadIdx.x; i < a.npad; i += NUM_THREADS) s_bias[i] = a.bias[i];
+    for (int i = threadIdx.x; i < (a.deconv ? a.cls_chunks * 8 : a.npad); i += NUM_THREADS) s_bias[i] = a.bias[i];
     if (!a.w_stream) {  // resident B image
       const uint4* wsrc = reinterpret_cast<const uint4*>(a.wpack);
       uint4* wdst = reinterpret_cast<uint4*>(smem + HDR_BYTES);
@@ -407,12 +411,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
       const int m = q * 32 + lane;
       // (col, rin) of this lane's position in tile 0 of its first pass; rel_bias makes the numerator non-negative
       int p = (u0 + wg) * UNIT + m;
-      int col, rin;
+      int col, rin, pg;
       {
         const int rel = p - a.lead + a.rel_bias;
         const int row = rel / a.Wp;
         col = rel - row * a.Wp;
-        rin = row % a.Hp;
+        pg = row / a.Hp;
+        rin = row - pg * a.Hp;
+        pg -= a.bias_pages;
       }
       auto in_image = [&](int pp, int c, int r) {
         return (c >= 1) && (c <= a.W) && (r >= 1) && (r <= a.H) && (pp >= a.lead) && (pp < a.body_end);
@@ -432,14 +438,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
+          if (a.deconv) {
+            // this lane's *input* pixel (j, i) = (rin-1, col-1), including the frame row / column j = H, i = W;
+            // it owns the four outputs full[2j+py, 2i+px], cropped by (offy, offx)  (layers.py:342-367)
+            const bool in_dom = (p >= a.lead) && (p < a.body_end) && (col >= 1) && (col <= a.W + 1) && (rin >= 1) &&
+                                (rin <= a.H + 1);
+            const int oy0 = 2 * (rin - 1) - a.offy, ox0 = 2 * (col - 1) - a.offx;
+            const long long po0 = (long long)a.lead_o + ((long long)pg * a.Hpo + oy0 + 1) * a.Wpo + ox0 + 1;
+#pragma unroll 1
+            for (int cls = 0; cls < 4; ++cls) {
+              const int oy = oy0 + (cls >> 1), ox = ox0 + (cls & 1);
+              const bool v = in_dom && (oy >= 0) && (oy < a.Ho) && (ox >= 0) && (ox < a.Wo);
+              const long long po = po0 + (long long)(cls >> 1) * a.Wpo + (cls & 1);
+#pragma unroll 1
+              for (int c = 0; c < a.cls_chunks; ++c) {
+                uint32_t v8[8];
+                tmem_ld8(taddr + (uint32_t)(t * a.npad + (cls * a.cls_chunks + c) * 8), v8);
+                tmem_ld_wait();
+                if (t == T - 1 && cls == 3 && c == a.cls_chunks - 1) {
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
+                }
+                if (v) {
+                  float acc[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    acc[j] = __uint_as_float(v8[j]) + s_bias[c * 8 + j];
+                    if (a.act == 1) acc[j] = fmaxf(acc[j], 0.f);
+                  }
+                  *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + po) * 8) = pack8(acc);
+                }
+              }
+            }
+            walk_adv(col, rin, pg, a.dc128, a.dr128, a.Wp, a.Hp);
+            p += TILE;
+            if (t == T - 1) {
+              walk_adv(col, rin, pg, a.dcT, a.drT, a.Wp, a.Hp);
+              p += UNIT;
+            }
+            continue;
+          }
           const int pt = p;
           const bool valid = v_next;
           uint4 r_cur = r_next;
           // step to the next tile of this warpgroup (the other warpgroup's pass is skipped after tile T-1)
-          walk_adv(col, rin, a.dc128, a.dr128, a.Wp, a.Hp);
+          walk_adv(col, rin, pg, a.dc128, a.dr128, a.Wp, a.Hp);
           p += TILE;
           if (t == T - 1) {
-            walk_adv(col, rin, a.dcT, a.drT, a.Wp, a.Hp);
+            walk_adv(col, rin, pg, a.dcT, a.drT, a.Wp, a.Hp);
             p += UNIT;
           }
           v_next = in_image(p, col, rin);
@@ -497,9 +544,11 @@ struct Window {
   int min_off, max_off, dlo, dhi, win;
 };
 
+// KxK SAME correlation: taps reach PB positions back in both directions (TF pads 1 before for 3x3 and 4x4);
+// the 2x2 form of the transposed convolution looks back only (PB = 1).
 Window make_window(int ks, int cin_chunks, int Wp, int unit) {
   Window w;
-  const int PB = (ks - 1) / 2;
+  const int PB = ks == 2 ? 1 : (ks - 1) / 2;
   w.min_off = -PB * (Wp + 1);
   w.max_off = (ks - 1 - PB) * (Wp + 1);
   if (cin_chunks == 1) w.max_off += 1;  // paired taps read one position further
@@ -529,13 +578,16 @@ uint16_t host_f_to_act(float v) {
 #endif
 }
 
-ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, size_t max_smem) {
+ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, size_t max_smem, bool deconv) {
   ConvTcPlan p;
-  p.ks = ks;
+  p.deconv = deconv;
+  p.ks = deconv ? 2 : ks;  // 3x3 stride-2 transposed conv == 2x2 correlation over the input with 4 parity classes in N
   p.cin_chunks = cdiv(cin, 8);
   p.cout_chunks = cdiv(cout, 8);
-  p.npad = cdiv(p.cout_chunks * 8, 16) * 16;
-  if (ks != 3 && ks != 4) { p.why = "kernel size"; return p; }
+  p.npad = cdiv((deconv ? 4 : 1) * p.cout_chunks * 8, 16) * 16;
+  if (deconv ? ks != 3 : (ks != 3 && ks != 4)) { p.why = "kernel size"; return p; }
+  if (deconv && p.cin_chunks == 1) { p.why = "transposed conv needs >= 16 input channels"; return p; }
+  ks = p.ks;
   if (p.cin_chunks != 1 && (p.cin_chunks & 1)) { p.why = "odd number of input chunks"; return p; }
   if (p.npad > 256) { p.why = "C_out > 256"; return p; }
   if (g.plane >= (1LL << 31) / 16) { p.why = "plane too large for 32-bit positions"; return p; }
@@ -582,7 +634,8 @@ ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, si
   p.why = "";
   const long long unit = TILE * p.T;
   p.tile_begin = g.pos(0, 0, 0) / unit;                          // in passes
-  p.tile_end = g.pos(g.N - 1, g.H - 1, g.W - 1) / unit + 1;
+  // the transposed conv also computes at the frame row / column (input pixel j = H, i = W feeds output 2H, 2W)
+  p.tile_end = (deconv ? g.pos(g.N - 1, g.H, g.W) : g.pos(g.N - 1, g.H - 1, g.W - 1)) / unit + 1;
   const long long passes = p.tile_end - p.tile_begin;
   p.grid = (int)(passes < num_sms ? passes : num_sms);
   return p;
@@ -613,15 +666,66 @@ void conv_tc_pack_weights(const ConvTcPlan& p, const float* w, int cin, int cout
         }
 }
 
+// Transposed-conv B image.  K = (2x2 look-back tap, input channel), N = (output parity class, output channel):
+//   full[2j+py, 2i+px] = sum over (ky2, kx2) in {0,1}^2 of in[j-1+ky2, i-1+kx2] . Wd[ky][kx],
+//   with ky = py (ky2 == 1: the pixel itself) or ky = 2 (ky2 == 0 and py == 0: the pixel above); same in x.
+// Wd is the TF filter [3][3][cout][cin] of Conv2DBackpropInput (layers.py:356-360).
+void conv_tc_pack_deconv(const ConvTcPlan& p, const float* w, int cin, int cout, uint16_t* dst) {
+  memset(dst, 0, p.wpack_bytes);
+  const int n_cp = p.cin_chunks / 2, cpad = p.cout_chunks * 8;
+  auto tap_of = [](int k2, int par) -> int { return k2 == 1 ? par : (par == 0 ? 2 : -1); };
+  for (int s = 0; s < p.n_steps; ++s) {
+    const int tap2 = s / n_cp, cp = s % n_cp;
+    const int ky2 = tap2 / 2, kx2 = tap2 % 2;
+    for (int h = 0; h < 2; ++h)
+      for (int cls = 0; cls < 4; ++cls) {
+        const int ky = tap_of(ky2, cls >> 1), kx = tap_of(kx2, cls & 1);
+        if (ky < 0 || kx < 0) continue;
+        for (int co = 0; co < cout; ++co)
+          for (int j = 0; j < 8; ++j) {
+            const int ci = (2 * cp + h) * 8 + j;
+            if (ci >= cin) continue;
+            const float v = w[(((size_t)ky * 3 + kx) * cout + co) * cin + ci];
+            dst[(((size_t)s * 2 + h) * p.npad + cls * cpad + co) * 8 + j] = host_f_to_act(v);
+          }
+      }
+  }
+}
+
+static cudaError_t launch_tc_common(cudaStream_t st, const ConvTcPlan& p, ConvTcArgs& a, const Geo& g);
+
+cudaError_t launch_deconv_tc(cudaStream_t st, const ConvTcPlan& p, PV in, PV out, const act_t* wpack, const float* bias_pad,
+                             const Geo& gi, const Geo& go, int act, int* err_flag) {
+  if (!p.ok || !p.deconv) return cudaErrorInvalidValue;
+  ConvTcArgs a{};
+  a.in = in.p; a.in_plane = in.plane;
+  a.out = out.p; a.out_plane = out.plane;
+  a.wpack = wpack; a.bias = bias_pad;
+  a.act = act;
+  a.err_flag = err_flag;
+  a.deconv = 1;
+  a.cls_chunks = p.cout_chunks;
+  a.Wo = go.W; a.Ho = go.H; a.Wpo = go.Wp; a.Hpo = go.Hp; a.lead_o = (int)go.lead;
+  a.offy = (2 * gi.H + 1 - go.H) / 2;
+  a.offx = (2 * gi.W + 1 - go.W) / 2;
+  return launch_tc_common(st, p, a, gi);
+}
+
 cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& p, PV in, PV out, PV out_pre, PV res, const act_t* wpack,
                            const float* bias_pad, const Geo& g, int act, int* err_flag) {
-  if (!p.ok) return cudaErrorInvalidValue;
-  ConvTcArgs a;
+  if (!p.ok || p.deconv) return cudaErrorInvalidValue;
+  ConvTcArgs a{};
   a.in = in.p; a.in_plane = in.plane;
   a.out = out.p; a.out_plane = out.plane;
   a.out_pre = out_pre.p; a.pre_plane = out_pre.plane;
   a.res = res.p; a.res_plane = res.plane;
   a.wpack = wpack; a.bias = bias_pad;
+  a.act = act;
+  a.err_flag = err_flag;
+  return launch_tc_common(st, p, a, g);
+}
+
+static cudaError_t launch_tc_common(cudaStream_t st, const ConvTcPlan& p, ConvTcArgs& a, const Geo& g) {
   a.ks = p.ks; a.cin_chunks = p.cin_chunks; a.cout_chunks = p.cout_chunks; a.npad = p.npad;
   a.n_steps = p.n_steps; a.n_units = p.n_slots; a.n_stages = p.n_stages;
   a.w_stream = p.w_stream; a.w_group = p.w_group; a.n_wst = p.n_wst;
@@ -640,8 +744,7 @@ cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& p, PV in, PV out, 
   a.dlo = w.dlo; a.dhi = w.dhi; a.min_off = w.min_off;
   a.dc128 = TILE % g.Wp; a.dr128 = TILE / g.Wp;
   a.dcT = unit % g.Wp; a.drT = unit / g.Wp;
-  a.act = act;
-  a.err_flag = err_flag;
+  a.bias_pages = (int)(a.rel_bias / page);
   using Kern = void (*)(const ConvTcArgs);
   Kern k = nullptr;
   const int mode = p.cin_chunks == 1 ? 0 : (p.w_stream ? 2 : 1);
@@ -652,16 +755,18 @@ cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& p, PV in, PV out, 
   ARU_TC_PICK(1, 4, 0) ARU_TC_PICK(2, 4, 0) ARU_TC_PICK(4, 4, 0)
   ARU_TC_PICK(1, 4, 1) ARU_TC_PICK(2, 4, 1) ARU_TC_PICK(4, 4, 1)
   ARU_TC_PICK(1, 4, 2) ARU_TC_PICK(2, 4, 2)
+  ARU_TC_PICK(1, 2, 1) ARU_TC_PICK(2, 2, 1) ARU_TC_PICK(4, 2, 1)
+  ARU_TC_PICK(1, 2, 2) ARU_TC_PICK(2, 2, 2)
 #undef ARU_TC_PICK
   if (!k) return cudaErrorInvalidValue;
-  static Kern configured[24];
+  static Kern configured[32];
   static int n_configured = 0;
   bool done = false;
   for (int i = 0; i < n_configured; ++i) done = done || configured[i] == k;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    if (n_configured < 24) configured[n_configured++] = k;
+    if (n_configured < 32) configured[n_configured++] = k;
   }
   k<<<p.grid, NUM_THREADS, p.smem_bytes, st>>>(a);
   return cudaGetLastError();

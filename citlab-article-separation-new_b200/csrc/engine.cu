@@ -186,7 +186,10 @@ int get_tc_image(aru_engine* e, int oi, const ConvTcPlan& tp, int begin, int chu
     if (im.ci_chunk_begin == begin && im.ci_chunks == chunks) { *out = im.w; return ARU_OK; }
   const aru_op& op = e->ops[oi];
   std::vector<uint16_t> img(tp.wpack_bytes / 2);
-  conv_tc_pack_weights(tp, e->weights.data() + op.w_off, op.in.ch, op.out.ch, begin * 8, img.data());
+  if (tp.deconv)
+    conv_tc_pack_deconv(tp, e->weights.data() + op.w_off, op.in.ch, op.out.ch, img.data());
+  else
+    conv_tc_pack_weights(tp, e->weights.data() + op.w_off, op.in.ch, op.out.ch, begin * 8, img.data());
   uint16_t* dev = nullptr;
   int rc = upload(e, img, &dev);
   if (rc) return rc;
@@ -282,9 +285,15 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
       break;
     }
     case ARU_OP_DECONV:
-      label = "deconv_direct";
-      err = launch_deconv_direct(st, make_pv(e, p, op.in), p->bufs[op.in.buf].geo, make_pv(e, p, op.out),
-                                 p->bufs[op.out.buf].geo, ow.w16, ow.bias, op.act);
+      if (!p->tc[oi].empty()) {
+        label = "deconv_tc";
+        err = launch_deconv_tc(st, p->tc[oi][0].plan, make_pv(e, p, op.in), make_pv(e, p, op.out), p->tc[oi][0].w, ow.bias,
+                               p->bufs[op.in.buf].geo, p->bufs[op.out.buf].geo, op.act, e->err_flag);
+      } else {
+        label = "deconv_direct";
+        err = launch_deconv_direct(st, make_pv(e, p, op.in), p->bufs[op.in.buf].geo, make_pv(e, p, op.out),
+                                   p->bufs[op.out.buf].geo, ow.w16, ow.bias, op.act);
+      }
       break;
     case ARU_OP_MAXPOOL:
     case ARU_OP_AVGPOOL: {
@@ -471,9 +480,20 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   // kernel selection for the chunk-planar convolutions
   for (int i = 0; i < no; ++i) {
     const aru_op& op = e->ops[i];
+    if (e->conv_path == 1) continue;
+    if (op.kind == ARU_OP_DECONV) {
+      ConvTcPlan tp = conv_tc_plan(3, op.in.ch, op.out.ch, p->bufs[op.in.buf].geo, e->num_sms, e->max_smem, true);
+      if (tp.ok) {
+        TcPart part;
+        part.plan = tp;
+        part.ci_chunks = cdiv(op.in.ch, 8);
+        if ((rc = get_tc_image(e, i, tp, -1, part.ci_chunks, &part.w))) { free_plan(p.get()); return rc; }
+        p->tc[i].push_back(part);
+      }
+      continue;
+    }
     if (op.kind != ARU_OP_CONV) continue;
     if (p->bufs[op.in.buf].kind != KIND_PLANAR || p->bufs[op.out.buf].kind != KIND_PLANAR) continue;
-    if (e->conv_path == 1) continue;
     const Geo& geo = p->bufs[op.out.buf].geo;
     const int cin_chunks = cdiv(op.in.ch, 8);
     for (int parts = 1; parts <= 4 && p->tc[i].empty(); parts *= 2) {

@@ -50,6 +50,7 @@ cudaError_t launch_unpack_nhwc(cudaStream_t st, PV in, const Geo& g, float* out)
 
 // ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) ---------------------------------------------
 struct ConvTcPlan {
+  bool deconv = false;   // 3x3 stride-2 transposed convolution (2x2 look-back taps x 4 output-parity classes)
   bool ok = false;       // false: shape not covered by the tensor-core kernel (caller must use another kernel)
   int ks = 0;
   int cin_chunks = 0;
@@ -70,10 +71,14 @@ struct ConvTcPlan {
 };
 
 // Decide whether / how the tcgen05 kernel runs conv (ks x ks, cin -> cout) on geometry g.
-ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, size_t max_smem);
+ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, size_t max_smem, bool deconv = false);
 // Pack input channels [ci_begin, ci_begin + 8*plan.cin_chunks) of a TF-layout filter [ks][ks][cin][cout]
 // (float32) into the kernel's shared-memory B image.
 void conv_tc_pack_weights(const ConvTcPlan& plan, const float* w_tf, int cin, int cout, int ci_begin, uint16_t* dst);
+// Transposed conv: filter [3][3][cout][cin] -> B image; launch over the *input* geometry gi, stores to go.
+void conv_tc_pack_deconv(const ConvTcPlan& plan, const float* w_tf, int cin, int cout, uint16_t* dst);
+cudaError_t launch_deconv_tc(cudaStream_t st, const ConvTcPlan& plan, PV in, PV out, const act_t* wpack,
+                             const float* bias_pad, const Geo& gi, const Geo& go, int act, int* err_flag);
 cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& plan, PV in, PV out, PV out_pre, PV res,
                            const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag);
 
