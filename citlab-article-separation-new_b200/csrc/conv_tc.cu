@@ -31,7 +31,8 @@
 //   warps 4..11   : two epilogue warpgroups (alternating passes): tcgen05.ld -> +bias (+res) -> act ->
 //                   16-bit pack -> 16 B coalesced global stores (in-image positions only; the zero frame of
 //                   the output tensor is never written)
-// All mbarrier waits are bounded: a protocol bug sets *err_flag and drains instead of hanging the GPU.
+// All mbarrier waits are bounded: a protocol bug records its barrier class in *err_flag and traps (the launch fails
+// loudly with a CUDA error) instead of hanging the GPU.
 #include <cstring>
 #include <vector>
 
@@ -56,11 +57,10 @@ constexpr int OFF_TFULL = OFF_EMPTY + 8 * MAX_UNITS;       // uint64 tmem_full[4
 constexpr int OFF_TEMPTY = OFF_TFULL + 32;                 // uint64 tmem_empty[4]
 constexpr int OFF_WFULL = OFF_TEMPTY + 32;                 // uint64 w_full[4]
 constexpr int OFF_WEMPTY = OFF_WFULL + 32;                 // uint64 w_empty[4]
-constexpr int OFF_TMEMPTR = OFF_WEMPTY + 32;               // uint32 tmem base, uint32 abort flag
-constexpr int OFF_STEPTAB = OFF_TMEMPTR + 16;              // int2 {A desc lo constant, window offset}[MAX_STEPS]
-constexpr int OFF_BTAB = OFF_STEPTAB + 8 * MAX_STEPS;      // uint32 B desc lo [MAX_STEPS]
-constexpr int OFF_BIAS = OFF_BTAB + 4 * MAX_STEPS;         // float bias[256]
+constexpr int OFF_TMEMPTR = OFF_WEMPTY + 32;               // uint32 tmem base
+constexpr int OFF_BIAS = OFF_TMEMPTR + 16;                 // float bias[256]
 constexpr int HDR_BYTES = ((OFF_BIAS + 4 * 256 + 127) / 128) * 128;
+constexpr int TAB_MAX = 768;         // A-operand start table entries (n_units * T * KS), lives in the kernel parameters
 
 struct ConvTcArgs {
   const act_t* in;
@@ -76,16 +76,21 @@ struct ConvTcArgs {
   int ks, cin_chunks, cout_chunks, npad, n_steps;
   int n_units, n_stages, tmem_cols;
   int w_stream, w_group, n_wst;   // weight streaming: steps per group, stages
-  int W, H, Wp, Hp;
+  int W, H, Wp, Hp, N;
   int lead, body_end, rel_bias;
   int pass_begin, pass_end;
   int dlo, dhi, min_off;
   int dc128, dr128, dcT, drT;     // (col,row) advance of 128 and 128*T positions
+  int dcS, drS;                   // (col,row) advance of 2*128*T positions (one epilogue warpgroup stride)
   int act;
   // transposed convolution (3x3 stride 2 as a 2x2 correlation with four output-parity classes in N)
   int deconv, cls_chunks, bias_pages;
   int Wo, Ho, Wpo, Hpo, lead_o, offy, offx;
   int* err_flag;
+  // Ring position (16-byte units) of the A operand of tile t, filter row ky, for ring phase s = pass % n_units:
+  // tab[(s*T + t)*KS + ky].  Precomputed on the host so that the issuer's descriptor arithmetic is
+  // base + table entry + compile-time tap offset: no ring-wrap arithmetic on the single issuing thread.
+  uint32_t tab[TAB_MAX];
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -116,25 +121,21 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: returns false (and raises the abort flags) when the barrier did not flip within 0.2 s.
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, volatile uint32_t* abort_smem, int* err_flag,
-                                            int code) {
+// Bounded wait: when the barrier did not flip within 0.2 s the barrier class is recorded and the kernel traps.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   const unsigned long long t0 = global_ns();
   while (true) {
     for (int i = 0; i < 64; ++i)
-      if (mbar_try_wait(bar, parity)) return true;
-    if (*abort_smem) return false;
+      if (mbar_try_wait(bar, parity)) return;
     if (global_ns() - t0 > 200000000ull) {
-      *abort_smem = 1;
       atomicCAS(err_flag, 0, code);
-      return false;
+      __threadfence_system();
+      __trap();
     }
   }
 }
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t* abort_smem, int* err_flag,
-                                          int code) {
-  if (mbar_try_wait(bar, parity)) return true;
-  return mbar_wait_slow(bar, parity, abort_smem, err_flag, code);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err_flag, code);
 }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
@@ -164,19 +165,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// One lane of a converged warp (the same lane every time for a full mask).  Issuing the TMA / UMMA
-// instructions under this predicate from warp-uniform control flow lets the compiler keep descriptors
-// in uniform registers instead of emitting a per-lane "waterfall" loop around every instruction.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // High word of a shared-memory matrix descriptor (no swizzle, K-major): SBO in 16-byte units at bits 32..45,
 // descriptor version 1 (sm_100) at bits 46..47.  Low word = start address >> 4 | (LBO >> 4) << 16.
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
@@ -193,14 +181,41 @@ __device__ __forceinline__ void walk_adv(int& col, int& rin, int& pg, int dc, in
   }
 }
 
+// ---- 16-bit packing of epilogue values -----------------------------------------------------------
+// two fp32 -> packed 16-bit pair, saturated to the finite range (fp16: an overflowing activation must not
+// become inf and poison later 0*x products), optionally ReLU'd.  max(.,0) commutes with the rounding.
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2_fin(float x, float y) {
+#ifdef ARU_USE_BF16
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  if (RELU) h = __hmax2(h, __floats2bfloat162_rn(0.f, 0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+#else
+  __half2 h = __floats2half2_rn(x, y);
+  const __half2 hi = __half2half2(__ushort_as_half((unsigned short)0x7bff));   // 65504
+  h = __hmin2(h, hi);
+  if (RELU) h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0)));
+  else h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0xfbff)));  // -65504
+  return *reinterpret_cast<uint32_t*>(&h);
+#endif
+}
+template <bool RELU>
+__device__ __forceinline__ uint4 pack8_fin(const float f[8], bool valid) {
+  uint4 v;
+  v.x = pack2_fin<RELU>(f[0], f[1]);
+  v.y = pack2_fin<RELU>(f[2], f[3]);
+  v.z = pack2_fin<RELU>(f[4], f[5]);
+  v.w = pack2_fin<RELU>(f[6], f[7]);
+  if (!valid) v = make_uint4(0u, 0u, 0u, 0u);   // frame / margin positions are (re)written with zeros
+  return v;
+}
+
 // ---- the kernel --------------------------------------------------------------------------------
 // MODE 0: C_in = 8 (paired taps)   1: resident weights, >= 2 input chunks   2: streamed weights
 template <int T, int KS, int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTcArgs a) {
   constexpr bool CIN1 = (MODE == 0);
   extern __shared__ __align__(128) uint8_t smem[];
-  // a previous launch hit a protocol timeout: do nothing (the host reports the error after the pass)
-  if (*reinterpret_cast<volatile int*>(a.err_flag) != 0) return;
 
   constexpr int UNIT = TILE * T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -209,7 +224,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
   const uint32_t s_tfull = s_base + OFF_TFULL, s_tempty = s_base + OFF_TEMPTY;
   const uint32_t s_wfull = s_base + OFF_WFULL, s_wempty = s_base + OFF_WEMPTY;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
-  volatile uint32_t* abort_smem = tmem_ptr + 1;
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
   const int step_bytes = 32 * a.npad;
   const int w_smem_bytes = a.w_stream ? a.n_wst * a.w_group * step_bytes : a.n_steps * step_bytes;
@@ -227,7 +241,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
-    *abort_smem = 0;
     for (int i = 0; i < a.n_units; ++i) {
       mbar_init(s_full + 8 * i, 1);
       mbar_init(s_empty + 8 * i, 1);
@@ -268,11 +281,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
       const long long first_pos = (long long)(u0 + a.dlo) * UNIT;  // ring origin in plane positions
       const uint32_t tx = (uint32_t)a.cin_chunks * UNIT * 16;
       const uint32_t tx_mirror = (uint32_t)a.cin_chunks * MIRROR * 16;
-      bool alive = true;
       int slot = 0;            // k % n_units and the parity of k / n_units, kept incrementally (no divisions
       uint32_t use_par = 0;    // in the steady-state loops of any role)
       auto load_unit = [&](int k) {
-        if (!mbar_wait(s_empty + 8 * slot, use_par ^ 1, abort_smem, a.err_flag, 1)) { alive = false; return; }
+        mbar_wait(s_empty + 8 * slot, use_par ^ 1, a.err_flag, 1);
         const uint32_t bar = s_full + 8 * slot;
         const act_t* src = a.in + (first_pos + (long long)k * UNIT) * 8;
         mbar_expect_tx(bar, slot == 0 ? tx + tx_mirror : tx);
@@ -284,16 +296,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
         if (++slot == a.n_units) { slot = 0; use_par ^= 1; }
       };
       if (!a.w_stream) {
-        for (int k = 0; k < n_load && alive; ++k) load_unit(k);
+        for (int k = 0; k < n_load; ++k) load_unit(k);
       } else {
         // consumption order: window of pass 0 (+ prefetch), then per pass its weight groups and one more unit
         int next = 0;
-        for (; next < min(n_load, a.n_units - 1) && alive; ++next) load_unit(next);
+        for (; next < min(n_load, a.n_units - 1); ++next) load_unit(next);
         int ws = 0;            // weight stage and its use parity
         uint32_t w_par = 0;
-        for (int pi = 0; pi < n_pass && alive; ++pi) {
-          for (int g = 0; g < n_groups && alive; ++g) {
-            if (!mbar_wait(s_wempty + 8 * ws, w_par ^ 1, abort_smem, a.err_flag, 5)) { alive = false; break; }
+        for (int pi = 0; pi < n_pass; ++pi) {
+          for (int g = 0; g < n_groups; ++g) {
+            mbar_wait(s_wempty + 8 * ws, w_par ^ 1, a.err_flag, 5);
             const int steps = min(a.w_group, a.n_steps - g * a.w_group);
             const uint32_t bytes = (uint32_t)(steps * step_bytes);
             mbar_expect_tx(s_wfull + 8 * ws, bytes);
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
                      reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)g * a.w_group * step_bytes, bytes, s_wfull + 8 * ws);
             if (++ws == a.n_wst) { ws = 0; w_par ^= 1; }
           }
-          if (next < n_load && alive) load_unit(next++);
+          if (next < n_load) load_unit(next++);
         }
       }
     } else if (warp == 0 && lane == 0) {
@@ -309,8 +321,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
       const uint32_t idesc = (1u << 4) | (ARU_UMMA_FMT << 7) | (ARU_UMMA_FMT << 10) | ((uint32_t)(a.npad >> 3) << 17) |
                              ((uint32_t)(TILE >> 4) << 24);
       const uint32_t hi = desc_hi(128);
-      const uint32_t uL = (uint32_t)L;
-      uint32_t ws = (uint32_t)(((-a.dlo) * UNIT + a.min_off) % L);  // ring position of the pass window start
       const uint32_t wstage_units = (uint32_t)(a.w_group * step_bytes) >> 4;
       const uint32_t step_units = (uint32_t)step_bytes >> 4;
       const uint32_t a_lbo = CIN1 ? 16u : (uint32_t)ring_plane * 16u;
@@ -318,66 +328,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
       const uint32_t b_lo0 = (s_w >> 4) | ((((uint32_t)a.npad * 16u) >> 4) << 16);
       const uint32_t cp_stride = (uint32_t)(2 * ring_plane);  // descriptor units between channel-chunk pairs
       const int n_cp = CIN1 ? 1 : a.cin_chunks / 2;
-      const uint32_t uWp = (uint32_t)a.Wp, npad = (uint32_t)a.npad;
-      bool alive = true;
+      const uint32_t npad = (uint32_t)a.npad;
       // incremental ring bookkeeping (no divisions in the loop)
-      int stage = 0, f_slot = 0, e_slot = 0, wst = 0;
+      int stage = 0, f_slot = 0, e_slot = 0, wst = 0, phase = 0;
       uint32_t stage_par = 0, f_par = 0, w_par = 0;
-      for (int pi = 0; pi < n_pass && alive; ++pi) {
-        alive = mbar_wait(s_tempty + 8 * stage, stage_par ^ 1, abort_smem, a.err_flag, 2);
+      for (int pi = 0; pi < n_pass; ++pi) {
+        mbar_wait(s_tempty + 8 * stage, stage_par ^ 1, a.err_flag, 2);
         // operands: pass pi reads units pi .. pi+win-1 (the first pass waits for its whole window)
-        for (int k = (pi == 0 ? 0 : win - 1); k < win && alive; ++k) {
-          alive = mbar_wait(s_full + 8 * f_slot, f_par, abort_smem, a.err_flag, 3);
+        for (int k = (pi == 0 ? 0 : win - 1); k < win; ++k) {
+          mbar_wait(s_full + 8 * f_slot, f_par, a.err_flag, 3);
           if (++f_slot == a.n_units) { f_slot = 0; f_par ^= 1; }
         }
-        if (!alive) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(stage * T) * npad;
+        const uint32_t* tab = a.tab + phase * (T * KS);
         // K loop in the order the B image was packed: taps (ky, kx) unrolled at compile time, channel-chunk
         // pairs inside.  C_in = 8 (CIN1): horizontally adjacent taps are paired into one K=16 step (the B
         // image holds zeros for the missing partner of the last tap of an odd-width kernel).
         uint32_t b_lo = b_lo0;
 #pragma unroll
         for (int ky = 0; ky < KS; ++ky) {
+          uint32_t a_row[T];
+#pragma unroll
+          for (int t = 0; t < T; ++t) a_row[t] = a_lo0 + tab[t * KS + ky];
 #pragma unroll
           for (int kx = 0; kx < KS; kx += (CIN1 ? 2 : 1)) {
-            uint32_t a_pos[T];
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-              uint32_t pos = ws + (uint32_t)ky * uWp + (uint32_t)(kx + t * TILE);  // position inside the ring
-              pos = min(pos, pos - uL);                                             // wrap (unsigned): pos < 2L
-              a_pos[t] = a_lo0 + pos;
-            }
             if constexpr (MODE == 0) {
 #pragma unroll
               for (int t = 0; t < T; ++t)
-                umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_pos[t]), desc64(hi, b_lo), idesc, (ky | kx) ? 1u : 0u);
+                umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx), desc64(hi, b_lo), idesc,
+                         (ky | kx) ? 1u : 0u);
               b_lo += step_units;
             } else if constexpr (MODE == 1) {
-              // rolled over the channel-chunk pairs (keeps the kernel small enough for the instruction cache);
-              // with one tile per pass two pairs are issued per iteration to amortise the loop overhead
-              int cp = 0;
-              if constexpr (T == 1) {
-                for (; cp + 1 < n_cp; cp += 2) {
-                  umma_f16(d_tmem, desc64(hi, a_pos[0] + (uint32_t)cp * cp_stride), desc64(hi, b_lo), idesc, (ky | kx | cp) ? 1u : 0u);
-                  umma_f16(d_tmem, desc64(hi, a_pos[0] + (uint32_t)(cp + 1) * cp_stride), desc64(hi, b_lo + step_units), idesc, 1u);
-                  b_lo += 2 * step_units;
-                }
-              }
+              // rolled over the channel-chunk pairs (keeps the kernel small enough for the instruction cache)
 #pragma unroll 1
-              for (; cp < n_cp; ++cp) {
+              for (int cp = 0; cp < n_cp; ++cp) {
                 const uint32_t acc = (ky | kx | cp) ? 1u : 0u;
 #pragma unroll
                 for (int t = 0; t < T; ++t)
-                  umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_pos[t] + (uint32_t)cp * cp_stride), desc64(hi, b_lo), idesc, acc);
+                  umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx + (uint32_t)cp * cp_stride),
+                           desc64(hi, b_lo), idesc, acc);
                 b_lo += step_units;
               }
             } else {
               // streamed weights: groups of w_group steps (w_group divides n_cp, so a group never straddles taps)
 #pragma unroll 1
-              for (int cp0 = 0; cp0 < n_cp && alive; cp0 += a.w_group) {
-                alive = mbar_wait(s_wfull + 8 * wst, w_par, abort_smem, a.err_flag, 6);
-                if (!alive) break;
+              for (int cp0 = 0; cp0 < n_cp; cp0 += a.w_group) {
+                mbar_wait(s_wfull + 8 * wst, w_par, a.err_flag, 6);
                 tc_fence_after();
                 b_lo = b_lo0 + (uint32_t)wst * wstage_units;
 #pragma unroll 1
@@ -385,7 +382,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
                   const uint32_t acc = (ky | kx | cp) ? 1u : 0u;
 #pragma unroll
                   for (int t = 0; t < T; ++t)
-                    umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_pos[t] + (uint32_t)cp * cp_stride), desc64(hi, b_lo), idesc, acc);
+                    umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx + (uint32_t)cp * cp_stride),
+                             desc64(hi, b_lo), idesc, acc);
                   b_lo += step_units;
                 }
                 umma_commit(s_wempty + 8 * wst);  // stage may be refilled once these MMAs retire
@@ -394,22 +392,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
             }
           }
         }
-        if (!alive) break;
         umma_commit(s_empty + 8 * e_slot);  // unit pi is not needed by later passes
         umma_commit(s_tfull + 8 * stage);   // accumulators ready for the epilogue
         if (++e_slot == a.n_units) e_slot = 0;
         if (++stage == a.n_stages) { stage = 0; stage_par ^= 1; }
-        ws += UNIT;
-        ws -= (ws >= uL) ? uL : 0u;
+        if (++phase == a.n_units) phase = 0;
       }
     } else if (warp >= 4) {
       // ================= epilogue =================
-      // Deliberately compact (rolled loops): ten warps run four different code regions of this kernel, and an
-      // unrolled epilogue made instruction-cache misses (stall_no_inst) its dominant stall.
       const int wg = (warp - 4) >> 2;  // warpgroup 0/1 -> even/odd passes
       const int q = warp & 3;          // TMEM lane quarter this warp may access
       const int m = q * 32 + lane;
-      // (col, rin) of this lane's position in tile 0 of its first pass; rel_bias makes the numerator non-negative
+      // (col, rin, pg) of this lane's position in tile 0 of its first pass; rel_bias makes the numerator non-negative
       int p = (u0 + wg) * UNIT + m;
       int col, rin, pg;
       {
@@ -420,31 +414,96 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
         rin = row - pg * a.Hp;
         pg -= a.bias_pages;
       }
-      auto in_image = [&](int pp, int c, int r) {
-        return (c >= 1) && (c <= a.W) && (r >= 1) && (r <= a.H) && (pp >= a.lead) && (pp < a.body_end);
-      };
-      // residual operand of the *next* tile is fetched one tile ahead (chunk 0) / one chunk ahead (others)
-      bool v_next = in_image(p, col, rin);
-      uint4 r_next = make_uint4(0, 0, 0, 0);
-      if (a.res && v_next) r_next = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)p * 8));
-      bool alive = true;
       int stage = wg;             // pi % n_stages and the parity of pi / n_stages (n_stages is 2 or 4)
       uint32_t stage_par = 0;
-      for (int pi = wg; pi < n_pass && alive; pi += 2) {
-        alive = mbar_wait(s_tfull + 8 * stage, stage_par, abort_smem, a.err_flag, 4);
-        alive = __shfl_sync(0xffffffffu, alive ? 1 : 0, 0) != 0;
-        if (!alive) break;
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
+      if (!a.deconv) {
+        // One lane = one position of each of the T tiles of the pass (unrolled: T independent chains).  Every
+        // position of the pass range is stored: in-image ones with the result, frame / margin ones with zero
+        // (they are zero anyway), so there is no divergence and no bounds logic beyond three range checks.
+        const bool has_res = a.res != nullptr, has_pre = a.out_pre != nullptr, relu = a.act == 1;
+        for (int pi = wg; pi < n_pass; pi += 2) {
+          long long pt[T];
+          bool vt[T];
+          {
+            int c2 = col, r2 = rin, g2 = pg;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              pt[t] = (long long)(p + t * TILE) * 8;
+              vt[t] = ((unsigned)(c2 - 1) < (unsigned)a.W) && ((unsigned)(r2 - 1) < (unsigned)a.H) && ((unsigned)g2 < (unsigned)a.N);
+              walk_adv(c2, r2, g2, a.dc128, a.dr128, a.Wp, a.Hp);
+            }
+          }
+          uint4 rr[T];
+          if (has_res) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) rr[t] = __ldg(reinterpret_cast<const uint4*>(a.res + pt[t]));
+          }
+          mbar_wait(s_tfull + 8 * stage, stage_par, a.err_flag, 4);
+          __syncwarp();
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
 #pragma unroll 1
-        for (int t = 0; t < T; ++t) {
-          if (a.deconv) {
-            // this lane's *input* pixel (j, i) = (rin-1, col-1), including the frame row / column j = H, i = W;
-            // it owns the four outputs full[2j+py, 2i+px], cropped by (offy, offx)  (layers.py:342-367)
-            const bool in_dom = (p >= a.lead) && (p < a.body_end) && (col >= 1) && (col <= a.W + 1) && (rin >= 1) &&
-                                (rin <= a.H + 1);
-            const int oy0 = 2 * (rin - 1) - a.offy, ox0 = 2 * (col - 1) - a.offx;
-            const long long po0 = (long long)a.lead_o + ((long long)pg * a.Hpo + oy0 + 1) * a.Wpo + ox0 + 1;
+          for (int c = 0; c < a.cout_chunks; ++c) {
+            uint32_t v[T][8];
+#pragma unroll
+            for (int t = 0; t < T; ++t) tmem_ld8(taddr + (uint32_t)(t * a.npad + c * 8), v[t]);
+            uint4 rn[T];
+            if (has_res && c + 1 < a.cout_chunks) {
+#pragma unroll
+              for (int t = 0; t < T; ++t)
+                rn[t] = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)(c + 1) * a.res_plane * 8 + pt[t]));
+            }
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
+            tmem_ld_wait();
+            if (c == a.cout_chunks - 1) {  // last TMEM read of this stage: hand the accumulators back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              float acc[8];
+              acc[0] = __uint_as_float(v[t][0]) + b0.x; acc[1] = __uint_as_float(v[t][1]) + b0.y;
+              acc[2] = __uint_as_float(v[t][2]) + b0.z; acc[3] = __uint_as_float(v[t][3]) + b0.w;
+              acc[4] = __uint_as_float(v[t][4]) + b1.x; acc[5] = __uint_as_float(v[t][5]) + b1.y;
+              acc[6] = __uint_as_float(v[t][6]) + b1.z; acc[7] = __uint_as_float(v[t][7]) + b1.w;
+              if (has_res) {
+                float r[8];
+                unpack8(rr[t], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += r[j];
+              }
+              if (has_pre)
+                *reinterpret_cast<uint4*>(a.out_pre + (long long)c * a.pre_plane * 8 + pt[t]) = pack8_fin<false>(acc, vt[t]);
+              const uint4 o = relu ? pack8_fin<true>(acc, vt[t]) : pack8_fin<false>(acc, vt[t]);
+              *reinterpret_cast<uint4*>(a.out + (long long)c * a.out_plane * 8 + pt[t]) = o;
+            }
+            if (has_res) {
+#pragma unroll
+              for (int t = 0; t < T; ++t) rr[t] = rn[t];
+            }
+          }
+          walk_adv(col, rin, pg, a.dcS, a.drS, a.Wp, a.Hp);
+          p += 2 * UNIT;
+          stage += 2;
+          if (stage >= a.n_stages) { stage -= a.n_stages; stage_par ^= 1; }
+        }
+      } else {
+        // transposed convolution: this lane's *input* pixel (j, i) = (rin-1, col-1), including the frame row /
+        // column j = H, i = W; it owns the four outputs full[2j+py, 2i+px], cropped by (offy, offx)
+        // (layers.py:342-367).  Deliberately compact (rolled loops).
+        for (int pi = wg; pi < n_pass; pi += 2) {
+          mbar_wait(s_tfull + 8 * stage, stage_par, a.err_flag, 4);
+          __syncwarp();
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
+          int c2 = col, r2 = rin, g2 = pg;
+#pragma unroll 1
+          for (int t = 0; t < T; ++t) {
+            const bool in_dom = ((unsigned)g2 < (unsigned)a.N) && (c2 >= 1) && (c2 <= a.W + 1) && (r2 >= 1) && (r2 <= a.H + 1);
+            const int oy0 = 2 * (r2 - 1) - a.offy, ox0 = 2 * (c2 - 1) - a.offx;
+            const long long po0 = (long long)a.lead_o + ((long long)g2 * a.Hpo + oy0 + 1) * a.Wpo + ox0 + 1;
 #pragma unroll 1
             for (int cls = 0; cls < 4; ++cls) {
               const int oy = oy0 + (cls >> 1), ox = ox0 + (cls & 1);
@@ -463,69 +522,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const ConvTcArgs a) 
                 if (v) {
                   float acc[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    acc[j] = __uint_as_float(v8[j]) + s_bias[c * 8 + j];
-                    if (a.act == 1) acc[j] = fmaxf(acc[j], 0.f);
-                  }
-                  *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + po) * 8) = pack8(acc);
+                  for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(v8[j]) + s_bias[c * 8 + j];
+                  *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + po) * 8) =
+                      a.act == 1 ? pack8_fin<true>(acc, true) : pack8_fin<false>(acc, true);
                 }
               }
             }
-            walk_adv(col, rin, pg, a.dc128, a.dr128, a.Wp, a.Hp);
-            p += TILE;
-            if (t == T - 1) {
-              walk_adv(col, rin, pg, a.dcT, a.drT, a.Wp, a.Hp);
-              p += UNIT;
-            }
-            continue;
+            walk_adv(c2, r2, g2, a.dc128, a.dr128, a.Wp, a.Hp);
           }
-          const int pt = p;
-          const bool valid = v_next;
-          uint4 r_cur = r_next;
-          // step to the next tile of this warpgroup (the other warpgroup's pass is skipped after tile T-1)
-          walk_adv(col, rin, pg, a.dc128, a.dr128, a.Wp, a.Hp);
-          p += TILE;
-          if (t == T - 1) {
-            walk_adv(col, rin, pg, a.dcT, a.drT, a.Wp, a.Hp);
-            p += UNIT;
-          }
-          v_next = in_image(p, col, rin);
-          if (a.res && v_next) r_next = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)p * 8));
-#pragma unroll 1
-          for (int c = 0; c < a.cout_chunks; ++c) {
-            uint32_t v[8];
-            tmem_ld8(taddr + (uint32_t)(t * a.npad + c * 8), v);
-            uint4 r_c1 = make_uint4(0, 0, 0, 0);
-            if (a.res && valid && c + 1 < a.cout_chunks)
-              r_c1 = __ldg(reinterpret_cast<const uint4*>(a.res + ((long long)(c + 1) * a.res_plane + pt) * 8));
-            tmem_ld_wait();
-            if (t == T - 1 && c == a.cout_chunks - 1) {  // last TMEM read of this stage: hand the accumulators back
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
-            }
-            if (valid) {
-              float acc[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(v[j]) + s_bias[c * 8 + j];
-              if (a.res) {
-                float r[8];
-                unpack8(r_cur, r);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += r[j];
-              }
-              if (a.out_pre) *reinterpret_cast<uint4*>(a.out_pre + ((long long)c * a.pre_plane + pt) * 8) = pack8(acc);
-              if (a.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-              }
-              *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + pt) * 8) = pack8(acc);
-            }
-            r_cur = r_c1;
-          }
+          walk_adv(col, rin, pg, a.dcS, a.drS, a.Wp, a.Hp);
+          stage += 2;
+          if (stage >= a.n_stages) { stage -= a.n_stages; stage_par ^= 1; }
         }
-        stage += 2;
-        if (stage >= a.n_stages) { stage -= a.n_stages; stage_par ^= 1; }
       }
     }
   }
@@ -610,7 +618,7 @@ ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, si
       if (stream && T > 2) continue;
       const Window w = make_window(ks, p.cin_chunks, g.Wp, TILE * T);
       const int n_units = w.win + pf;
-      if (n_units > MAX_UNITS) continue;
+      if (n_units > MAX_UNITS || n_units * T * ks > TAB_MAX) continue;
       const size_t ring = (size_t)p.cin_chunks * (n_units * TILE * T + MIRROR) * 16;
       const size_t smem = HDR_BYTES + (stream ? w_streamed : w_resident) + ring;
       if (smem > max_smem) continue;
@@ -623,7 +631,7 @@ ConvTcPlan conv_tc_plan(int ks, int cin, int cout, const Geo& g, int num_sms, si
       // Deepen the prefetch with whatever shared memory is left: HBM latency under load is ~1-2 us, so a
       // CTA needs tens of KB of loads in flight to sustain its share (~45 GB/s) of the memory bandwidth.
       const size_t unit_bytes = (size_t)p.cin_chunks * TILE * T * 16;
-      while (p.n_slots < MAX_UNITS && p.smem_bytes + unit_bytes <= max_smem &&
+      while (p.n_slots < MAX_UNITS && (p.n_slots + 1) * T * ks <= TAB_MAX && p.smem_bytes + unit_bytes <= max_smem &&
              (size_t)(p.n_slots + 1 - w.win) * unit_bytes <= 96 * 1024) {
         ++p.n_slots;
         p.smem_bytes += unit_bytes;
@@ -733,7 +741,7 @@ static cudaError_t launch_tc_common(cudaStream_t st, const ConvTcPlan& p, ConvTc
   int pow2 = 32;
   while (pow2 < cols) pow2 <<= 1;
   a.tmem_cols = pow2;
-  a.W = g.W; a.H = g.H; a.Wp = g.Wp; a.Hp = g.Hp;
+  a.W = g.W; a.H = g.H; a.Wp = g.Wp; a.Hp = g.Hp; a.N = g.N;
   a.lead = (int)g.lead;
   a.body_end = (int)(g.lead + (long long)g.N * g.Hp * g.Wp);
   const long long page = (long long)g.Wp * g.Hp;
@@ -744,8 +752,20 @@ static cudaError_t launch_tc_common(cudaStream_t st, const ConvTcPlan& p, ConvTc
   a.dlo = w.dlo; a.dhi = w.dhi; a.min_off = w.min_off;
   a.dc128 = TILE % g.Wp; a.dr128 = TILE / g.Wp;
   a.dcT = unit % g.Wp; a.drT = unit / g.Wp;
+  a.dcS = (2 * unit) % g.Wp; a.drS = (2 * unit) / g.Wp;
+  {
+    // ring position of the A operand of (phase s, tile t, filter row ky); the tap column kx is added by the issuer
+    // (the mirror behind the ring keeps start + kx + 127 contiguous)
+    const long long L = (long long)p.n_slots * unit;
+    const long long ws0 = ((((long long)(-w.dlo) * unit + w.min_off) % L) + L) % L;
+    if (p.n_slots * p.T * p.ks > TAB_MAX) return cudaErrorInvalidValue;
+    for (int s = 0; s < p.n_slots; ++s)
+      for (int t = 0; t < p.T; ++t)
+        for (int ky = 0; ky < p.ks; ++ky)
+          a.tab[(s * p.T + t) * p.ks + ky] = (uint32_t)((ws0 + (long long)s * unit + (long long)t * TILE + (long long)ky * g.Wp) % L);
+  }
   a.bias_pages = (int)(a.rel_bias / page);
-  using Kern = void (*)(const ConvTcArgs);
+  using Kern = void (*)(const __grid_constant__ ConvTcArgs);
   Kern k = nullptr;
   const int mode = p.cin_chunks == 1 ? 0 : (p.w_stream ? 2 : 1);
 #define ARU_TC_PICK(TT, KK, MM) if (p.T == TT && p.ks == KK && mode == MM) k = k_conv_tc<TT, KK, MM>;
