@@ -165,6 +165,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp.  Issuing the UMMA instructions under this predicate from warp-uniform control flow
+// lets the compiler keep descriptors in uniform registers instead of a per-lane waterfall around every instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // High word of a shared-memory matrix descriptor (no swizzle, K-major): SBO in 16-byte units at bits 32..45,
 // descriptor version 1 (sm_100) at bits 46..47.  Low word = start address >> 4 | (LBO >> 4) << 16.
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
@@ -218,7 +230,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
   extern __shared__ __align__(128) uint8_t smem[];
 
   constexpr int UNIT = TILE * T;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
+  const int lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_full = s_base + OFF_FULL, s_empty = s_base + OFF_EMPTY;
   const uint32_t s_tfull = s_base + OFF_TFULL, s_tempty = s_base + OFF_TEMPTY;
@@ -316,8 +329,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
           if (next < n_load) load_unit(next++);
         }
       }
-    } else if (warp == 0 && lane == 0) {
+    } else if (warp == 0) {
       // ================= MMA issuer =================
+      // The whole warp runs this role convergently and one elected lane issues each instruction: ptxas then keeps
+      // descriptors in uniform registers and emits back-to-back UTCHMMAs (39 cycles / MMA at N = 16 measured by
+      // tools/mma_issue_bench.cu variant 3, against 50 for a single-lane region with its per-instruction waterfall).
       const uint32_t idesc = (1u << 4) | (ARU_UMMA_FMT << 7) | (ARU_UMMA_FMT << 10) | ((uint32_t)(a.npad >> 3) << 17) |
                              ((uint32_t)(TILE >> 4) << 24);
       const uint32_t hi = desc_hi(128);
@@ -356,7 +372,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
             if constexpr (MODE == 0) {
 #pragma unroll
               for (int t = 0; t < T; ++t)
-                umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx), desc64(hi, b_lo), idesc,
+                if (elect_one()) umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx), desc64(hi, b_lo), idesc,
                          (ky | kx) ? 1u : 0u);
               b_lo += step_units;
             } else if constexpr (MODE == 1) {
@@ -366,7 +382,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                 const uint32_t acc = (ky | kx | cp) ? 1u : 0u;
 #pragma unroll
                 for (int t = 0; t < T; ++t)
-                  umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx + (uint32_t)cp * cp_stride),
+                  if (elect_one()) umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx + (uint32_t)cp * cp_stride),
                            desc64(hi, b_lo), idesc, acc);
                 b_lo += step_units;
               }
@@ -382,18 +398,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                   const uint32_t acc = (ky | kx | cp) ? 1u : 0u;
 #pragma unroll
                   for (int t = 0; t < T; ++t)
-                    umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx + (uint32_t)cp * cp_stride),
+                    if (elect_one()) umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx + (uint32_t)cp * cp_stride),
                              desc64(hi, b_lo), idesc, acc);
                   b_lo += step_units;
                 }
-                umma_commit(s_wempty + 8 * wst);  // stage may be refilled once these MMAs retire
+                if (elect_one()) umma_commit(s_wempty + 8 * wst);  // stage may be refilled once these MMAs retire
                 if (++wst == a.n_wst) { wst = 0; w_par ^= 1; }
               }
             }
           }
         }
-        umma_commit(s_empty + 8 * e_slot);  // unit pi is not needed by later passes
-        umma_commit(s_tfull + 8 * stage);   // accumulators ready for the epilogue
+        if (elect_one()) {
+          umma_commit(s_empty + 8 * e_slot);  // unit pi is not needed by later passes
+          umma_commit(s_tfull + 8 * stage);   // accumulators ready for the epilogue
+        }
         if (++e_slot == a.n_units) e_slot = 0;
         if (++stage == a.n_stages) { stage = 0; stage_par ^= 1; }
         if (++phase == a.n_units) phase = 0;
