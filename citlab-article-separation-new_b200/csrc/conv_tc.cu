@@ -86,6 +86,9 @@ struct ConvTcArgs {
   // transposed convolution (3x3 stride 2 as a 2x2 correlation with four output-parity classes in N)
   int deconv, cls_chunks, bias_pages;
   int Wo, Ho, Wpo, Hpo, lead_o, offy, offx;
+  // dense float32 NHWC output [N][H][W][f32_c] with the head activation (classifier / attention logit), else null
+  float* out_f32;
+  int f32_c;
   int* err_flag;
   // Ring position (16-byte units) of the A operand of tile t, filter row ky, for ring phase s = pass % n_units:
   // tab[(s*T + t)*KS + ky].  Precomputed on the host so that the issuer's descriptor arithmetic is
@@ -434,7 +437,70 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
       }
       int stage = wg;             // pi % n_stages and the parity of pi / n_stages (n_stages is 2 or 4)
       uint32_t stage_par = 0;
-      if (!a.deconv) {
+      if (a.out_f32) {
+        // Small-C_out head (attention logit: ReLU; classifier: softmax / sigmoid over the classes, fp32) written
+        // as dense float32 NHWC: lane = pixel, so a warp stores 32 consecutive pixels.
+        const int C = a.f32_c;
+        for (int pi = wg; pi < n_pass; pi += 2) {
+          long long px[T];
+          bool vt[T];
+          {
+            int c2 = col, r2 = rin, g2 = pg;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              vt[t] = ((unsigned)(c2 - 1) < (unsigned)a.W) && ((unsigned)(r2 - 1) < (unsigned)a.H) && ((unsigned)g2 < (unsigned)a.N);
+              px[t] = (((long long)g2 * a.H + (r2 - 1)) * a.W + (c2 - 1)) * C;
+              walk_adv(c2, r2, g2, a.dc128, a.dr128, a.Wp, a.Hp);
+            }
+          }
+          mbar_wait(s_tfull + 8 * stage, stage_par, a.err_flag, 4);
+          __syncwarp();
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
+          uint32_t v[T][8];
+#pragma unroll
+          for (int t = 0; t < T; ++t) tmem_ld8(taddr + (uint32_t)(t * a.npad), v[t]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(v[t][j]) + s_bias[j];
+            if (a.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+            } else if (a.act == 2) {  // softmax over the C classes (layers.py:48-49)
+              float mx = acc[0];
+#pragma unroll
+              for (int j = 1; j < 8; ++j) if (j < C) mx = fmaxf(mx, acc[j]);
+              float sum = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (j < C) { acc[j] = expf(acc[j] - mx); sum += acc[j]; }
+              const float inv = 1.f / sum;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] *= inv;
+            } else if (a.act == 3) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = 1.f / (1.f + expf(-acc[j]));
+            }
+            if (vt[t]) {
+              float* o = a.out_f32 + px[t];
+              if (C == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+              else if (C == 1) *o = acc[0];
+              else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < C) o[j] = acc[j];
+              }
+            }
+          }
+          walk_adv(col, rin, pg, a.dcS, a.drS, a.Wp, a.Hp);
+          stage += 2;
+          if (stage >= a.n_stages) { stage -= a.n_stages; stage_par ^= 1; }
+        }
+      } else if (!a.deconv) {
         // One lane = one position of each of the T tiles of the pass (unrolled: T independent chains).  Every
         // position of the pass range is stored: in-image ones with the result, frame / margin ones with zero
         // (they are zero anyway), so there is no divergence and no bounds logic beyond three range checks.
@@ -745,6 +811,18 @@ cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& p, PV in, PV out, 
   a.out = out.p; a.out_plane = out.plane;
   a.out_pre = out_pre.p; a.pre_plane = out_pre.plane;
   a.res = res.p; a.res_plane = res.plane;
+  a.wpack = wpack; a.bias = bias_pad;
+  a.act = act;
+  a.err_flag = err_flag;
+  return launch_tc_common(st, p, a, g);
+}
+
+cudaError_t launch_conv_tc_f32(cudaStream_t st, const ConvTcPlan& p, PV in, float* out_f32, int cout, const act_t* wpack,
+                               const float* bias_pad, const Geo& g, int act, int* err_flag) {
+  if (!p.ok || p.deconv || cout < 1 || cout > 8 || p.cout_chunks != 1) return cudaErrorInvalidValue;
+  ConvTcArgs a{};
+  a.in = in.p; a.in_plane = in.plane;
+  a.out_f32 = out_f32; a.f32_c = cout;
   a.wpack = wpack; a.bias = bias_pad;
   a.act = act;
   a.err_flag = err_flag;

@@ -256,7 +256,12 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
       if (bi.kind == KIND_F32) {
         label = "conv_stem";
         err = launch_conv_stem(st, op.ksize, f32_ptr(e, p, op.in.buf, parity), make_pv(e, p, op.out),
-                               make_pv(e, p, op.out_pre), ow.w32, ow.bias, bo.geo, op.act);
+                               make_pv(e, p, op.out_pre), e->weights.data() + op.w_off, e->weights.data() + op.b_off,
+                               bo.geo, op.act);
+      } else if (bo.kind != KIND_PLANAR && !p->tc[oi].empty()) {
+        label = "conv_tc_head";
+        err = launch_conv_tc_f32(st, p->tc[oi][0].plan, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), op.out.ch,
+                                 p->tc[oi][0].w, ow.bias, bi.geo, op.act, e->err_flag);
       } else if (bo.kind != KIND_PLANAR) {
         label = "conv_small";
         err = launch_conv_small(st, op.ksize, op.out.ch, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), ow.w32,
@@ -493,7 +498,19 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       continue;
     }
     if (op.kind != ARU_OP_CONV) continue;
-    if (p->bufs[op.in.buf].kind != KIND_PLANAR || p->bufs[op.out.buf].kind != KIND_PLANAR) continue;
+    if (p->bufs[op.in.buf].kind != KIND_PLANAR) continue;
+    if (p->bufs[op.out.buf].kind != KIND_PLANAR) {
+      // float32-output head (attention logit, classifier): one launch, no split-K
+      ConvTcPlan tp = conv_tc_plan(op.ksize, op.in.ch, op.out.ch, p->bufs[op.in.buf].geo, e->num_sms, e->max_smem);
+      if (tp.ok && tp.cout_chunks == 1) {
+        TcPart part;
+        part.plan = tp;
+        part.ci_chunks = cdiv(op.in.ch, 8);
+        if ((rc = get_tc_image(e, i, tp, 0, part.ci_chunks, &part.w))) { free_plan(p.get()); return rc; }
+        p->tc[i].push_back(part);
+      }
+      continue;
+    }
     const Geo& geo = p->bufs[op.out.buf].geo;
     const int cin_chunks = cdiv(op.in.ch, 8);
     for (int parts = 1; parts <= 4 && p->tc[i].empty(); parts *= 2) {

@@ -12,6 +12,7 @@ struct PV {
   int C = 0;            // logical channels
 };
 
+#define ARU_COMBINE_MAX 8
 struct CombineArgs {
   const float* att[8];
   const act_t* det[8];
@@ -19,6 +20,7 @@ struct CombineArgs {
   Geo det_geo[8];
   int att_h[8], att_w[8], att_up[8], att_oy[8], att_ox[8];
   int det_up[8], det_oy[8], det_ox[8], det_chunks[8];
+  int att_sh[8], det_sh[8];  // log2 of the upsample factors (-1: not a power of two), filled by launch_combine
   int A;
   act_t* out;
   long long out_plane;
@@ -27,8 +29,9 @@ struct CombineArgs {
 };
 
 // ---- CUDA-core kernels (kernels_simple.cu) -------------------------------------------------------
-cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w,
-                             const float* bias, const Geo& g, int act);
+// w_host / bias_host: HOST pointers to the TF filter [ks][ks][1][C_out] and bias [C_out] (passed as kernel parameters)
+cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w_host,
+                             const float* bias_host, const Geo& g, int act);
 cudaError_t launch_conv_direct(cudaStream_t st, int ks, PV in, PV out, PV out_pre, PV res, const act_t* w,
                                const float* bias, const Geo& g, int act);
 cudaError_t launch_conv_small(cudaStream_t st, int ks, int cout, PV in, float* out, const float* w, const float* bias,
@@ -81,6 +84,10 @@ cudaError_t launch_deconv_tc(cudaStream_t st, const ConvTcPlan& plan, PV in, PV 
                              const float* bias_pad, const Geo& gi, const Geo& go, int act, int* err_flag);
 cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& plan, PV in, PV out, PV out_pre, PV res,
                            const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag);
+
+// Small-C_out head (C_out <= 8) writing dense float32 NHWC with ReLU / softmax / sigmoid (enum aru_act) in the epilogue.
+cudaError_t launch_conv_tc_f32(cudaStream_t st, const ConvTcPlan& plan, PV in, float* out_f32, int cout,
+                               const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag);
 
 // host-side 16-bit conversion matching act_t
 uint16_t host_f_to_act(float v);

@@ -27,47 +27,56 @@ static __device__ __forceinline__ void pix_coords(long long i, int H, int W, int
 
 // ---------------------------------------------------------------------------------------------
 // Stem conv: C_in = 1 float32 plane -> C_out <= 16 chunk-planar.  layers.py:191-247 with the 1-channel
-// inputs of ARU_v1.py:173 (attention conv1, 4x4) and :212 (unet_down_0/conv1, 3x3).  HBM-bound.
-// Weights float32 [tap][cpad], bias [cpad].
+// inputs of ARU_v1.py:173 (attention conv1, 4x4) and :212 (unet_down_0/conv1, 3x3).  HBM-bound by bytes
+// (4 B in, 16-32 B out per pixel), so the work is to keep the FMA count off the critical path: the
+// filter lives in the kernel parameters (constant bank), every FFMA takes its weight as a constant
+// operand (no shared-memory or register traffic for weights), the loops are fully unrolled over the
+// real C_out, and the input taps come from a shared-memory row tile loaded once per block.
+// One block = 128 consecutive pixels of one image row; grid = (ceil(W/128), H, N): no index divisions.
 // ---------------------------------------------------------------------------------------------
-template <int KS>
-__global__ void __launch_bounds__(256) k_conv_stem(const float* __restrict__ in, act_t* __restrict__ out,
+struct StemW {
+  float w[16 * 16];  // [tap][16]
+  float b[16];
+};
+
+template <int KS, int COUT>
+__global__ void __launch_bounds__(128) k_conv_stem(const float* __restrict__ in, act_t* __restrict__ out,
                                                    long long out_plane, act_t* __restrict__ out_pre,
-                                                   long long pre_plane, const float* __restrict__ w,
-                                                   const float* __restrict__ bias, Geo g, int chunks, int act) {
-  __shared__ float sw[KS * KS * 16];
-  __shared__ float sb[16];
-  const int cpad = chunks * 8;
-  for (int i = threadIdx.x; i < KS * KS * cpad; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < cpad; i += blockDim.x) sb[i] = bias[i];
-  __syncthreads();
-  const long long total = (long long)g.N * g.H * g.W;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int n, y, x;
-  pix_coords(i, g.H, g.W, n, y, x);
+                                                   long long pre_plane, const __grid_constant__ StemW sw, Geo g,
+                                                   int act) {
+  constexpr int CH = (COUT + 7) / 8, PB = (KS - 1) / 2, TW = 128 + KS - 1;
+  __shared__ float tile[KS][TW + 1];
+  const int n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 128;
   const float* img = in + (long long)n * g.H * g.W;
-  constexpr int PB = (KS - 1) / 2;
+  for (int i = threadIdx.x; i < KS * TW; i += 128) {
+    const int r = i / TW, c = i - r * TW;
+    const int yy = y + r - PB, xx = x0 + c - PB;
+    tile[r][c] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? __ldg(img + (long long)yy * g.W + xx) : 0.f;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x;
+  if (x >= g.W) return;
   float v[KS * KS];
 #pragma unroll
   for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < KS; ++kx) {
-      const int yy = y + ky - PB, xx = x + kx - PB;
-      v[ky * KS + kx] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? __ldg(img + (long long)yy * g.W + xx) : 0.f;
-    }
+    for (int kx = 0; kx < KS; ++kx) v[ky * KS + kx] = tile[ky][threadIdx.x + kx];
   const long long p = g.pos(n, y, x);
-  for (int c = 0; c < chunks; ++c) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[c * 8 + j];
+    for (int j = 0; j < 8; ++j) acc[j] = (c * 8 + j < COUT) ? sw.b[c * 8 + j] : 0.f;
 #pragma unroll
     for (int t = 0; t < KS * KS; ++t)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[t], sw[t * cpad + c * 8 + j], acc[j]);
+      for (int j = 0; j < 8; ++j)
+        if (c * 8 + j < COUT) acc[j] = fmaf(v[t], sw.w[t * 16 + c * 8 + j], acc[j]);
     if (out_pre) *reinterpret_cast<uint4*>(out_pre + (c * pre_plane + p) * 8) = pack8(acc);
+    if (act == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = apply_act(acc[j], act);
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
     *reinterpret_cast<uint4*>(out + (c * out_plane + p) * 8) = pack8(acc);
   }
 }
@@ -312,50 +321,71 @@ __global__ void __launch_bounds__(256) k_pool_f32(const float* __restrict__ in, 
 //   out  = sum_k d_k * s_k
 // One thread per output pixel; low-resolution operands are re-read through L1/L2.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_combine(const CombineArgs a) {
+static __device__ __forceinline__ int div_up(int v, int up, int sh) { return sh >= 0 ? (v >> sh) : (v / up); }
+
+// grid = (ceil(W/128), H, N): the row-wise source indices are block-uniform, the column-wise ones are shifts
+// (the upsample factors of the ARU topology are powers of two; other factors take the division).
+__global__ void __launch_bounds__(128) k_combine(const __grid_constant__ CombineArgs a) {
   const Geo& g = a.geo;
-  const long long total = (long long)g.N * g.H * g.W;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int n, y, x;
-  pix_coords(i, g.H, g.W, n, y, x);
+  const int n = blockIdx.z, y = blockIdx.y, x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= g.W) return;
   const long long p = g.pos(n, y, x);
-  float s[8];
+  float s[ARU_COMBINE_MAX];
   float m = -INFINITY;
-  for (int k = 0; k < a.A; ++k) {
-    const int sy = (y + a.att_oy[k]) / a.att_up[k], sx = (x + a.att_ox[k]) / a.att_up[k];
-    s[k] = __ldg(a.att[k] + ((long long)n * a.att_h[k] + sy) * a.att_w[k] + sx);
-    m = fmaxf(m, s[k]);
+#pragma unroll
+  for (int k = 0; k < ARU_COMBINE_MAX; ++k) {
+    if (k < a.A) {
+      const int sy = div_up(y + a.att_oy[k], a.att_up[k], a.att_sh[k]);
+      const int sx = div_up(x + a.att_ox[k], a.att_up[k], a.att_sh[k]);
+      s[k] = __ldg(a.att[k] + ((long long)n * a.att_h[k] + sy) * a.att_w[k] + sx);
+      m = fmaxf(m, s[k]);
+    }
   }
   float den = 0.f;
-  for (int k = 0; k < a.A; ++k) {
-    s[k] = expf(s[k] - m);
-    den += s[k];
+#pragma unroll
+  for (int k = 0; k < ARU_COMBINE_MAX; ++k) {
+    if (k < a.A) {
+      s[k] = __expf(s[k] - m);
+      den += s[k];
+    }
   }
   const float inv = 1.f / den;
+  // low-resolution detection maps: channel sum of the source pixel (the ones-filter quirk), shared by all chunks
+  float dsum[ARU_COMBINE_MAX];
+#pragma unroll
+  for (int k = 0; k < ARU_COMBINE_MAX; ++k) {
+    dsum[k] = 0.f;
+    if (k < a.A && a.det_up[k] != 1) {
+      const int sy = div_up(y + a.det_oy[k], a.det_up[k], a.det_sh[k]);
+      const int sx = div_up(x + a.det_ox[k], a.det_up[k], a.det_sh[k]);
+      const long long q = a.det_geo[k].pos(n, sy, sx);
+      float sum = 0.f;
+      for (int c = 0; c < a.det_chunks[k]; ++c) {
+        float d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (c * a.det_plane[k] + q) * 8)), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += d[j];
+      }
+      dsum[k] = sum * s[k] * inv;
+    }
+  }
   for (int oc = 0; oc < a.out_chunks; ++oc) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = 0; k < a.A; ++k) {
-      const float wk = s[k] * inv;
-      if (a.det_up[k] == 1) {
-        float d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (oc * a.det_plane[k] + p) * 8)), d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], wk, acc[j]);
-      } else {
-        const int sy = (y + a.det_oy[k]) / a.det_up[k], sx = (x + a.det_ox[k]) / a.det_up[k];
-        const long long q = a.det_geo[k].pos(n, sy, sx);
-        float sum = 0.f;
-        for (int c = 0; c < a.det_chunks[k]; ++c) {
+    for (int k = 0; k < ARU_COMBINE_MAX; ++k) {
+      if (k < a.A) {
+        if (a.det_up[k] == 1) {
+          const float wk = s[k] * inv;
           float d[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (c * a.det_plane[k] + q) * 8)), d);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (oc * a.det_plane[k] + p) * 8)), d);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) sum += d[j];
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], wk, acc[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += dsum[k];
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(sum, wk, acc[j]);
       }
     }
     *reinterpret_cast<uint4*>(a.out + (oc * a.out_plane + p) * 8) = pack8(acc);
@@ -436,16 +466,23 @@ __global__ void __launch_bounds__(256) k_unpack_nhwc(const act_t* __restrict__ i
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 static inline long long npix(const Geo& g) { return (long long)g.N * g.H * g.W; }
 
-cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w,
-                             const float* bias, const Geo& g, int act) {
-  if (out.chunks > 2) return cudaErrorInvalidValue;
-  const unsigned nb = blocks_for(npix(g), 256);
-  if (ks == 3)
-    k_conv_stem<3><<<nb, 256, 0, st>>>(in, out.p, out.plane, out_pre.p, out_pre.plane, w, bias, g, out.chunks, act);
-  else if (ks == 4)
-    k_conv_stem<4><<<nb, 256, 0, st>>>(in, out.p, out.plane, out_pre.p, out_pre.plane, w, bias, g, out.chunks, act);
-  else
-    return cudaErrorInvalidValue;
+cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w_host,
+                             const float* bias_host, const Geo& g, int act) {
+  // w_host: the TF filter [ks][ks][1][C_out] (host memory), bias_host [C_out]; both travel in the kernel parameters
+  const int cout = out.C;
+  if (cout < 1 || cout > 16 || (ks != 3 && ks != 4) || g.H > 65535 || g.N > 65535) return cudaErrorInvalidValue;
+  StemW sw;
+  for (int i = 0; i < 16 * 16; ++i) sw.w[i] = 0.f;
+  for (int i = 0; i < 16; ++i) sw.b[i] = i < cout ? bias_host[i] : 0.f;
+  for (int t = 0; t < ks * ks; ++t)
+    for (int c = 0; c < cout; ++c) sw.w[t * 16 + c] = w_host[(size_t)t * cout + c];
+  const dim3 grid((unsigned)cdiv(g.W, 128), (unsigned)g.H, (unsigned)g.N);
+  const int cc = cout <= 8 ? 8 : (cout <= 12 ? 12 : 16);  // instantiated widths (padding channels have zero weights)
+#define ARU_STEM(KK, CC)                                                                                              \
+  if (ks == KK && cc == CC)                                                                                           \
+    k_conv_stem<KK, CC><<<grid, 128, 0, st>>>(in, out.p, out.plane, out_pre.p, out_pre.plane, sw, g, act);
+  ARU_STEM(3, 8) ARU_STEM(3, 12) ARU_STEM(3, 16) ARU_STEM(4, 8) ARU_STEM(4, 12) ARU_STEM(4, 16)
+#undef ARU_STEM
   return cudaGetLastError();
 }
 
@@ -513,8 +550,16 @@ cudaError_t launch_pool_f32(cudaStream_t st, bool is_max, const float* in, float
   return cudaGetLastError();
 }
 
-cudaError_t launch_combine(cudaStream_t st, const CombineArgs& a) {
-  k_combine<<<blocks_for(npix(a.geo), 256), 256, 0, st>>>(a);
+cudaError_t launch_combine(cudaStream_t st, const CombineArgs& a_in) {
+  CombineArgs a = a_in;
+  if (a.A < 1 || a.A > ARU_COMBINE_MAX || a.geo.H > 65535 || a.geo.N > 65535) return cudaErrorInvalidValue;
+  auto log2_or_neg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
+  for (int k = 0; k < a.A; ++k) {
+    a.att_sh[k] = log2_or_neg(a.att_up[k]);
+    a.det_sh[k] = log2_or_neg(a.det_up[k]);
+  }
+  const dim3 grid((unsigned)cdiv(a.geo.W, 128), (unsigned)a.geo.H, (unsigned)a.geo.N);
+  k_combine<<<grid, 128, 0, st>>>(a);
   return cudaGetLastError();
 }
 
