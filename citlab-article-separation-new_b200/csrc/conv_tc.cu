@@ -196,35 +196,6 @@ __device__ __forceinline__ void walk_adv(int& col, int& rin, int& pg, int dc, in
   }
 }
 
-// ---- 16-bit packing of epilogue values -----------------------------------------------------------
-// two fp32 -> packed 16-bit pair, saturated to the finite range (fp16: an overflowing activation must not
-// become inf and poison later 0*x products), optionally ReLU'd.  max(.,0) commutes with the rounding.
-template <bool RELU>
-__device__ __forceinline__ uint32_t pack2_fin(float x, float y) {
-#ifdef ARU_USE_BF16
-  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-  if (RELU) h = __hmax2(h, __floats2bfloat162_rn(0.f, 0.f));
-  return *reinterpret_cast<uint32_t*>(&h);
-#else
-  __half2 h = __floats2half2_rn(x, y);
-  const __half2 hi = __half2half2(__ushort_as_half((unsigned short)0x7bff));   // 65504
-  h = __hmin2(h, hi);
-  if (RELU) h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0)));
-  else h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0xfbff)));  // -65504
-  return *reinterpret_cast<uint32_t*>(&h);
-#endif
-}
-template <bool RELU>
-__device__ __forceinline__ uint4 pack8_fin(const float f[8], bool valid) {
-  uint4 v;
-  v.x = pack2_fin<RELU>(f[0], f[1]);
-  v.y = pack2_fin<RELU>(f[2], f[3]);
-  v.z = pack2_fin<RELU>(f[4], f[5]);
-  v.w = pack2_fin<RELU>(f[6], f[7]);
-  if (!valid) v = make_uint4(0u, 0u, 0u, 0u);   // frame / margin positions are (re)written with zeros
-  return v;
-}
-
 // ---- the kernel --------------------------------------------------------------------------------
 // MODE 0: C_in = 8 (paired taps)   1: resident weights, >= 2 input chunks   2: streamed weights
 template <int T, int KS, int MODE>

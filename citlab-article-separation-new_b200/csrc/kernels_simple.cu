@@ -31,53 +31,60 @@ static __device__ __forceinline__ void pix_coords(long long i, int H, int W, int
 // (4 B in, 16-32 B out per pixel), so the work is to keep the FMA count off the critical path: the
 // filter lives in the kernel parameters (constant bank), every FFMA takes its weight as a constant
 // operand (no shared-memory or register traffic for weights), the loops are fully unrolled over the
-// real C_out, and the input taps come from a shared-memory row tile loaded once per block.
-// One block = 128 consecutive pixels of one image row; grid = (ceil(W/128), H, N): no index divisions.
+// real C_out.
+// One thread = one image column, walking 16 rows with a sliding KS x KS window in registers (KS coalesced
+// loads per pixel); grid = (ceil(W/128), ceil(H/16), N): no index divisions.
 // ---------------------------------------------------------------------------------------------
 struct StemW {
   float w[16 * 16];  // [tap][16]
   float b[16];
 };
 
+constexpr int STEM_ROWS = 16;  // image rows one thread walks down (sliding KS x KS window in registers)
+
 template <int KS, int COUT>
 __global__ void __launch_bounds__(128) k_conv_stem(const float* __restrict__ in, act_t* __restrict__ out,
                                                    long long out_plane, act_t* __restrict__ out_pre,
                                                    long long pre_plane, const __grid_constant__ StemW sw, Geo g,
                                                    int act) {
-  constexpr int CH = (COUT + 7) / 8, PB = (KS - 1) / 2, TW = 128 + KS - 1;
-  __shared__ float tile[KS][TW + 1];
-  const int n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 128;
-  const float* img = in + (long long)n * g.H * g.W;
-  for (int i = threadIdx.x; i < KS * TW; i += 128) {
-    const int r = i / TW, c = i - r * TW;
-    const int yy = y + r - PB, xx = x0 + c - PB;
-    tile[r][c] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? __ldg(img + (long long)yy * g.W + xx) : 0.f;
-  }
-  __syncthreads();
-  const int x = x0 + threadIdx.x;
+  constexpr int CH = (COUT + 7) / 8, PB = (KS - 1) / 2;
+  const int n = blockIdx.z, y0 = blockIdx.y * STEM_ROWS, x = blockIdx.x * 128 + threadIdx.x;
   if (x >= g.W) return;
-  float v[KS * KS];
+  const float* img = in + (long long)n * g.H * g.W;
+  bool okx[KS];
 #pragma unroll
-  for (int ky = 0; ky < KS; ++ky)
+  for (int kx = 0; kx < KS; ++kx) okx[kx] = (unsigned)(x + kx - PB) < (unsigned)g.W;
+  auto load_row = [&](int yy, float r[KS]) {
+    const bool oky = (unsigned)yy < (unsigned)g.H;
+    const float* row = img + (long long)yy * g.W + (x - PB);
 #pragma unroll
-    for (int kx = 0; kx < KS; ++kx) v[ky * KS + kx] = tile[ky][threadIdx.x + kx];
-  const long long p = g.pos(n, y, x);
+    for (int kx = 0; kx < KS; ++kx) r[kx] = (oky && okx[kx]) ? __ldg(row + kx) : 0.f;
+  };
+  float v[KS][KS];
 #pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    float acc[8];
+  for (int ky = 0; ky < KS - 1; ++ky) load_row(y0 + ky - PB, v[ky + 1]);   // rows ky = 1..KS-1 of the first window, shifted below
+  const int y1 = min(y0 + STEM_ROWS, g.H);
+  long long p = g.pos(n, y0, x);
+  for (int y = y0; y < y1; ++y, p += g.Wp) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (c * 8 + j < COUT) ? sw.b[c * 8 + j] : 0.f;
+    for (int ky = 0; ky < KS - 1; ++ky)
 #pragma unroll
-    for (int t = 0; t < KS * KS; ++t)
+      for (int kx = 0; kx < KS; ++kx) v[ky][kx] = v[ky + 1][kx];
+    load_row(y + KS - 1 - PB, v[KS - 1]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (c * 8 + j < COUT) acc[j] = fmaf(v[t], sw.w[t * 16 + c * 8 + j], acc[j]);
-    if (out_pre) *reinterpret_cast<uint4*>(out_pre + (c * pre_plane + p) * 8) = pack8(acc);
-    if (act == 1) {
+    for (int c = 0; c < CH; ++c) {
+      float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      for (int j = 0; j < 8; ++j) acc[j] = (c * 8 + j < COUT) ? sw.b[c * 8 + j] : 0.f;
+#pragma unroll
+      for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c * 8 + j < COUT) acc[j] = fmaf(v[t / KS][t % KS], sw.w[t * 16 + c * 8 + j], acc[j]);
+      if (out_pre) *reinterpret_cast<uint4*>(out_pre + (c * pre_plane + p) * 8) = pack8_fin<false>(acc, true);
+      *reinterpret_cast<uint4*>(out + (c * out_plane + p) * 8) =
+          act == 1 ? pack8_fin<true>(acc, true) : pack8_fin<false>(acc, true);
     }
-    *reinterpret_cast<uint4*>(out + (c * out_plane + p) * 8) = pack8(acc);
   }
 }
 
@@ -323,72 +330,71 @@ __global__ void __launch_bounds__(256) k_pool_f32(const float* __restrict__ in, 
 // ---------------------------------------------------------------------------------------------
 static __device__ __forceinline__ int div_up(int v, int up, int sh) { return sh >= 0 ? (v >> sh) : (v / up); }
 
-// grid = (ceil(W/128), H, N): the row-wise source indices are block-uniform, the column-wise ones are shifts
-// (the upsample factors of the ARU topology are powers of two; other factors take the division).
+constexpr int COMBINE_ROWS = 16;
+
+// One thread = one output column walking 16 rows; grid = (ceil(W/128), ceil(H/16), N).  Column-wise source indices
+// are computed once per thread, row-wise ones are shifts (the upsample factors of the ARU topology are powers of two;
+// other factors take the division).  Templated on the number of scales so the per-scale state lives in registers.
+template <int A>
 __global__ void __launch_bounds__(128) k_combine(const __grid_constant__ CombineArgs a) {
   const Geo& g = a.geo;
-  const int n = blockIdx.z, y = blockIdx.y, x = blockIdx.x * 128 + threadIdx.x;
+  const int n = blockIdx.z, y0 = blockIdx.y * COMBINE_ROWS, x = blockIdx.x * 128 + threadIdx.x;
   if (x >= g.W) return;
-  const long long p = g.pos(n, y, x);
-  float s[ARU_COMBINE_MAX];
-  float m = -INFINITY;
+  const float* att_col[A];
+  long long det_col[A];   // position of (n, row 0, source column) in the low-resolution detection map
 #pragma unroll
-  for (int k = 0; k < ARU_COMBINE_MAX; ++k) {
-    if (k < a.A) {
-      const int sy = div_up(y + a.att_oy[k], a.att_up[k], a.att_sh[k]);
-      const int sx = div_up(x + a.att_ox[k], a.att_up[k], a.att_sh[k]);
-      s[k] = __ldg(a.att[k] + ((long long)n * a.att_h[k] + sy) * a.att_w[k] + sx);
+  for (int k = 0; k < A; ++k) {
+    att_col[k] = a.att[k] + (long long)n * a.att_h[k] * a.att_w[k] + div_up(x + a.att_ox[k], a.att_up[k], a.att_sh[k]);
+    det_col[k] = a.det_geo[k].pos(n, 0, div_up(x + a.det_ox[k], a.det_up[k], a.det_sh[k]));
+  }
+  const int y1 = min(y0 + COMBINE_ROWS, g.H);
+  long long p = g.pos(n, y0, x);
+  for (int y = y0; y < y1; ++y, p += g.Wp) {
+    float s[A];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+      s[k] = __ldg(att_col[k] + (long long)div_up(y + a.att_oy[k], a.att_up[k], a.att_sh[k]) * a.att_w[k]);
       m = fmaxf(m, s[k]);
     }
-  }
-  float den = 0.f;
+    float den = 0.f;
 #pragma unroll
-  for (int k = 0; k < ARU_COMBINE_MAX; ++k) {
-    if (k < a.A) {
+    for (int k = 0; k < A; ++k) {
       s[k] = __expf(s[k] - m);
       den += s[k];
     }
-  }
-  const float inv = 1.f / den;
-  // low-resolution detection maps: channel sum of the source pixel (the ones-filter quirk), shared by all chunks
-  float dsum[ARU_COMBINE_MAX];
+    const float inv = 1.f / den;
+    // low-resolution detection maps: channel sum of the source pixel (the ones-filter quirk), shared by all chunks
+    float low = 0.f;
 #pragma unroll
-  for (int k = 0; k < ARU_COMBINE_MAX; ++k) {
-    dsum[k] = 0.f;
-    if (k < a.A && a.det_up[k] != 1) {
-      const int sy = div_up(y + a.det_oy[k], a.det_up[k], a.det_sh[k]);
-      const int sx = div_up(x + a.det_ox[k], a.det_up[k], a.det_sh[k]);
-      const long long q = a.det_geo[k].pos(n, sy, sx);
-      float sum = 0.f;
-      for (int c = 0; c < a.det_chunks[k]; ++c) {
-        float d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (c * a.det_plane[k] + q) * 8)), d);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += d[j];
+    for (int k = 0; k < A; ++k) {
+      if (a.det_up[k] != 1) {
+        const long long q = det_col[k] + (long long)div_up(y + a.det_oy[k], a.det_up[k], a.det_sh[k]) * a.det_geo[k].Wp;
+        float sum = 0.f;
+        for (int c = 0; c < a.det_chunks[k]; ++c) {
+          float d[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (c * a.det_plane[k] + q) * 8)), d);
+          sum += ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
+        }
+        low = fmaf(sum, s[k] * inv, low);
       }
-      dsum[k] = sum * s[k] * inv;
     }
-  }
-  for (int oc = 0; oc < a.out_chunks; ++oc) {
-    float acc[8];
+    for (int oc = 0; oc < a.out_chunks; ++oc) {
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[j] = low;
 #pragma unroll
-    for (int k = 0; k < ARU_COMBINE_MAX; ++k) {
-      if (k < a.A) {
+      for (int k = 0; k < A; ++k) {
         if (a.det_up[k] == 1) {
           const float wk = s[k] * inv;
           float d[8];
           unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (oc * a.det_plane[k] + p) * 8)), d);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], wk, acc[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += dsum[k];
         }
       }
+      *reinterpret_cast<uint4*>(a.out + (oc * a.out_plane + p) * 8) = pack8_fin<false>(acc, true);
     }
-    *reinterpret_cast<uint4*>(a.out + (oc * a.out_plane + p) * 8) = pack8(acc);
   }
 }
 
@@ -476,7 +482,7 @@ cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, P
   for (int i = 0; i < 16; ++i) sw.b[i] = i < cout ? bias_host[i] : 0.f;
   for (int t = 0; t < ks * ks; ++t)
     for (int c = 0; c < cout; ++c) sw.w[t * 16 + c] = w_host[(size_t)t * cout + c];
-  const dim3 grid((unsigned)cdiv(g.W, 128), (unsigned)g.H, (unsigned)g.N);
+  const dim3 grid((unsigned)cdiv(g.W, 128), (unsigned)cdiv(g.H, STEM_ROWS), (unsigned)g.N);
   const int cc = cout <= 8 ? 8 : (cout <= 12 ? 12 : 16);  // instantiated widths (padding channels have zero weights)
 #define ARU_STEM(KK, CC)                                                                                              \
   if (ks == KK && cc == CC)                                                                                           \
@@ -558,8 +564,17 @@ cudaError_t launch_combine(cudaStream_t st, const CombineArgs& a_in) {
     a.att_sh[k] = log2_or_neg(a.att_up[k]);
     a.det_sh[k] = log2_or_neg(a.det_up[k]);
   }
-  const dim3 grid((unsigned)cdiv(a.geo.W, 128), (unsigned)a.geo.H, (unsigned)a.geo.N);
-  k_combine<<<grid, 128, 0, st>>>(a);
+  const dim3 grid((unsigned)cdiv(a.geo.W, 128), (unsigned)cdiv(a.geo.H, COMBINE_ROWS), (unsigned)a.geo.N);
+  switch (a.A) {
+    case 1: k_combine<1><<<grid, 128, 0, st>>>(a); break;
+    case 2: k_combine<2><<<grid, 128, 0, st>>>(a); break;
+    case 3: k_combine<3><<<grid, 128, 0, st>>>(a); break;
+    case 4: k_combine<4><<<grid, 128, 0, st>>>(a); break;
+    case 5: k_combine<5><<<grid, 128, 0, st>>>(a); break;
+    case 6: k_combine<6><<<grid, 128, 0, st>>>(a); break;
+    case 7: k_combine<7><<<grid, 128, 0, st>>>(a); break;
+    default: k_combine<8><<<grid, 128, 0, st>>>(a); break;
+  }
   return cudaGetLastError();
 }
 
