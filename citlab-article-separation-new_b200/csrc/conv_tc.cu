@@ -140,6 +140,19 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err_flag, code);
 }
+// Fully inlined variant for the MMA issuer: a CALL in its loop would force every loop-carried descriptor value out of
+// the uniform registers (they are not preserved across calls) and back through R2UR before each UTCHMMA.
+__device__ __forceinline__ void mbar_wait_inline(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (global_ns() - t0 > 200000000ull) {
+      atomicCAS(err_flag, 0, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
@@ -179,6 +192,41 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// T MMAs of one K-step (the T tiles of a pass) in ONE asm block under ONE election: A descriptor low words
+// a_lo[t] + a_add, a common B descriptor, accumulators d0 + t * dstep.  With warp-uniform operands ptxas keeps all of
+// it on the uniform datapath: ~2-3 instructions per UTCHMMA instead of ~15 with a C++-level election per MMA.
+#define ARU_MMA_HEAD                                                                                       \
+  "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 al, dd;\n\t"                                      \
+  "elect.sync _|p, 0xffffffff;\n\t"                                                                        \
+  "setp.ne.b32 q, %4, 0;\n\t"                                                                              \
+  "mov.b64 db, {%1, %2};\n\t"                                                                              \
+  "mov.b32 dd, %5;\n\t"
+#define ARU_MMA_ONE(AREG)                                                                                  \
+  "add.u32 al, " AREG ", %0;\n\tmov.b64 da, {al, %2};\n\t"                                                  \
+  "@p tcgen05.mma.cta_group::1.kind::f16 [dd], da, db, %3, q;\n\t"                                         \
+  "add.u32 dd, dd, %6;\n\t"
+template <int T>
+__device__ __forceinline__ void umma_tiles(const uint32_t (&a_lo)[T], uint32_t a_add, uint32_t b_lo, uint32_t hi,
+                                           uint32_t d0, uint32_t dstep, uint32_t idesc, uint32_t acc) {
+  static_assert(T == 1 || T == 2 || T == 4, "tiles per pass");
+  if constexpr (T == 1) {
+    asm volatile(ARU_MMA_HEAD ARU_MMA_ONE("%7") "}" ::"r"(a_add), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc), "r"(d0),
+                 "r"(dstep), "r"(a_lo[0])
+                 : "memory");
+  } else if constexpr (T == 2) {
+    asm volatile(ARU_MMA_HEAD ARU_MMA_ONE("%7") ARU_MMA_ONE("%8") "}" ::"r"(a_add), "r"(b_lo), "r"(hi), "r"(idesc),
+                 "r"(acc), "r"(d0), "r"(dstep), "r"(a_lo[0]), "r"(a_lo[1])
+                 : "memory");
+  } else {
+    asm volatile(ARU_MMA_HEAD ARU_MMA_ONE("%7") ARU_MMA_ONE("%8") ARU_MMA_ONE("%9") ARU_MMA_ONE("%10") "}" ::"r"(a_add),
+                 "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc), "r"(d0), "r"(dstep), "r"(a_lo[0]), "r"(a_lo[1]), "r"(a_lo[2]),
+                 "r"(a_lo[3])
+                 : "memory");
+  }
+}
+#undef ARU_MMA_HEAD
+#undef ARU_MMA_ONE
 
 // High word of a shared-memory matrix descriptor (no swizzle, K-major): SBO in 16-byte units at bits 32..45,
 // descriptor version 1 (sm_100) at bits 46..47.  Low word = start address >> 4 | (LBO >> 4) << 16.
@@ -262,7 +310,86 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
   const int n_groups = a.w_stream ? (a.n_steps + a.w_group - 1) / a.w_group : 0;
 
   if (n_pass > 0) {
-    if (warp == 1 && lane == 0) {
+    if (warp == 0) {
+      // ================= MMA issuer =================
+      // The whole warp runs this role convergently and one elected lane issues each instruction: ptxas then keeps
+      // descriptors in uniform registers and emits back-to-back UTCHMMAs (39 cycles / MMA at N = 16 measured by
+      // tools/mma_issue_bench.cu variant 3, against 50 for a single-lane region with its per-instruction waterfall).
+      const uint32_t idesc = (1u << 4) | (ARU_UMMA_FMT << 7) | (ARU_UMMA_FMT << 10) | ((uint32_t)(a.npad >> 3) << 17) |
+                             ((uint32_t)(TILE >> 4) << 24);
+      const uint32_t hi = desc_hi(128);
+      const uint32_t wstage_units = (uint32_t)(a.w_group * step_bytes) >> 4;
+      const uint32_t step_units = (uint32_t)step_bytes >> 4;
+      const uint32_t a_lbo = CIN1 ? 16u : (uint32_t)ring_plane * 16u;
+      const uint32_t a_lo0 = (s_ring >> 4) | ((a_lbo >> 4) << 16);
+      const uint32_t b_lo0 = (s_w >> 4) | ((((uint32_t)a.npad * 16u) >> 4) << 16);
+      const uint32_t cp_stride = (uint32_t)(2 * ring_plane);  // descriptor units between channel-chunk pairs
+      const int n_cp = CIN1 ? 1 : a.cin_chunks / 2;
+      const uint32_t npad = (uint32_t)a.npad;
+      // incremental ring bookkeeping (no divisions in the loop)
+      int stage = 0, f_slot = 0, e_slot = 0, wst = 0, phase = 0;
+      uint32_t stage_par = 0, f_par = 0, w_par = 0;
+      for (int pi = 0; pi < n_pass; ++pi) {
+        mbar_wait_inline(s_tempty + 8 * stage, stage_par ^ 1, a.err_flag, 2);
+        // operands: pass pi reads units pi .. pi+win-1 (the first pass waits for its whole window)
+        for (int k = (pi == 0 ? 0 : win - 1); k < win; ++k) {
+          mbar_wait_inline(s_full + 8 * f_slot, f_par, a.err_flag, 3);
+          if (++f_slot == a.n_units) { f_slot = 0; f_par ^= 1; }
+        }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(stage * T) * npad;
+        const uint32_t* tab = a.tab + phase * (T * KS);
+        // K loop in the order the B image was packed: taps (ky, kx) unrolled at compile time, channel-chunk
+        // pairs inside.  C_in = 8 (CIN1): horizontally adjacent taps are paired into one K=16 step (the B
+        // image holds zeros for the missing partner of the last tap of an odd-width kernel).
+        uint32_t b_lo = b_lo0;
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+          uint32_t a_row[T];
+#pragma unroll
+          for (int t = 0; t < T; ++t) a_row[t] = a_lo0 + tab[t * KS + ky];
+#pragma unroll
+          for (int kx = 0; kx < KS; kx += (CIN1 ? 2 : 1)) {
+            if constexpr (MODE == 0) {
+              umma_tiles<T>(a_row, (uint32_t)kx, b_lo, hi, d_tmem, npad, idesc, (ky | kx) ? 1u : 0u);
+              b_lo += step_units;
+            } else if constexpr (MODE == 1) {
+              // rolled over the channel-chunk pairs (keeps the kernel small enough for the instruction cache)
+#pragma unroll 1
+              for (int cp = 0; cp < n_cp; ++cp) {
+                umma_tiles<T>(a_row, (uint32_t)kx + (uint32_t)cp * cp_stride, b_lo, hi, d_tmem, npad, idesc,
+                              (ky | kx | cp) ? 1u : 0u);
+                b_lo += step_units;
+              }
+            } else {
+              // streamed weights: groups of w_group steps (w_group divides n_cp, so a group never straddles taps)
+#pragma unroll 1
+              for (int cp0 = 0; cp0 < n_cp; cp0 += a.w_group) {
+                mbar_wait_inline(s_wfull + 8 * wst, w_par, a.err_flag, 6);
+                tc_fence_after();
+                b_lo = b_lo0 + (uint32_t)wst * wstage_units;
+#pragma unroll 1
+                for (int cp = cp0; cp < cp0 + a.w_group; ++cp) {
+                  umma_tiles<T>(a_row, (uint32_t)kx + (uint32_t)cp * cp_stride, b_lo, hi, d_tmem, npad, idesc,
+                                (ky | kx | cp) ? 1u : 0u);
+                  b_lo += step_units;
+                }
+                if (elect_one()) umma_commit(s_wempty + 8 * wst);  // stage may be refilled once these MMAs retire
+                if (++wst == a.n_wst) { wst = 0; w_par ^= 1; }
+              }
+            }
+          }
+        }
+        if (elect_one()) {
+          umma_commit(s_empty + 8 * e_slot);  // unit pi is not needed by later passes
+          umma_commit(s_tfull + 8 * stage);   // accumulators ready for the epilogue
+        }
+        if (++e_slot == a.n_units) e_slot = 0;
+        if (++stage == a.n_stages) { stage = 0; stage_par ^= 1; }
+        if (++phase == a.n_units) phase = 0;
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
       // ================= producer =================
       const int n_load = n_pass + win - 1;
       const long long first_pos = (long long)(u0 + a.dlo) * UNIT;  // ring origin in plane positions
@@ -303,92 +430,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
           if (next < n_load) load_unit(next++);
         }
       }
-    } else if (warp == 0) {
-      // ================= MMA issuer =================
-      // The whole warp runs this role convergently and one elected lane issues each instruction: ptxas then keeps
-      // descriptors in uniform registers and emits back-to-back UTCHMMAs (39 cycles / MMA at N = 16 measured by
-      // tools/mma_issue_bench.cu variant 3, against 50 for a single-lane region with its per-instruction waterfall).
-      const uint32_t idesc = (1u << 4) | (ARU_UMMA_FMT << 7) | (ARU_UMMA_FMT << 10) | ((uint32_t)(a.npad >> 3) << 17) |
-                             ((uint32_t)(TILE >> 4) << 24);
-      const uint32_t hi = desc_hi(128);
-      const uint32_t wstage_units = (uint32_t)(a.w_group * step_bytes) >> 4;
-      const uint32_t step_units = (uint32_t)step_bytes >> 4;
-      const uint32_t a_lbo = CIN1 ? 16u : (uint32_t)ring_plane * 16u;
-      const uint32_t a_lo0 = (s_ring >> 4) | ((a_lbo >> 4) << 16);
-      const uint32_t b_lo0 = (s_w >> 4) | ((((uint32_t)a.npad * 16u) >> 4) << 16);
-      const uint32_t cp_stride = (uint32_t)(2 * ring_plane);  // descriptor units between channel-chunk pairs
-      const int n_cp = CIN1 ? 1 : a.cin_chunks / 2;
-      const uint32_t npad = (uint32_t)a.npad;
-      // incremental ring bookkeeping (no divisions in the loop)
-      int stage = 0, f_slot = 0, e_slot = 0, wst = 0, phase = 0;
-      uint32_t stage_par = 0, f_par = 0, w_par = 0;
-      for (int pi = 0; pi < n_pass; ++pi) {
-        mbar_wait(s_tempty + 8 * stage, stage_par ^ 1, a.err_flag, 2);
-        // operands: pass pi reads units pi .. pi+win-1 (the first pass waits for its whole window)
-        for (int k = (pi == 0 ? 0 : win - 1); k < win; ++k) {
-          mbar_wait(s_full + 8 * f_slot, f_par, a.err_flag, 3);
-          if (++f_slot == a.n_units) { f_slot = 0; f_par ^= 1; }
-        }
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(stage * T) * npad;
-        const uint32_t* tab = a.tab + phase * (T * KS);
-        // K loop in the order the B image was packed: taps (ky, kx) unrolled at compile time, channel-chunk
-        // pairs inside.  C_in = 8 (CIN1): horizontally adjacent taps are paired into one K=16 step (the B
-        // image holds zeros for the missing partner of the last tap of an odd-width kernel).
-        uint32_t b_lo = b_lo0;
-#pragma unroll
-        for (int ky = 0; ky < KS; ++ky) {
-          uint32_t a_row[T];
-#pragma unroll
-          for (int t = 0; t < T; ++t) a_row[t] = a_lo0 + tab[t * KS + ky];
-#pragma unroll
-          for (int kx = 0; kx < KS; kx += (CIN1 ? 2 : 1)) {
-            if constexpr (MODE == 0) {
-#pragma unroll
-              for (int t = 0; t < T; ++t)
-                if (elect_one()) umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx), desc64(hi, b_lo), idesc,
-                         (ky | kx) ? 1u : 0u);
-              b_lo += step_units;
-            } else if constexpr (MODE == 1) {
-              // rolled over the channel-chunk pairs (keeps the kernel small enough for the instruction cache)
-#pragma unroll 1
-              for (int cp = 0; cp < n_cp; ++cp) {
-                const uint32_t acc = (ky | kx | cp) ? 1u : 0u;
-#pragma unroll
-                for (int t = 0; t < T; ++t)
-                  if (elect_one()) umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx + (uint32_t)cp * cp_stride),
-                           desc64(hi, b_lo), idesc, acc);
-                b_lo += step_units;
-              }
-            } else {
-              // streamed weights: groups of w_group steps (w_group divides n_cp, so a group never straddles taps)
-#pragma unroll 1
-              for (int cp0 = 0; cp0 < n_cp; cp0 += a.w_group) {
-                mbar_wait(s_wfull + 8 * wst, w_par, a.err_flag, 6);
-                tc_fence_after();
-                b_lo = b_lo0 + (uint32_t)wst * wstage_units;
-#pragma unroll 1
-                for (int cp = cp0; cp < cp0 + a.w_group; ++cp) {
-                  const uint32_t acc = (ky | kx | cp) ? 1u : 0u;
-#pragma unroll
-                  for (int t = 0; t < T; ++t)
-                    if (elect_one()) umma_f16(d_tmem + (uint32_t)t * npad, desc64(hi, a_row[t] + (uint32_t)kx + (uint32_t)cp * cp_stride),
-                             desc64(hi, b_lo), idesc, acc);
-                  b_lo += step_units;
-                }
-                if (elect_one()) umma_commit(s_wempty + 8 * wst);  // stage may be refilled once these MMAs retire
-                if (++wst == a.n_wst) { wst = 0; w_par ^= 1; }
-              }
-            }
-          }
-        }
-        if (elect_one()) {
-          umma_commit(s_empty + 8 * e_slot);  // unit pi is not needed by later passes
-          umma_commit(s_tfull + 8 * stage);   // accumulators ready for the epilogue
-        }
-        if (++e_slot == a.n_units) e_slot = 0;
-        if (++stage == a.n_stages) { stage = 0; stage_par ^= 1; }
-        if (++phase == a.n_units) phase = 0;
       }
     } else if (warp >= 4) {
       // ================= epilogue =================
