@@ -153,7 +153,7 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
             dims[buf] = (hh.value, ww.value)
         return dims[buf]
 
-    classes = {}
+    classes, shapes = {}, {}
     for op, (_, kernel, ms) in zip(prog.ops, prof):
         flops = bytes_ = 0.0
         if op.kind in (P.OP_CONV, P.OP_DECONV):
@@ -182,6 +182,10 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
                 bytes_ += n * (ah * aw * 4 + dh * dw * d.ch * 2)
         c = classes.setdefault(kernel, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         c["ms"] += ms; c["flops"] += flops; c["bytes"] += bytes_; c["launches"] += 1
+        if op.kind in (P.OP_CONV, P.OP_DECONV):
+            key = f"{kernel} {op.ksize}x{op.ksize} {op.inp.ch}->{op.out.ch} {oh}x{ow} n{n}"
+            sgrp = shapes.setdefault(key, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            sgrp["ms"] += ms; sgrp["flops"] += flops; sgrp["bytes"] += bytes_; sgrp["launches"] += 1
     total_ms = sum(c["ms"] for c in classes.values())
     out = []
     for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
@@ -195,7 +199,25 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
                     "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
                     "frac": round(achieved / peak, 4), "tflops": round(c["flops"] / t / 1e12, 2),
                     "gbs": round(c["bytes"] / t / 1e9, 1)})
-    return out, total_ms
+    # the dominant kernel = the launch shape with the largest share of the pass (same kernel, same tensor sizes)
+    key, g = max(shapes.items(), key=lambda kv: kv[1]["ms"])
+    t = g["ms"] * 1e-3 / g["launches"]
+    b, f = g["bytes"] / g["launches"], g["flops"] / g["launches"]
+    bound = "tensor" if f / (peaks["bf16_tflops"] * 1e12) > b / (peaks["hbm_gbs"] * 1e9) else "hbm"
+    achieved = f / t / 1e12 if bound == "tensor" else b / t / 1e9
+    peak = peaks["bf16_tflops"] if bound == "tensor" else peaks["hbm_gbs"]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            traffic = json.load(fh).get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    dominant = {"kernel": key, "bound": bound, "achieved": round(achieved, 2), "peak": peak,
+                "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "launches_per_pass": g["launches"], "us_per_launch": round(t * 1e6, 2),
+                "algorithmic_bytes_per_launch": int(b), "flops_per_launch": int(f),
+                "share_of_step": round(g["ms"] / total_ms, 4)}
+    return out, total_ms, dominant
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -283,8 +305,7 @@ def run_b200(args):
     if rank == 0:
         import ctypes
         mb_pages = min(n, max(1, min((40 << 20) // (H * W), 32)))
-        classes, prof_ms = class_rooflines(eng, mb_pages, H, W, peaks)
-        dom = classes[0]
+        classes, prof_ms, dom = class_rooflines(eng, mb_pages, H, W, peaks)
         n_mb = -(-n // mb_pages)
         gflop_page = 2.0 * aru_conv_macs(H, W) / 1e9
         total_pages = world * n * args.steps
@@ -302,10 +323,9 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches * n_mb * args.steps),
             "achieved_tflops": round(value / world * gflop_page / 1e3, 2),
-            "roofline": {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
-                         "unit": dom["unit"], "frac": dom["frac"], "traffic": None, "peaks": peaks_src,
-                         "share_of_step": dom["share"],
-                         "note": "all launches of the class in one micro-batch pass, CUDA events on the engine stream"},
+            "roofline": dict(dom, peaks=peaks_src,
+                             note="dominant launch shape of one micro-batch pass; CUDA events on the engine stream, mean over "
+                                  "its launches; traffic = ncu dram read+write bytes of the same launch (profiles/ncu_traffic.json)"),
             "roofline_by_class": classes,
             "clocks": clocks,
         }

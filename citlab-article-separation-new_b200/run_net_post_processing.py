@@ -1,0 +1,156 @@
+"""GPU-sharded counterpart of the reference's
+``article_separation/image_segmentation/net_post_processing/run_net_post_processing.py``.
+
+Same argparse surface (``--path_to_image_list --path_to_pb --mode {heading,separator} --num_processes
+--fixed_height --scaling_factor --threshold``, defaults per reference :27-57: fixed height 1500 for the
+separator net, 900 for the heading net).  What changes is the sharder (reference :59-82, a
+``ProcessPoolExecutor`` of CPU workers with their own ``tf.Session``): here one *process per GPU* takes a
+page shard (``sharding.shard_for_rank``), owns one engine and needs no collective.  Ranks come from
+``torchrun`` (RANK / WORLD_SIZE / LOCAL_RANK) or from ``--gpus N``, which re-executes this module N times.
+
+Two back ends per rank:
+  * the reference's own, unmodified ``SeparatorNetPostProcessor`` / ``HeadingNetPostProcessor`` when the
+    reference package (and its lxml / shapely / rasterio dependencies) is importable - ``net_boundary.install()``
+    makes them call the B200 engine, and PAGE-XML is written exactly as before;
+  * ``--dump_dir``: the path up to the reference's integer forms - ``load_and_scale_image`` -> net ->
+    ``uint8(p*255)`` and the thresholded mask (separator_net_post_processor.py:146-149) - written as PNGs plus a
+    per-rank manifest (a re-run skips pages already listed, and the parent checks every page was done: worker
+    failures are silent in the reference because its futures are never awaited, reference :77,82).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+from typing import List
+
+import numpy as np
+
+if __package__ in (None, ""):  # executed as a script: make ``aru_b200`` importable
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    __package__ = "aru_b200"
+
+from . import net_boundary, sharding  # noqa: E402
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="ARU-Net separator / heading inference on B200, page-sharded over GPUs")
+    p.add_argument("--path_to_image_list", type=str, required=True, help="Path to the list file holding the image paths.")
+    p.add_argument("--path_to_pb", type=str, required=True, help="Path to the TensorFlow pixel labelling graph.")
+    p.add_argument("--num_processes", type=int, default=8,
+                   help="Accepted for compatibility; parallelism is one process per GPU (--gpus / torchrun).")
+    p.add_argument("--fixed_height", type=int, required=False, help="Input image height")
+    p.add_argument("--scaling_factor", type=float, default=1.0, help="Scaling factor of images.")
+    p.add_argument("--mode", type=str, required=True, choices=["heading", "separator"])
+    p.add_argument("--threshold", type=float, default=0.05, help="Threshold for binarization of net output.")
+    p.add_argument("--gpus", type=int, default=0, help="Spawn this many single-GPU ranks (0: use the torchrun env / 1 rank).")
+    p.add_argument("--dump_dir", type=str, default=None,
+                   help="Write uint8 probability maps / masks + a manifest here instead of running the PAGE-XML writers.")
+    return p
+
+
+def default_fixed_height(mode: str) -> int:
+    return 900 if mode == "heading" else 1500  # reference :51-57
+
+
+def _pixel_counts(paths: List[str]):
+    try:
+        from PIL import Image
+    except Exception:
+        return None
+    out = []
+    for p in paths:
+        try:
+            with Image.open(p) as im:
+                out.append(im.size[0] * im.size[1])
+        except Exception:
+            return None
+    return out
+
+
+def _reference_available() -> bool:
+    try:
+        import importlib
+        importlib.import_module("article_separation.image_segmentation.net_post_processing.region_to_page_writer")
+        return True
+    except Exception:
+        return False
+
+
+def run_rank(args, rank: int, world: int, local_rank: int) -> int:
+    paths = net_boundary.load_image_paths(args.path_to_image_list)
+    shard = sharding.shard_for_rank(paths, world, rank, _pixel_counts(paths))
+    fixed_height = args.fixed_height if args.fixed_height is not None else default_fixed_height(args.mode)
+    os.environ.setdefault("ARU_B200_DEVICE", str(local_rank))
+    if args.dump_dir is None:
+        if not _reference_available():
+            raise SystemExit("the reference package (article_separation + lxml/shapely/rasterio) is not importable: "
+                             "pass --dump_dir to write probability maps / masks instead of PAGE-XML")
+        net_boundary.install()
+        if args.mode == "separator":
+            from article_separation.image_segmentation.net_post_processing.separator_net_post_processor import \
+                SeparatorNetPostProcessor
+            SeparatorNetPostProcessor(shard, args.path_to_pb, fixed_height, args.scaling_factor, args.threshold,
+                                      gpu_devices="").run()
+        else:
+            from article_separation.image_segmentation.net_post_processing.heading_net_post_processor import \
+                HeadingNetPostProcessor
+            HeadingNetPostProcessor(shard, args.path_to_pb, fixed_height, args.scaling_factor,
+                                    {"net": 0.8, "stroke_width": 0.0, "text_height": 0.2}, 0.4,
+                                    {"net_thresh": 1.0, "stroke_width_thresh": 1.0, "text_height_thresh": 0.9,
+                                     "sw_th_thresh": 0.9}, 0.8).run(gpu_device="")
+        return len(shard)
+
+    import cv2
+    os.makedirs(args.dump_dir, exist_ok=True)
+    manifest_path = os.path.join(args.dump_dir, f"manifest_rank{rank}.json")
+    done = {}
+    if os.path.exists(manifest_path):
+        with open(manifest_path) as f:
+            done = json.load(f).get("pages", {})
+    graph = net_boundary.load_graph(args.path_to_pb)
+    eng = graph.engine(net_boundary.resolve_device(""))
+    for path in shard:
+        if path in done:
+            continue
+        _, image_grey, sc = net_boundary.load_and_scale_image(path, fixed_height, args.scaling_factor)
+        _, u8, mask = eng.forward(image_grey, want_u8=True, want_mask=True, threshold=args.threshold)
+        stem = os.path.splitext(os.path.basename(path))[0]
+        cv2.imwrite(os.path.join(args.dump_dir, stem + "_prob.png"), np.ascontiguousarray(u8[0, :, :, 0]))
+        if args.mode == "separator":
+            cv2.imwrite(os.path.join(args.dump_dir, stem + "_mask.png"), np.ascontiguousarray(mask[0]))
+        done[path] = {"scale": sc, "shape": list(image_grey.shape)}
+        with open(manifest_path, "w") as f:
+            json.dump({"rank": rank, "world": world, "pages": done}, f)
+    return len(shard)
+
+
+def main(argv=None) -> int:
+    args = build_parser().parse_args(argv)
+    rank, world, local = sharding.rank_from_env()
+    if args.gpus and args.gpus > 1 and "RANK" not in os.environ:
+        procs = []
+        for r in range(args.gpus):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(args.gpus), LOCAL_RANK=str(r))
+            procs.append(subprocess.Popen([sys.executable, "-m", "aru_b200.run_net_post_processing"] + (argv or sys.argv[1:]),
+                                          env=env))
+        rcs = [p.wait() for p in procs]
+        if any(rcs):
+            raise SystemExit(f"rank exit codes {rcs}")
+        if args.dump_dir:   # every page must be in exactly one manifest
+            paths = net_boundary.load_image_paths(args.path_to_image_list)
+            seen = []
+            for r in range(args.gpus):
+                with open(os.path.join(args.dump_dir, f"manifest_rank{r}.json")) as f:
+                    seen += list(json.load(f)["pages"])
+            if sorted(seen) != sorted(paths):
+                raise SystemExit("page manifest does not cover the image list exactly once")
+        return 0
+    run_rank(args, rank, world, local)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

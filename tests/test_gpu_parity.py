@@ -203,3 +203,44 @@ def test_benchmark_size_properties(engines):
     np.testing.assert_allclose(a.sum(-1), 1.0, atol=1e-5)   # softmax over classes
     frac = float(_mask(a).mean())
     assert 0.001 < frac < 0.5, frac
+
+
+def test_cli_dump_matches_the_engine(tmp_path, engines):
+    """run_net_post_processing --dump_dir on two ranks' worth of pages == Engine.forward on the same scaled pages."""
+    import cv2
+    from aru_b200 import net_boundary
+    from aru_b200.run_net_post_processing import main
+    from aru_b200.synth import synth_pb, synth_page
+    pb = tmp_path / "sep.pb"
+    pb.write_bytes(synth_pb("separator"))
+    paths = []
+    for i, (h, w) in enumerate([(120, 90), (150, 100), (120, 90), (90, 130), (200, 64)]):
+        p = tmp_path / f"page_{i}.png"
+        cv2.imwrite(str(p), synth_page(h, w, 40 + i))
+        paths.append(str(p))
+    lst = tmp_path / "pages.lst"
+    lst.write_text("\n".join(paths) + "\n")
+    out = tmp_path / "out"
+    base = ["--path_to_image_list", str(lst), "--path_to_pb", str(pb), "--mode", "separator", "--fixed_height", "96",
+            "--dump_dir", str(out)]
+    env = dict(os.environ)
+    try:
+        for r in range(2):                                     # two ranks, run back to back on the one GPU
+            os.environ.update(RANK=str(r), WORLD_SIZE="2", LOCAL_RANK="0")
+            assert main(base) == 0
+    finally:
+        os.environ.clear()
+        os.environ.update(env)
+    import json
+    seen = []
+    for r in range(2):
+        seen += list(json.load(open(out / f"manifest_rank{r}.json"))["pages"])
+    assert sorted(seen) == sorted(paths)
+    eng = engines("separator")
+    for p in paths:
+        _, grey, _ = net_boundary.load_and_scale_image(p, 96, 1.0)
+        assert grey.shape[0] == 96
+        _, u8, mask = eng.forward(grey, want_u8=True, want_mask=True, threshold=0.05)
+        stem = os.path.splitext(os.path.basename(p))[0]
+        assert np.array_equal(cv2.imread(str(out / f"{stem}_prob.png"), cv2.IMREAD_UNCHANGED), u8[0, :, :, 0])
+        assert np.array_equal(cv2.imread(str(out / f"{stem}_mask.png"), cv2.IMREAD_UNCHANGED), mask[0])

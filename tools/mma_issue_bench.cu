@@ -61,7 +61,7 @@ __device__ __forceinline__ void umma_x8(uint32_t tmem_d, uint32_t a_lo, uint32_t
 constexpr int NITER = 4096;  // MMAs per issuer
 
 template <int VARIANT>
-__global__ void __launch_bounds__(256, 1) k_bench(int npad, long long* out_cycles) {
+__global__ void __launch_bounds__(256, 1) k_bench(int npad, long long* out_cycles, int a_off) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bars[4];
   __shared__ uint32_t tmem_ptr;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256, 1) k_bench(int npad, long long* out_cycle
   for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   const uint32_t s_a = smem_u32(smem), s_b = s_a + 40 * 1024;
   const uint32_t hi = (128u >> 4) | (1u << 14);
-  const uint32_t a_lo0 = (s_a >> 4) | ((16u >> 4) << 16);                   // LBO = 16 B (paired-tap style)
+  const uint32_t a_lo0 = ((s_a >> 4) + (uint32_t)a_off) | ((16u >> 4) << 16);  // LBO = 16 B (paired-tap style); a_off: misalignment in 16 B units
   const uint32_t b_lo0 = (s_b >> 4) | ((((uint32_t)npad * 16u) >> 4) << 16);
   if (threadIdx.x < 64) tab[threadIdx.x] = make_int2((int)(a_lo0 + threadIdx.x * 8), (int)b_lo0);
   if (threadIdx.x == 0)
@@ -144,23 +144,28 @@ __global__ void __launch_bounds__(256, 1) k_bench(int npad, long long* out_cycle
 }
 
 template <int V>
-void run(const char* name, int npad) {
+void run(const char* name, int npad, int a_off = 0) {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   long long* d;
   cudaMalloc(&d, sms * sizeof(long long));
   cudaFuncSetAttribute(k_bench<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  for (int rep = 0; rep < 2; ++rep) k_bench<V><<<sms, 256, 64 * 1024>>>(npad, d);
+  for (int rep = 0; rep < 2; ++rep) k_bench<V><<<sms, 256, 64 * 1024>>>(npad, d, a_off);
   cudaError_t e = cudaDeviceSynchronize();
   std::vector<long long> h(sms);
   cudaMemcpy(h.data(), d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
   std::sort(h.begin(), h.end());
-  printf("variant %d (%-44s) N=%3d: %7.1f cycles per MMA per issuer (median CTA)  %s\n", V, name, npad,
+  printf("variant %d (%-44s) N=%3d a_off=%d: %7.1f cycles per MMA per issuer (median CTA)  %s\n", V, name, npad, a_off,
          (double)h[sms / 2] / NITER, e == cudaSuccess ? "" : cudaGetErrorString(e));
   cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) {  // alignment sweep of the best variant: does a 16-byte-misaligned A start cost tensor-pipe time?
+    for (int npad : {16, 64})
+      for (int off : {0, 1, 3, 4, 7}) run<3>("warp + elect, unroll 8", npad, off);
+    return 0;
+  }
   for (int npad : {16, 64, 256}) {
     run<0>("1 lane, smem table, unroll 2", npad);
     run<1>("1 lane, arithmetic, rolled", npad);
