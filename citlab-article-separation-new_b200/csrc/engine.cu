@@ -33,6 +33,8 @@ struct OpWeights {
   // K-parts of a split launch (built lazily at plan time)
   struct TcImage { int ci_chunk_begin, ci_chunks; act_t* w; };
   std::vector<TcImage> tc_images;
+  act_t* band_w = nullptr;  // banded masters of conv_band.cu (depend on the filter only)
+  size_t band_bytes = 0;
   float* w32 = nullptr;     // stem [tap][cpad] / small [tap][cin_pad][cout]
   float* bias = nullptr;    // zero-padded to a multiple of 16
   int cin = 0, cout = 0;
@@ -58,6 +60,7 @@ struct Plan {
   int n = 0, h = 0, w = 0;
   std::vector<BufPlan> bufs;
   std::vector<std::vector<TcPart>> tc;  // per op: K-parts of the tensor-core launch (empty: other kernel)
+  std::vector<ConvBandPlan> band;       // per op: row-banded tensor-core launch (ok == false: other kernel)
   act_t* scratch = nullptr;             // partial sums of split-K launches
   size_t scratch_bytes = 0;
   std::vector<const char*> kernel;   // per op label
@@ -266,6 +269,10 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
         label = "conv_small";
         err = launch_conv_small(st, op.ksize, op.out.ch, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), ow.w32,
                                 ow.bias, bi.geo, op.act);
+      } else if (p->band[oi].ok) {
+        label = "conv_band";
+        err = launch_conv_band(st, p->band[oi], make_pv(e, p, op.in), make_pv(e, p, op.out), make_pv(e, p, op.out_pre),
+                               make_pv(e, p, op.res), ow.band_w, ow.bias, bo.geo, op.act, e->err_flag);
       } else if (!p->tc[oi].empty()) {
         // K-parts chain through the scratch buffer: part 0 adds the op's residual, the last part adds the
         // bias, applies the activation and writes the real outputs
@@ -391,6 +398,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   const int nb = (int)e->buffers.size(), no = (int)e->ops.size();
   p->bufs.resize(nb);
   p->tc.resize(no);
+  p->band.resize(no);
   p->kernel.assign(no, "?");
   for (int i = 0; i < nb; ++i) {
     p->bufs[i].kind = e->kind[i];
@@ -513,6 +521,24 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     }
     const Geo& geo = p->bufs[op.out.buf].geo;
     const int cin_chunks = cdiv(op.in.ch, 8);
+    if (e->conv_path == 0) {
+      // small C_out: output rows x channels on the MMA M axis (HBM bound instead of tensor-issue bound)
+      ConvBandPlan bp = conv_band_plan(op.ksize, op.in.ch, op.out.ch, geo, e->num_sms, e->max_smem);
+      if (bp.ok) {
+        OpWeights& ow = e->opw[i];
+        if (!ow.band_w || ow.band_bytes != bp.wpack_bytes) {
+          if (ow.band_w) { cudaFree(ow.band_w); ow.band_w = nullptr; }
+          std::vector<uint16_t> img(bp.wpack_bytes / 2);
+          conv_band_pack(bp, e->weights.data() + op.w_off, op.in.ch, op.out.ch, img.data());
+          uint16_t* dev = nullptr;
+          if ((rc = upload(e, img, &dev))) { free_plan(p.get()); return rc; }
+          ow.band_w = reinterpret_cast<act_t*>(dev);
+          ow.band_bytes = bp.wpack_bytes;
+        }
+        p->band[i] = bp;
+        continue;
+      }
+    }
     for (int parts = 1; parts <= 4 && p->tc[i].empty(); parts *= 2) {
       if (cin_chunks % parts || (parts > 1 && (cin_chunks / parts) % 2)) break;
       const int pc = cin_chunks / parts;
@@ -768,6 +794,7 @@ void aru_destroy(aru_engine* e) {
   for (auto& w : e->opw) {
     if (w.w16) cudaFree(w.w16);
     for (auto& im : w.tc_images) cudaFree(im.w);
+    if (w.band_w) cudaFree(w.band_w);
     if (w.w32) cudaFree(w.w32);
     if (w.bias) cudaFree(w.bias);
   }
@@ -783,7 +810,7 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
   if (!e) return ARU_EINVAL;
   switch (option) {
     case ARU_OPT_CONV_PATH:
-      if (value != 0 && value != 1) return fail(e, ARU_EINVAL, "ARU_OPT_CONV_PATH must be 0 or 1");
+      if (value < 0 || value > 2) return fail(e, ARU_EINVAL, "ARU_OPT_CONV_PATH must be 0, 1 or 2");
       if (e->conv_path != (int)value) {  // plans bake the kernel choice in
         cudaSetDevice(e->device);
         cudaDeviceSynchronize();

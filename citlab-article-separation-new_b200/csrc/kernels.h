@@ -89,6 +89,31 @@ cudaError_t launch_conv_tc(cudaStream_t st, const ConvTcPlan& plan, PV in, PV ou
 cudaError_t launch_conv_tc_f32(cudaStream_t st, const ConvTcPlan& plan, PV in, float* out_f32, int cout,
                                const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag);
 
+// ---- tcgen05 row-banded convolution for C_out <= 64 (conv_band.cu) ------------------------------
+// Output rows x channels on the MMA M axis, N = a strip of up to 256 output columns, banded weight masters as A.
+struct ConvBandPlan {
+  bool ok = false;
+  int ks = 0;
+  int cin_chunks = 0;
+  int cop = 0;           // C_out padded to a power of two (8..64); planes written = cop / 8
+  int R = 0;             // output rows per tile = 128 / cop
+  int J = 0;             // row groups of a banded master = 2R + ks - 2
+  int N = 0;             // output columns per tile (UMMA N, multiple of 16)
+  int n_strips = 0, n_ty = 0;
+  int S = 0;             // row slots of the input ring (even)
+  int n_masters = 0, n_steps = 0;
+  int grid = 0;
+  long long tiles = 0;
+  size_t smem_bytes = 0;
+  size_t wpack_bytes = 0;
+  const char* why = "";
+};
+ConvBandPlan conv_band_plan(int ks, int cin, int cout, const Geo& g, int num_sms, size_t max_smem);
+// TF filter [ks][ks][cin][cout] (float32) -> banded masters (16-bit), the kernel's resident shared-memory image
+void conv_band_pack(const ConvBandPlan& plan, const float* w_tf, int cin, int cout, uint16_t* dst);
+cudaError_t launch_conv_band(cudaStream_t st, const ConvBandPlan& plan, PV in, PV out, PV out_pre, PV res,
+                             const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag);
+
 // host-side 16-bit conversion matching act_t
 uint16_t host_f_to_act(float v);
 

@@ -58,7 +58,7 @@ __device__ __forceinline__ void umma_x8(uint32_t tmem_d, uint32_t a_lo, uint32_t
       ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(astep) : "memory");
 }
 
-constexpr int NITER = 4096;  // MMAs per issuer
+constexpr int NITER = 4080;  // multiple of 24  // MMAs per issuer
 
 template <int VARIANT>
 __global__ void __launch_bounds__(256, 1) k_bench(int npad, long long* out_cycles, int a_off) {
@@ -97,6 +97,26 @@ __global__ void __launch_bounds__(256, 1) k_bench(int npad, long long* out_cycle
       for (int i = 0; i < NITER; ++i) {
         const uint32_t a_lo = a_lo0 + (uint32_t)((i & 63) * 8);
         if (elect_one()) umma_f16(d, desc64(hi, a_lo), desc64(hi, b_lo0), idesc, 1u);
+      }
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+      while (!mbar_try_wait(bar, 0)) {}
+      t1 = clock64();
+    } else if (VARIANT == 8 || VARIANT == 9) {
+      // 8: accumulator rotates every MMA over 4 tiles, B changes every 4 MMAs (the conv kernel's t-inner order)
+      // 9: 6 consecutive MMAs into one accumulator with 6 different B images, then the next tile (k-inner order)
+      const uint32_t bstep = (uint32_t)(32 * npad) >> 4;
+      t0 = clock64();
+#pragma unroll 1
+      for (int i = 0; i < NITER; i += 24) {
+        const uint32_t a_base = a_lo0 + (uint32_t)((i & 63) * 8);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          const int t = VARIANT == 8 ? (j & 3) : (j / 6), k = VARIANT == 8 ? (j >> 2) : (j % 6);
+          if (elect_one())
+            umma_f16(d + (uint32_t)(t * npad), desc64(hi, a_base + (uint32_t)(t * 256 + (k >> 1) * 84 + (k & 1) * 2)),
+                     desc64(hi, b_lo0 + (uint32_t)k * bstep), idesc, k ? 1u : 0u);
+        }
       }
       if (elect_one()) umma_commit(bar);
       __syncwarp();
@@ -143,6 +163,70 @@ __global__ void __launch_bounds__(256, 1) k_bench(int npad, long long* out_cycle
   }
 }
 
+// Queue depth: time for the elected lane to get n MMAs *accepted* (clock right after the last issue), and until they retire.
+__global__ void __launch_bounds__(256, 1) k_queue(int npad, long long* out, int n) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[4];
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  const uint32_t s_a = smem_u32(smem), s_b = s_a + 40 * 1024;
+  const uint32_t hi = (128u >> 4) | (1u << 14);
+  const uint32_t a_lo0 = (s_a >> 4) | ((16u >> 4) << 16);
+  const uint32_t b_lo0 = (s_b >> 4) | ((((uint32_t)npad * 16u) >> 4) << 16);
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 7) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_ptr;
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(npad >> 3) << 17) | ((128u >> 4) << 24);
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (warp == 0) {
+    const uint32_t bar = smem_u32(&bars[0]);
+    uint32_t par = 0;
+    for (int rep = 0; rep < 3; ++rep) {  // last repetition is reported (warm instruction cache)
+      t0 = clock64();
+#pragma unroll 1
+      for (int i = 0; i < n; ++i)
+        if (elect_one()) umma_f16(tmem, desc64(hi, a_lo0 + (uint32_t)((i & 63) * 8)), desc64(hi, b_lo0), idesc, 1u);
+      t1 = clock64();
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+      while (!mbar_try_wait(bar, par)) {}
+      par ^= 1;
+      t2 = clock64();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) { out[2 * blockIdx.x] = t1 - t0; out[2 * blockIdx.x + 1] = t2 - t0; }
+  if (warp == 7) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+void run_queue(int npad) {
+  long long* d;
+  cudaMalloc(&d, 2 * sizeof(long long));
+  cudaFuncSetAttribute(k_queue, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int n : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64}) {
+    k_queue<<<1, 256, 64 * 1024>>>(npad, d, n);
+    cudaDeviceSynchronize();
+    long long h[2];
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("queue N=%3d: %2d MMAs accepted after %5lld cycles, retired after %5lld cycles\n", npad, n, h[0], h[1]);
+  }
+  cudaFree(d);
+}
+
 template <int V>
 void run(const char* name, int npad, int a_off = 0) {
   int sms = 0;
@@ -164,6 +248,12 @@ int main(int argc, char** argv) {
   if (argc > 1) {  // alignment sweep of the best variant: does a 16-byte-misaligned A start cost tensor-pipe time?
     for (int npad : {16, 64})
       for (int off : {0, 1, 3, 4, 7}) run<3>("warp + elect, unroll 8", npad, off);
+    run_queue(16);
+    run_queue(64);
+    for (int npad : {16, 32, 64}) {
+      run<8>("warp + elect, D rotates per MMA (t-inner)", npad);
+      run<9>("warp + elect, 6 MMAs per D (k-inner)", npad);
+    }
     return 0;
   }
   for (int npad : {16, 64, 256}) {
