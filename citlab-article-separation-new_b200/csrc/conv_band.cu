@@ -626,7 +626,7 @@ ConvBandPlan conv_band_plan(int ks, int cin, int cout, const Geo& g, int num_sms
   if (ks != 3 && ks != 4) { p.why = "kernel size"; return p; }
   int cop = 8;
   while (cop < cout) cop <<= 1;
-  if (cop > 32 || cin > 32) { p.why = "C > 32: N shrinks below the operand-read floor, the position-major kernel is faster"; return p; }
+  if (cop > 64 || cin > 64) { p.why = "C > 64: the position-major kernel is at its floor there"; return p; }
   if (cdiv(cout, 8) * 8 != cop) { p.why = "C_out planes are not a power of two"; return p; }
   if (p.cin_chunks != 1 && (p.cin_chunks & 1)) { p.why = "odd number of input chunks"; return p; }
   p.cop = cop;
@@ -725,11 +725,11 @@ cudaError_t launch_conv_band(cudaStream_t st, const ConvBandPlan& p, PV in, PV o
   Kern k = nullptr;
   int ki = -1;
 #define ARU_BAND_PICK(KK, NN, II) if (p.ks == KK && ncp == NN) { k = k_conv_band<KK, NN>; ki = II; }
-  ARU_BAND_PICK(3, 0, 0) ARU_BAND_PICK(3, 1, 1) ARU_BAND_PICK(3, 2, 2)
-  ARU_BAND_PICK(4, 0, 3) ARU_BAND_PICK(4, 1, 4) ARU_BAND_PICK(4, 2, 5)
+  ARU_BAND_PICK(3, 0, 0) ARU_BAND_PICK(3, 1, 1) ARU_BAND_PICK(3, 2, 2) ARU_BAND_PICK(3, 4, 6)
+  ARU_BAND_PICK(4, 0, 3) ARU_BAND_PICK(4, 1, 4) ARU_BAND_PICK(4, 2, 5) ARU_BAND_PICK(4, 4, 7)
 #undef ARU_BAND_PICK
   if (!k) return cudaErrorInvalidValue;
-  static bool configured[6] = {false, false, false, false, false, false};
+  static bool configured[8] = {false, false, false, false, false, false, false, false};
   if (!configured[ki]) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;

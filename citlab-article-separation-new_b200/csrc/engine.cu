@@ -10,8 +10,11 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -61,6 +64,7 @@ struct Plan {
   std::vector<BufPlan> bufs;
   std::vector<std::vector<TcPart>> tc;  // per op: K-parts of the tensor-core launch (empty: other kernel)
   std::vector<ConvBandPlan> band;       // per op: row-banded tensor-core launch (ok == false: other kernel)
+  std::vector<char> use_band;           // per op: the row-banded kernel won the plan-time timing (or is the only one)
   act_t* scratch = nullptr;             // partial sums of split-K launches
   size_t scratch_bytes = 0;
   std::vector<const char*> kernel;   // per op label
@@ -94,6 +98,9 @@ struct aru_engine {
   int* err_flag = nullptr;
   float* zero_bias = nullptr;
   std::vector<std::unique_ptr<Plan>> plans;
+  // plan-time kernel choice per (op, page height, page width): independent of the batch size, so that a page gives
+  // bit-identical results whatever micro-batch it travels in
+  std::map<std::tuple<int, int, int>, char> tune_cache;
   Plan* cur = nullptr;
   uint64_t tick = 0;
   std::string error;
@@ -269,7 +276,7 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
         label = "conv_small";
         err = launch_conv_small(st, op.ksize, op.out.ch, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), ow.w32,
                                 ow.bias, bi.geo, op.act);
-      } else if (p->band[oi].ok) {
+      } else if (p->band[oi].ok && p->use_band[oi]) {
         label = "conv_band";
         err = launch_conv_band(st, p->band[oi], make_pv(e, p, op.in), make_pv(e, p, op.out), make_pv(e, p, op.out_pre),
                                make_pv(e, p, op.res), ow.band_w, ow.bias, bo.geo, op.act, e->err_flag);
@@ -399,6 +406,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   p->bufs.resize(nb);
   p->tc.resize(no);
   p->band.resize(no);
+  p->use_band.assign(no, 0);
   p->kernel.assign(no, "?");
   for (int i = 0; i < nb; ++i) {
     p->bufs[i].kind = e->kind[i];
@@ -521,7 +529,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     }
     const Geo& geo = p->bufs[op.out.buf].geo;
     const int cin_chunks = cdiv(op.in.ch, 8);
-    if (e->conv_path == 0) {
+    if (e->conv_path == 0 || e->conv_path == 3) {
       // small C_out: output rows x channels on the MMA M axis (HBM bound instead of tensor-issue bound)
       ConvBandPlan bp = conv_band_plan(op.ksize, op.in.ch, op.out.ch, geo, e->num_sms, e->max_smem);
       if (bp.ok) {
@@ -536,7 +544,8 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
           ow.band_bytes = bp.wpack_bytes;
         }
         p->band[i] = bp;
-        continue;
+        p->use_band[i] = 1;
+        if (e->conv_path == 3) continue;   // forced: no position-major alternative is planned
       }
     }
     for (int parts = 1; parts <= 4 && p->tc[i].empty(); parts *= 2) {
@@ -556,6 +565,46 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     }
   }
   if (p->scratch_bytes) CU(e, cudaMalloc((void**)&p->scratch, p->scratch_bytes));
+  // Ops both tensor-core kernels cover: time each on this plan's geometry and keep the faster (the timing does not
+  // depend on the data; ARU_AUTOTUNE=0 keeps the row-banded kernel wherever it applies).
+  {
+    const char* env = getenv("ARU_AUTOTUNE");
+    const bool tune = !(env && env[0] == '0');
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    for (int i = 0; i < no && tune; ++i) {
+      if (!p->band[i].ok || p->tc[i].empty()) continue;
+      const auto key = std::make_tuple(i, h, w);
+      const auto hit = e->tune_cache.find(key);
+      if (hit != e->tune_cache.end()) { p->use_band[i] = hit->second; continue; }
+      {
+        // small launches are timing noise: fixed rule (keeps small-page results identical from process to process)
+        const Geo& og = p->bufs[e->ops[i].out.buf].geo;
+        if ((long long)og.N * og.H * og.W < (1LL << 21)) {
+          p->use_band[i] = p->band[i].cop <= 16 ? 1 : 0;
+          e->tune_cache[key] = p->use_band[i];
+          continue;
+        }
+      }
+      if (!ev0) { CU(e, cudaEventCreate(&ev0)); CU(e, cudaEventCreate(&ev1)); }
+      float best[2] = {1e30f, 1e30f};
+      for (int which = 0; which < 2; ++which) {
+        p->use_band[i] = (char)which;
+        for (int rep = 0; rep < 3; ++rep) {
+          CU(e, cudaEventRecord(ev0, e->s_comp));
+          if ((rc = run_op(e, p.get(), i, 0, e->s_comp))) { free_plan(p.get()); return rc; }
+          CU(e, cudaEventRecord(ev1, e->s_comp));
+          CU(e, cudaEventSynchronize(ev1));
+          float ms = 0.f;
+          CU(e, cudaEventElapsedTime(&ms, ev0, ev1));
+          if (rep > 0) best[which] = std::min(best[which], ms);
+        }
+      }
+      p->use_band[i] = best[1] < 1.03f * best[0] ? 1 : 0;   // ties go to the row-banded kernel
+      e->tune_cache[key] = p->use_band[i];
+    }
+    if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+    if ((rc = check_err_flag(e))) { free_plan(p.get()); return rc; }
+  }
   // one eager pass (sets function attributes, validates every launch), then capture
   rc = run_all(e, p.get(), 0, e->s_comp);
   if (rc) { free_plan(p.get()); return rc; }
@@ -810,7 +859,7 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
   if (!e) return ARU_EINVAL;
   switch (option) {
     case ARU_OPT_CONV_PATH:
-      if (value < 0 || value > 2) return fail(e, ARU_EINVAL, "ARU_OPT_CONV_PATH must be 0, 1 or 2");
+      if (value < 0 || value > 3) return fail(e, ARU_EINVAL, "ARU_OPT_CONV_PATH must be 0..3");
       if (e->conv_path != (int)value) {  // plans bake the kernel choice in
         cudaSetDevice(e->device);
         cudaDeviceSynchronize();

@@ -95,8 +95,9 @@ typedef struct aru_graph_desc {
 typedef struct aru_engine aru_engine;
 
 /* engine options (aru_set_option) */
-#define ARU_OPT_CONV_PATH 1   /* 0 = auto (tcgen05: row-banded kernel for C_out <= 64, position-major otherwise),
-                                 1 = force the CUDA-core kernels (validation), 2 = tcgen05 position-major kernel only */
+#define ARU_OPT_CONV_PATH 1   /* 0 = auto (tcgen05; where both the row-banded and the position-major kernel apply, the
+                                     faster one by a plan-time timing), 1 = force the CUDA-core kernels (validation),
+                                 2 = tcgen05 position-major kernel only, 3 = row-banded kernel wherever it applies */
 #define ARU_OPT_USE_GRAPH 2   /* 1 = replay a captured CUDA graph per plan (default), 0 = plain launches */
 #define ARU_OPT_MICRO_BATCH 3 /* pages per pass through the net inside aru_forward (0 = auto) */
 
