@@ -162,7 +162,7 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
             px_mac = ih * iw if op.kind == P.OP_DECONV else oh * ow
             flops = 2.0 * n * px_mac * op.ksize * op.ksize * op.inp.ch * op.out.ch
             in_b = 4 if op.inp.ch == 1 else 2
-            out_b = 4 if kernel == "conv_small" else 2
+            out_b = 4 if kernel in ("conv_small", "conv_tc_head", "conv_band_head") else 2
             bytes_ = n * (ih * iw * op.inp.ch * in_b + oh * ow * op.out.ch * out_b)
             if op.res.buf >= 0:
                 bytes_ += n * oh * ow * op.out.ch * 2
@@ -183,7 +183,8 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
         c = classes.setdefault(kernel, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         c["ms"] += ms; c["flops"] += flops; c["bytes"] += bytes_; c["launches"] += 1
         if op.kind in (P.OP_CONV, P.OP_DECONV):
-            key = f"{kernel} {op.ksize}x{op.ksize} {op.inp.ch}->{op.out.ch} {oh}x{ow} n{n}"
+            key = (f"{kernel} {op.ksize}x{op.ksize} {op.inp.ch}->{op.out.ch} {oh}x{ow} n{n}"
+                   + ("+res" if op.res.buf >= 0 else "") + ("+pre" if op.out_pre.buf >= 0 else ""))
             sgrp = shapes.setdefault(key, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
             sgrp["ms"] += ms; sgrp["flops"] += flops; sgrp["bytes"] += bytes_; sgrp["launches"] += 1
     total_ms = sum(c["ms"] for c in classes.values())

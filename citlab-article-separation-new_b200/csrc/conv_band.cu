@@ -74,6 +74,9 @@ struct ConvBandArgs {
   long long lead;
   long long tiles;
   int act;
+  // dense float32 NHWC output [N][H][W][f32_c] with the head activation (classifier / attention logit), else null
+  float* out_f32;
+  int f32_c;
   int* err_flag;
   int dbg;
 };
@@ -251,7 +254,9 @@ __device__ __forceinline__ TileRef tile_ref(long long L, int n_strips, int n_ty)
 }
 
 // KS: filter size.  NCP: channel-chunk pairs per tap (C_in / 16), 0 for C_in = 8 (tap pairs instead).
-template <int KS, int NCP>
+// HEAD: dense float32 NHWC output with the head activation instead of 16-bit planes (separate instances keep the
+// plane path free of its registers and branches).
+template <int KS, int NCP, bool HEAD>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_constant__ ConvBandArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -490,6 +495,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
             c_se += clock64() - c1;
             uint8_t* my_st = slabs + b * SLAB_BYTES + st_off;
             tmem_ld_wait();
+            if constexpr (HEAD) {
+              // head: the logits of the (<= 4) real channels stay fp32 through the slab, 16 B per position
+              if ((m & 7) < 4) {
+                float* fs = reinterpret_cast<float*>(slabs + b * SLAB_BYTES + (m >> 3) * SLAB_ROW + (m & 7) * 4);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) fs[k * 4] = __uint_as_float(v[k]) + bias;
+              }
+            } else
 #pragma unroll
             for (int k = 0; k < 32; k += 2) {
               const uint32_t h2 = pack2_raw(__uint_as_float(v[k]) + bias, __uint_as_float(v[k + 1]) + bias);
@@ -586,7 +599,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
             if (lane == 0) mbar_arrive(s_sempty + 8 * b);   // the slab is in registers
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (xv && gv[k]) {
+              if (HEAD && xv && gv[k]) {
+                // classifier / attention-logit head (cop = 8, one chunk): fp32 logits -> activation -> dense NHWC
+                const int C = a.f32_c;
+                const int y = y_top + (a.R - 1 - (q4 + 4 * k));
+                float* o = a.out_f32 + (((long long)tr.n * a.H + y) * a.W + (x_left + xl)) * C;
+                float z[4] = {__uint_as_float(raw[k].x), __uint_as_float(raw[k].y), __uint_as_float(raw[k].z), __uint_as_float(raw[k].w)};
+                if (a.act == 2 && C == 2) {   // two-class softmax (layers.py:48-49): the shipped separator / heading nets
+                  const float mx = fmaxf(z[0], z[1]);
+                  const float e0 = __expf(z[0] - mx), e1 = __expf(z[1] - mx);
+                  const float inv = __fdividef(1.f, e0 + e1);
+                  *reinterpret_cast<float2*>(o) = make_float2(e0 * inv, e1 * inv);
+                } else {
+                  if (a.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) z[j] = fmaxf(z[j], 0.f);
+                  } else if (a.act == 2) {
+                    float mx = z[0];
+                    for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
+                    float sum = 0.f;
+                    for (int j = 0; j < C; ++j) { z[j] = __expf(z[j] - mx); sum += z[j]; }
+                    const float inv = __fdividef(1.f, sum);
+                    for (int j = 0; j < C; ++j) z[j] *= inv;
+                  } else if (a.act == 3) {
+                    for (int j = 0; j < C; ++j) z[j] = __fdividef(1.f, 1.f + __expf(-z[j]));
+                  }
+                  for (int j = 0; j < C; ++j) o[j] = z[j];
+                }
+              } else if (!HEAD && xv && gv[k]) {
                 const int c = (q4 + 4 * k) & nc_mask;
                 const long long p8 = gpos[k] + (long long)xl * 8;
                 uint4 val = raw[k];
@@ -699,9 +739,11 @@ void conv_band_pack(const ConvBandPlan& p, const float* w, int cin, int cout, ui
 }
 
 cudaError_t launch_conv_band(cudaStream_t st, const ConvBandPlan& p, PV in, PV out, PV out_pre, PV res, const act_t* wpack,
-                             const float* bias_pad, const Geo& g, int act, int* err_flag) {
+                             const float* bias_pad, const Geo& g, int act, int* err_flag, float* out_f32, int f32_c) {
   if (!p.ok) return cudaErrorInvalidValue;
+  if (out_f32 && (p.cop != 8 || f32_c < 1 || f32_c > 4)) return cudaErrorInvalidValue;
   ConvBandArgs a{};
+  a.out_f32 = out_f32; a.f32_c = f32_c;
   a.in = in.p; a.in_plane = in.plane;
   a.out = out.p; a.out_plane = out.plane;
   a.out_pre = out_pre.p; a.pre_plane = out_pre.plane;
@@ -724,12 +766,14 @@ cudaError_t launch_conv_band(cudaStream_t st, const ConvBandPlan& p, PV in, PV o
   const int ncp = p.cin_chunks == 1 ? 0 : p.cin_chunks / 2;
   Kern k = nullptr;
   int ki = -1;
-#define ARU_BAND_PICK(KK, NN, II) if (p.ks == KK && ncp == NN) { k = k_conv_band<KK, NN>; ki = II; }
-  ARU_BAND_PICK(3, 0, 0) ARU_BAND_PICK(3, 1, 1) ARU_BAND_PICK(3, 2, 2) ARU_BAND_PICK(3, 4, 6)
-  ARU_BAND_PICK(4, 0, 3) ARU_BAND_PICK(4, 1, 4) ARU_BAND_PICK(4, 2, 5) ARU_BAND_PICK(4, 4, 7)
+  const bool head = out_f32 != nullptr;
+#define ARU_BAND_PICK(KK, NN, HH, II) if (p.ks == KK && ncp == NN && head == HH) { k = k_conv_band<KK, NN, HH>; ki = II; }
+  ARU_BAND_PICK(3, 0, false, 0) ARU_BAND_PICK(3, 1, false, 1) ARU_BAND_PICK(3, 2, false, 2) ARU_BAND_PICK(3, 4, false, 6)
+  ARU_BAND_PICK(4, 0, false, 3) ARU_BAND_PICK(4, 1, false, 4) ARU_BAND_PICK(4, 2, false, 5) ARU_BAND_PICK(4, 4, false, 7)
+  ARU_BAND_PICK(3, 0, true, 8) ARU_BAND_PICK(4, 0, true, 9)
 #undef ARU_BAND_PICK
   if (!k) return cudaErrorInvalidValue;
-  static bool configured[8] = {false, false, false, false, false, false, false, false};
+  static bool configured[10] = {false, false, false, false, false, false, false, false, false, false};
   if (!configured[ki]) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;

@@ -268,6 +268,10 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
         err = launch_conv_stem(st, op.ksize, f32_ptr(e, p, op.in.buf, parity), make_pv(e, p, op.out),
                                make_pv(e, p, op.out_pre), e->weights.data() + op.w_off, e->weights.data() + op.b_off,
                                bo.geo, op.act);
+      } else if (bo.kind != KIND_PLANAR && p->band[oi].ok && p->use_band[oi]) {
+        label = "conv_band_head";
+        err = launch_conv_band(st, p->band[oi], make_pv(e, p, op.in), PV(), PV(), PV(), ow.band_w, ow.bias, bi.geo, op.act,
+                               e->err_flag, f32_ptr(e, p, op.out.buf, parity), op.out.ch);
       } else if (bo.kind != KIND_PLANAR && !p->tc[oi].empty()) {
         label = "conv_tc_head";
         err = launch_conv_tc_f32(st, p->tc[oi][0].plan, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), op.out.ch,
@@ -498,6 +502,26 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     CU(e, cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
     CU(e, cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming));
   }
+  // row-banded tensor-core plan of conv op i (+ its banded weight masters, cached per engine)
+  auto plan_band = [&](int i, const Geo& geo) -> int {
+    const aru_op& op = e->ops[i];
+    ConvBandPlan bp = conv_band_plan(op.ksize, op.in.ch, op.out.ch, geo, e->num_sms, e->max_smem);
+    if (!bp.ok) return ARU_OK;
+    OpWeights& ow = e->opw[i];
+    if (!ow.band_w || ow.band_bytes != bp.wpack_bytes) {
+      if (ow.band_w) { cudaFree(ow.band_w); ow.band_w = nullptr; }
+      std::vector<uint16_t> img(bp.wpack_bytes / 2);
+      conv_band_pack(bp, e->weights.data() + op.w_off, op.in.ch, op.out.ch, img.data());
+      uint16_t* dev = nullptr;
+      int rc2 = upload(e, img, &dev);
+      if (rc2) return rc2;
+      ow.band_w = reinterpret_cast<act_t*>(dev);
+      ow.band_bytes = bp.wpack_bytes;
+    }
+    p->band[i] = bp;
+    p->use_band[i] = 1;
+    return ARU_OK;
+  };
   // kernel selection for the chunk-planar convolutions
   for (int i = 0; i < no; ++i) {
     const aru_op& op = e->ops[i];
@@ -517,6 +541,10 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     if (p->bufs[op.in.buf].kind != KIND_PLANAR) continue;
     if (p->bufs[op.out.buf].kind != KIND_PLANAR) {
       // float32-output head (attention logit, classifier): one launch, no split-K
+      if ((e->conv_path == 0 || e->conv_path == 3) && op.out.ch <= 4 && op.in.ch <= 8) {   // the classifier head
+        if ((rc = plan_band(i, p->bufs[op.in.buf].geo))) { free_plan(p.get()); return rc; }
+        if (p->band[i].ok && e->conv_path == 3) continue;
+      }
       ConvTcPlan tp = conv_tc_plan(op.ksize, op.in.ch, op.out.ch, p->bufs[op.in.buf].geo, e->num_sms, e->max_smem);
       if (tp.ok && tp.cout_chunks == 1) {
         TcPart part;
@@ -531,22 +559,8 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     const int cin_chunks = cdiv(op.in.ch, 8);
     if (e->conv_path == 0 || e->conv_path == 3) {
       // small C_out: output rows x channels on the MMA M axis (HBM bound instead of tensor-issue bound)
-      ConvBandPlan bp = conv_band_plan(op.ksize, op.in.ch, op.out.ch, geo, e->num_sms, e->max_smem);
-      if (bp.ok) {
-        OpWeights& ow = e->opw[i];
-        if (!ow.band_w || ow.band_bytes != bp.wpack_bytes) {
-          if (ow.band_w) { cudaFree(ow.band_w); ow.band_w = nullptr; }
-          std::vector<uint16_t> img(bp.wpack_bytes / 2);
-          conv_band_pack(bp, e->weights.data() + op.w_off, op.in.ch, op.out.ch, img.data());
-          uint16_t* dev = nullptr;
-          if ((rc = upload(e, img, &dev))) { free_plan(p.get()); return rc; }
-          ow.band_w = reinterpret_cast<act_t*>(dev);
-          ow.band_bytes = bp.wpack_bytes;
-        }
-        p->band[i] = bp;
-        p->use_band[i] = 1;
-        if (e->conv_path == 3) continue;   // forced: no position-major alternative is planned
-      }
+      if ((rc = plan_band(i, geo))) { free_plan(p.get()); return rc; }
+      if (p->band[i].ok && e->conv_path == 3) continue;   // forced: no position-major alternative is planned
     }
     for (int parts = 1; parts <= 4 && p->tc[i].empty(); parts *= 2) {
       if (cin_chunks % parts || (parts > 1 && (cin_chunks / parts) % 2)) break;
@@ -578,7 +592,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       if (hit != e->tune_cache.end()) { p->use_band[i] = hit->second; continue; }
       {
         // small launches are timing noise: fixed rule (keeps small-page results identical from process to process)
-        const Geo& og = p->bufs[e->ops[i].out.buf].geo;
+        const Geo& og = p->bufs[e->ops[i].in.buf].geo;
         if ((long long)og.N * og.H * og.W < (1LL << 21)) {
           p->use_band[i] = p->band[i].cop <= 16 ? 1 : 0;
           e->tune_cache[key] = p->use_band[i];
@@ -902,8 +916,21 @@ int aru_forward(aru_engine* e, const float* in, int n, int h, int w, float* out,
   const int C = e->n_class;
   int slot = 0;
   std::vector<Plan*> used;
-  for (int i0 = 0; i0 < n; i0 += mb, ++slot) {
-    const int cnt = std::min(mb, n - i0);
+  // Micro-batch schedule.  The host->device copy of the first micro-batch and the device->host copy of the last one
+  // cannot overlap with compute, so those two are half size: [mb/2, mb, ..., mb, (rest), mb/2].
+  std::vector<int> sched;
+  if (n > mb && mb >= 4) {
+    const int edge = mb / 2;
+    sched.push_back(edge);
+    int left = n - 2 * edge;
+    while (left > 0) { sched.push_back(std::min(mb, left)); left -= sched.back(); }
+    sched.push_back(edge);
+  } else {
+    for (int left = n; left > 0; left -= mb) sched.push_back(std::min(mb, left));
+  }
+  int i0 = 0;
+  for (size_t si = 0; si < sched.size(); i0 += sched[si], ++si, ++slot) {
+    const int cnt = sched[si];
     Plan* p = nullptr;
     int rc = get_plan(e, cnt, h, w, &p);
     if (rc) return rc;

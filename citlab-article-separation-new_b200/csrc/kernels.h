@@ -111,8 +111,10 @@ struct ConvBandPlan {
 ConvBandPlan conv_band_plan(int ks, int cin, int cout, const Geo& g, int num_sms, size_t max_smem);
 // TF filter [ks][ks][cin][cout] (float32) -> banded masters (16-bit), the kernel's resident shared-memory image
 void conv_band_pack(const ConvBandPlan& plan, const float* w_tf, int cin, int cout, uint16_t* dst);
+// out_f32 != null: small-C_out head (C_out <= 4) writing dense float32 NHWC with ReLU / softmax / sigmoid instead of planes
 cudaError_t launch_conv_band(cudaStream_t st, const ConvBandPlan& plan, PV in, PV out, PV out_pre, PV res,
-                             const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag);
+                             const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag,
+                             float* out_f32 = nullptr, int f32_c = 0);
 
 // host-side 16-bit conversion matching act_t
 uint16_t host_f_to_act(float v);

@@ -41,7 +41,7 @@ for i, (op, (name, kernel, ms)) in enumerate(zip(eng.program.ops, prof)):
         px = ih * iw if op.kind == P.OP_DECONV else oh * ow
         flops = 2.0 * n * px * op.ksize ** 2 * op.inp.ch * op.out.ch
     ib = 4 if op.inp.ch == 1 else 2
-    ob = 4 if kernel == "conv_small" else 2
+    ob = 4 if kernel in ("conv_small", "conv_tc_head", "conv_band_head") else 2
     bytes_ = n * (ih * iw * op.inp.ch * ib + oh * ow * op.out.ch * ob)
     if op.res.buf >= 0:
         bytes_ += n * oh * ow * op.out.ch * 2

@@ -47,7 +47,7 @@ def diag(net, h, w, n=1, max_report=4):
     bad = 0
     for op in eng.program.ops:
         k = vals[0]["kernels"].get(op.name)
-        if not ((k or "").startswith("conv_tc") or k in ("deconv_tc", "conv_band")):
+        if not ((k or "").startswith("conv_tc") or k in ("deconv_tc", "conv_band", "conv_band_head")):
             continue
         # the op's output node: find by view
         for node, v in eng.program.tensor_of_node.items():
