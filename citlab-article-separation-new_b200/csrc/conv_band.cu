@@ -74,6 +74,10 @@ struct ConvBandArgs {
   long long lead;
   long long tiles;
   int act;
+  // fused 2x2 stride-2 max-pool of the (ReLU'd) output into a second chunk-planar tensor, else null
+  act_t* pool_out;
+  long long pool_plane, lead_o;
+  int Wpo, Hpo;
   // dense float32 NHWC output [N][H][W][f32_c] with the head activation (classifier / attention logit), else null
   float* out_f32;
   int f32_c;
@@ -239,6 +243,14 @@ __device__ __forceinline__ uint4 add8(uint4 x, const uint4& y) {
   return x;
 }
 
+__device__ __forceinline__ uint4 max8(uint4 x, const uint4& y) {
+  act2_t* a = reinterpret_cast<act2_t*>(&x);
+  const act2_t* b = reinterpret_cast<const act2_t*>(&y);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = __hmax2(a[i], b[i]);
+  return x;
+}
+
 // tile index -> page, strip, row tile
 struct TileRef {
   int n, s, ty;
@@ -256,7 +268,8 @@ __device__ __forceinline__ TileRef tile_ref(long long L, int n_strips, int n_ty)
 // KS: filter size.  NCP: channel-chunk pairs per tap (C_in / 16), 0 for C_in = 8 (tap pairs instead).
 // HEAD: dense float32 NHWC output with the head activation instead of 16-bit planes (separate instances keep the
 // plane path free of its registers and branches).
-template <int KS, int NCP, bool HEAD>
+// POOL: fused max-pool output (plane path only).
+template <int KS, int NCP, bool HEAD, bool POOL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_constant__ ConvBandArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
     }
     for (int i = 0; i < N_SLAB_BUF; ++i) {
       mbar_init(s_sfull + 8 * i, 4);
-      mbar_init(s_sempty + 8 * i, 4);
+      mbar_init(s_sempty + 8 * i, 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -526,118 +539,128 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
         // ---- store warps: slab -> position-major 16 B vectors -> (+ residual) -> activation -> 512 B coalesced stores
         const bool has_res = a.res != nullptr, has_pre = a.out_pre != nullptr, relu = a.act == 1;
         const int nc_mask = (1 << a.nc_shift) - 1;
-        // two store groups (warps 8-11 / 12-15) take alternate slabs of the ring: twice the loads and stores in flight
-        const int sg = (warp - 8) >> 2;
-        int g = 0;                     // slab sequence number over all tiles
+        // Each of the 8 store warps owns two row segments of every slab (lane = column): the two image rows of a 2x2
+        // pooling window in one channel chunk, so a fused max-pool never leaves the warp.  rs = rho * nc + chunk.
+        const int pp = warp - 8;                       // vertical pair 0..7
+        const int cch = pp & nc_mask;                  // channel chunk
+        const int rho0 = 2 * (pp >> a.nc_shift);       // rho of k = 0 (odd image row); k = 1 is rho0 + 1 (the even row above)
+        const int rs0 = (rho0 << a.nc_shift) + cch, rs1 = rs0 + (1 << a.nc_shift);
+        const long long out_c = (long long)cch * a.out_plane * 8, pre_c = (long long)cch * a.pre_plane * 8,
+                        res_c = (long long)cch * a.res_plane * 8;
+        int b = 0;
+        uint32_t bpar = 0;
         TileRef tr = tile_ref(L0, a.n_strips, a.n_ty);
         long long c_sf = 0;
         for (int t = 0; t < n_tiles; ++t) {
           const int y_top = tr.ty * a.R, x_left = tr.s * a.N;
-          // this warp owns row segments q4, q4+4, q4+8, q4+12 of every slab; lane = column inside the slab
-          long long gpos[4];   // element offset of (row, column x_left) for each owned row segment
-          bool gv[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int rho = (q4 + 4 * k) >> a.nc_shift;
-            const int y = y_top + (a.R - 1 - rho);
-            gv[k] = y < a.H;
-            gpos[k] = (a.lead + ((long long)tr.n * a.Hp + y + 1) * a.Wp + (x_left + 1)) * 8;
-          }
-          uint4 rr[4];
+          const int y1 = y_top + (a.R - 2 - rho0);     // even image row (k = 1); k = 0 is y1 + 1
+          const bool gv[2] = {y1 + 1 < a.H, y1 < a.H};
+          // element offset of (row y1, column x_left); row k = 0 is one padded row further
+          const long long gp1 = (a.lead + ((long long)tr.n * a.Hp + y1 + 1) * a.Wp + (x_left + 1)) * 8;
+          const long long row8 = (long long)a.Wp * 8;
+          long long ppos = 0;   // element offset of the pooled row (column x_left / 2)
+          if constexpr (POOL)
+            ppos = ((long long)cch * a.pool_plane + a.lead_o + ((long long)tr.n * a.Hpo + (y1 >> 1) + 1) * a.Wpo + (x_left >> 1) + 1) * 8;
+          float* fo = nullptr;
+          if constexpr (HEAD) fo = a.out_f32 + (((long long)tr.n * a.H + y1) * a.W + x_left) * a.f32_c;
+          uint4 rr[2];
           if (has_res) {
-            // Residual of the NEXT tile -> L2 now (one 128 B line per lane and row segment): the register prefetch below
-            // only reaches one slab ahead, which covers an L2 hit but not DRAM latency.
+            // Residual of the NEXT tile -> L2 now (one 128 B line per lane and row): the register prefetch below only
+            // reaches one slab ahead, which covers an L2 hit but not DRAM latency.
             TileRef nx = tr;
             if (++nx.ty == a.n_ty) { nx.ty = 0; if (++nx.s == a.n_strips) { nx.s = 0; ++nx.n; } }
-            if (t + 1 < n_tiles && sg == 0) {
+            if (t + 1 < n_tiles) {
               const int cols = min(a.N, a.W - nx.s * a.N);
+              const int yn = nx.ty * a.R + (a.R - 2 - rho0);
               if (lane * 8 < cols) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int rs = q4 + 4 * k;
-                  const int y = nx.ty * a.R + (a.R - 1 - (rs >> a.nc_shift));
-                  if (y < a.H) {
-                    const long long pos = a.lead + ((long long)nx.n * a.Hp + y + 1) * a.Wp + (nx.s * a.N + 1) + lane * 8;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + ((long long)(rs & nc_mask) * a.res_plane + pos) * 8));
-                  }
-                }
+                const long long pos = a.lead + ((long long)nx.n * a.Hp + yn + 1) * a.Wp + (nx.s * a.N + 1) + lane * 8;
+                if (yn < a.H) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + res_c + pos * 8));
+                if (yn + 1 < a.H) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + res_c + (pos + a.Wp) * 8));
               }
             }
-            const int x0 = ((g ^ sg) & 1) * SLAB + lane;   // column in this group's first slab of the tile
-            const bool xv = (x0 < a.N) && (x_left + x0 < a.W);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              rr[k] = ldg_nc_v4(a.res + (long long)((q4 + 4 * k) & nc_mask) * a.res_plane * 8 + gpos[k] + (long long)x0 * 8,
-                                xv && gv[k]);
+            const bool xv = (lane < a.N) && (x_left + lane < a.W);
+            rr[0] = ldg_nc_v4(a.res + res_c + gp1 + row8 + (long long)lane * 8, xv && gv[0]);
+            rr[1] = ldg_nc_v4(a.res + res_c + gp1 + (long long)lane * 8, xv && gv[1]);
           }
-          const int sb0 = (g ^ sg) & 1;   // first slab of this tile that belongs to this group
-          g += n_slabs;
 #pragma unroll 1
-          for (int sb = sb0; sb < n_slabs; sb += 2) {
-            const int gs = g - n_slabs + sb;
-            const int b = gs & (N_SLAB_BUF - 1);
-            const uint32_t bpar = (uint32_t)(gs / N_SLAB_BUF) & 1u;
+          for (int sb = 0; sb < n_slabs; ++sb) {
             const int xl = sb * SLAB + lane;
             const bool xv = (xl < a.N) && (x_left + xl < a.W);
-            uint4 rn[4];
-            if (has_res && sb + 2 < n_slabs) {   // residual vectors of this group's next slab: two slab times of latency hiding
-              const int xn = xl + 2 * SLAB;
+            uint4 rn[2];
+            if (has_res && sb + 1 < n_slabs) {   // residual vectors of the next slab: a slab time of latency hiding
+              const int xn = xl + SLAB;
               const bool xnv = (xn < a.N) && (x_left + xn < a.W);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                rn[k] = ldg_nc_v4(a.res + (long long)((q4 + 4 * k) & nc_mask) * a.res_plane * 8 + gpos[k] + (long long)xn * 8,
-                                  xnv && gv[k]);
+              rn[0] = ldg_nc_v4(a.res + res_c + gp1 + row8 + (long long)xn * 8, xnv && gv[0]);
+              rn[1] = ldg_nc_v4(a.res + res_c + gp1 + (long long)xn * 8, xnv && gv[1]);
             }
             long long c2 = clock64();
             mbar_wait_sleep(s_sfull + 8 * b, bpar, a.err_flag, 6);
             c_sf += clock64() - c2;
             const uint8_t* slab = slabs + b * SLAB_BYTES;
-            uint4 raw[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) raw[k] = *reinterpret_cast<const uint4*>(slab + (q4 + 4 * k) * SLAB_ROW + lane * 16);
+            uint4 raw[2];
+            raw[0] = *reinterpret_cast<const uint4*>(slab + rs0 * SLAB_ROW + lane * 16);
+            raw[1] = *reinterpret_cast<const uint4*>(slab + rs1 * SLAB_ROW + lane * 16);
             __syncwarp();
             if (lane == 0) mbar_arrive(s_sempty + 8 * b);   // the slab is in registers
+            if (++b == N_SLAB_BUF) { b = 0; bpar ^= 1u; }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (HEAD && xv && gv[k]) {
-                // classifier / attention-logit head (cop = 8, one chunk): fp32 logits -> activation -> dense NHWC
-                const int C = a.f32_c;
-                const int y = y_top + (a.R - 1 - (q4 + 4 * k));
-                float* o = a.out_f32 + (((long long)tr.n * a.H + y) * a.W + (x_left + xl)) * C;
-                float z[4] = {__uint_as_float(raw[k].x), __uint_as_float(raw[k].y), __uint_as_float(raw[k].z), __uint_as_float(raw[k].w)};
-                if (a.act == 2 && C == 2) {   // two-class softmax (layers.py:48-49): the shipped separator / heading nets
-                  const float mx = fmaxf(z[0], z[1]);
-                  const float e0 = __expf(z[0] - mx), e1 = __expf(z[1] - mx);
-                  const float inv = __fdividef(1.f, e0 + e1);
-                  *reinterpret_cast<float2*>(o) = make_float2(e0 * inv, e1 * inv);
-                } else {
-                  if (a.act == 1) {
+            for (int k = 0; k < 2; ++k) {
+              if constexpr (HEAD) {
+                if (xv && gv[k]) {
+                  // classifier / attention-logit head (cop = 8, one chunk): fp32 logits -> activation -> dense NHWC
+                  const int C = a.f32_c;
+                  float* o = fo + ((long long)(1 - k) * a.W + xl) * C;
+                  float z[4] = {__uint_as_float(raw[k].x), __uint_as_float(raw[k].y), __uint_as_float(raw[k].z), __uint_as_float(raw[k].w)};
+                  if (a.act == 2 && C == 2) {   // two-class softmax (layers.py:48-49): the shipped separator / heading nets
+                    const float mx = fmaxf(z[0], z[1]);
+                    const float e0 = __expf(z[0] - mx), e1 = __expf(z[1] - mx);
+                    const float inv = __fdividef(1.f, e0 + e1);
+                    *reinterpret_cast<float2*>(o) = make_float2(e0 * inv, e1 * inv);
+                  } else {
+                    if (a.act == 1) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) z[j] = fmaxf(z[j], 0.f);
-                  } else if (a.act == 2) {
-                    float mx = z[0];
-                    for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
-                    float sum = 0.f;
-                    for (int j = 0; j < C; ++j) { z[j] = __expf(z[j] - mx); sum += z[j]; }
-                    const float inv = __fdividef(1.f, sum);
-                    for (int j = 0; j < C; ++j) z[j] *= inv;
-                  } else if (a.act == 3) {
-                    for (int j = 0; j < C; ++j) z[j] = __fdividef(1.f, 1.f + __expf(-z[j]));
+                      for (int j = 0; j < 4; ++j) z[j] = fmaxf(z[j], 0.f);
+                    } else if (a.act == 2) {
+                      float mx = z[0];
+                      for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
+                      float sum = 0.f;
+                      for (int j = 0; j < C; ++j) { z[j] = __expf(z[j] - mx); sum += z[j]; }
+                      const float inv = __fdividef(1.f, sum);
+                      for (int j = 0; j < C; ++j) z[j] *= inv;
+                    } else if (a.act == 3) {
+                      for (int j = 0; j < C; ++j) z[j] = __fdividef(1.f, 1.f + __expf(-z[j]));
+                    }
+                    for (int j = 0; j < C; ++j) o[j] = z[j];
                   }
-                  for (int j = 0; j < C; ++j) o[j] = z[j];
                 }
-              } else if (!HEAD && xv && gv[k]) {
-                const int c = (q4 + 4 * k) & nc_mask;
-                const long long p8 = gpos[k] + (long long)xl * 8;
+              } else {
+                const long long p8 = gp1 + (k == 0 ? row8 : 0) + (long long)xl * 8;
                 uint4 val = raw[k];
                 if (has_res) val = add8(val, rr[k]);
-                if (has_pre) *reinterpret_cast<uint4*>(a.out_pre + (long long)c * a.pre_plane * 8 + p8) = clamp8<false>(val);
-                *reinterpret_cast<uint4*>(a.out + (long long)c * a.out_plane * 8 + p8) = relu ? clamp8<true>(val) : clamp8<false>(val);
+                const uint4 fin = relu ? clamp8<true>(val) : clamp8<false>(val);
+                if (xv && gv[k]) {
+                  if (has_pre) *reinterpret_cast<uint4*>(a.out_pre + pre_c + p8) = clamp8<false>(val);
+                  *reinterpret_cast<uint4*>(a.out + out_c + p8) = fin;
+                }
+                if constexpr (POOL) raw[k] = (xv && gv[k]) ? fin : make_uint4(0u, 0u, 0u, 0u);   // ReLU'd: 0 is neutral
               }
             }
+            if constexpr (POOL) {
+              // fused 2x2 stride-2 SAME max-pool of the ReLU'd output (layers.py:526-534): the two rows are a vertical
+              // pair, lanes (2j, 2j+1) a horizontal one; cells outside the page count as 0, which max() ignores.
+              uint4 mx = max8(raw[0], raw[1]);
+              uint4 ot;
+              ot.x = __shfl_xor_sync(0xffffffffu, mx.x, 1);
+              ot.y = __shfl_xor_sync(0xffffffffu, mx.y, 1);
+              ot.z = __shfl_xor_sync(0xffffffffu, mx.z, 1);
+              ot.w = __shfl_xor_sync(0xffffffffu, mx.w, 1);
+              mx = max8(mx, ot);
+              if (!(lane & 1) && xv && gv[1])   // even column, and the even row of the pair is in the page
+                *reinterpret_cast<uint4*>(a.pool_out + ppos + (long long)(xl >> 1) * 8) = mx;
+            }
             if (has_res) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) rr[k] = rn[k];
+              rr[0] = rn[0];
+              rr[1] = rn[1];
             }
           }
           if (++tr.ty == a.n_ty) { tr.ty = 0; if (++tr.s == a.n_strips) { tr.s = 0; ++tr.n; } }
@@ -739,11 +762,19 @@ void conv_band_pack(const ConvBandPlan& p, const float* w, int cin, int cout, ui
 }
 
 cudaError_t launch_conv_band(cudaStream_t st, const ConvBandPlan& p, PV in, PV out, PV out_pre, PV res, const act_t* wpack,
-                             const float* bias_pad, const Geo& g, int act, int* err_flag, float* out_f32, int f32_c) {
+                             const float* bias_pad, const Geo& g, int act, int* err_flag, float* out_f32, int f32_c,
+                             PV pool, const Geo* pool_geo) {
   if (!p.ok) return cudaErrorInvalidValue;
   if (out_f32 && (p.cop != 8 || f32_c < 1 || f32_c > 4)) return cudaErrorInvalidValue;
   ConvBandArgs a{};
   a.out_f32 = out_f32; a.f32_c = f32_c;
+  if (pool.p) {
+    // the fused pool relies on max(x, 0) = x (ReLU'd values, zero cells outside the page) and on even tile origins
+    if (!pool_geo || out_f32 || act != 1 || p.R < 2 || pool_geo->H != (g.H + 1) / 2 || pool_geo->W != (g.W + 1) / 2)
+      return cudaErrorInvalidValue;
+    a.pool_out = pool.p; a.pool_plane = pool.plane; a.lead_o = pool_geo->lead;
+    a.Wpo = pool_geo->Wp; a.Hpo = pool_geo->Hp;
+  }
   a.in = in.p; a.in_plane = in.plane;
   a.out = out.p; a.out_plane = out.plane;
   a.out_pre = out_pre.p; a.pre_plane = out_pre.plane;
@@ -766,14 +797,18 @@ cudaError_t launch_conv_band(cudaStream_t st, const ConvBandPlan& p, PV in, PV o
   const int ncp = p.cin_chunks == 1 ? 0 : p.cin_chunks / 2;
   Kern k = nullptr;
   int ki = -1;
-  const bool head = out_f32 != nullptr;
-#define ARU_BAND_PICK(KK, NN, HH, II) if (p.ks == KK && ncp == NN && head == HH) { k = k_conv_band<KK, NN, HH>; ki = II; }
-  ARU_BAND_PICK(3, 0, false, 0) ARU_BAND_PICK(3, 1, false, 1) ARU_BAND_PICK(3, 2, false, 2) ARU_BAND_PICK(3, 4, false, 6)
-  ARU_BAND_PICK(4, 0, false, 3) ARU_BAND_PICK(4, 1, false, 4) ARU_BAND_PICK(4, 2, false, 5) ARU_BAND_PICK(4, 4, false, 7)
-  ARU_BAND_PICK(3, 0, true, 8) ARU_BAND_PICK(4, 0, true, 9)
+  const bool head = out_f32 != nullptr, pl = pool.p != nullptr;
+#define ARU_BAND_PICK(KK, NN, HH, PP, II) \
+  if (p.ks == KK && ncp == NN && head == HH && pl == PP) { k = k_conv_band<KK, NN, HH, PP>; ki = II; }
+  ARU_BAND_PICK(3, 0, false, false, 0) ARU_BAND_PICK(3, 1, false, false, 1) ARU_BAND_PICK(3, 2, false, false, 2)
+  ARU_BAND_PICK(3, 4, false, false, 3) ARU_BAND_PICK(4, 0, false, false, 4) ARU_BAND_PICK(4, 1, false, false, 5)
+  ARU_BAND_PICK(4, 2, false, false, 6) ARU_BAND_PICK(4, 4, false, false, 7)
+  ARU_BAND_PICK(3, 0, true, false, 8) ARU_BAND_PICK(4, 0, true, false, 9)
+  ARU_BAND_PICK(3, 0, false, true, 10) ARU_BAND_PICK(3, 1, false, true, 11) ARU_BAND_PICK(3, 2, false, true, 12)
+  ARU_BAND_PICK(4, 0, false, true, 13) ARU_BAND_PICK(4, 1, false, true, 14) ARU_BAND_PICK(4, 2, false, true, 15)
 #undef ARU_BAND_PICK
   if (!k) return cudaErrorInvalidValue;
-  static bool configured[10] = {false, false, false, false, false, false, false, false, false, false};
+  static bool configured[16] = {};
   if (!configured[ki]) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;

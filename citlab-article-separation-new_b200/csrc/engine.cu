@@ -65,6 +65,8 @@ struct Plan {
   std::vector<std::vector<TcPart>> tc;  // per op: K-parts of the tensor-core launch (empty: other kernel)
   std::vector<ConvBandPlan> band;       // per op: row-banded tensor-core launch (ok == false: other kernel)
   std::vector<char> use_band;           // per op: the row-banded kernel won the plan-time timing (or is the only one)
+  std::vector<int> fused_pool;          // per conv op: the MAXPOOL op its row-banded launch also performs (-1: none)
+  std::vector<char> skip;               // per op: performed by another op's launch
   act_t* scratch = nullptr;             // partial sums of split-K launches
   size_t scratch_bytes = 0;
   std::vector<const char*> kernel;   // per op label
@@ -281,9 +283,12 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
         err = launch_conv_small(st, op.ksize, op.out.ch, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), ow.w32,
                                 ow.bias, bi.geo, op.act);
       } else if (p->band[oi].ok && p->use_band[oi]) {
-        label = "conv_band";
+        const int pj = p->fused_pool[oi];
+        label = pj >= 0 ? "conv_band_pool" : "conv_band";
         err = launch_conv_band(st, p->band[oi], make_pv(e, p, op.in), make_pv(e, p, op.out), make_pv(e, p, op.out_pre),
-                               make_pv(e, p, op.res), ow.band_w, ow.bias, bo.geo, op.act, e->err_flag);
+                               make_pv(e, p, op.res), ow.band_w, ow.bias, bo.geo, op.act, e->err_flag, nullptr, 0,
+                               pj >= 0 ? make_pv(e, p, e->ops[pj].out) : PV(),
+                               pj >= 0 ? &p->bufs[e->ops[pj].out.buf].geo : nullptr);
       } else if (!p->tc[oi].empty()) {
         // K-parts chain through the scratch buffer: part 0 adds the op's residual, the last part adds the
         // bias, applies the activation and writes the real outputs
@@ -322,7 +327,9 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
     case ARU_OP_AVGPOOL: {
       const BufPlan& bi = p->bufs[op.in.buf];
       const BufPlan& bo = p->bufs[op.out.buf];
-      if (bi.kind == KIND_F32) {
+      if (p->skip[oi]) {
+        label = "pool_fused";   // written by the producing convolution's launch
+      } else if (bi.kind == KIND_F32) {
         label = "pool_f32";
         err = launch_pool_f32(st, op.kind == ARU_OP_MAXPOOL, f32_ptr(e, p, op.in.buf, parity),
                               f32_ptr(e, p, op.out.buf, parity), p->n, bi.h, bi.w, bo.h, bo.w);
@@ -411,6 +418,8 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   p->tc.resize(no);
   p->band.resize(no);
   p->use_band.assign(no, 0);
+  p->fused_pool.assign(no, -1);
+  p->skip.assign(no, 0);
   p->kernel.assign(no, "?");
   for (int i = 0; i < nb; ++i) {
     p->bufs[i].kind = e->kind[i];
@@ -619,6 +628,26 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
     if ((rc = check_err_flag(e))) { free_plan(p.get()); return rc; }
   }
+  // max-pools whose input is the ReLU'd output of a row-banded convolution are written by that launch
+  {
+    const char* env = getenv("ARU_FUSE_POOL");
+    const bool fuse = !(env && env[0] == '0');
+    for (int j = 0; j < no && fuse; ++j) {
+      const aru_op& po = e->ops[j];
+      if (po.kind != ARU_OP_MAXPOOL || p->bufs[po.in.buf].kind != KIND_PLANAR) continue;
+      for (int i = j - 1; i >= 0; --i) {
+        const aru_op& co = e->ops[i];
+        if (co.out.buf != po.in.buf) continue;
+        if (co.kind == ARU_OP_CONV && co.out.ch_off == po.in.ch_off && co.out.ch == po.in.ch && p->band[i].ok &&
+            p->use_band[i] && p->fused_pool[i] < 0 && p->bufs[co.out.buf].kind == KIND_PLANAR &&
+            conv_band_can_pool(p->band[i], co.act, co.in.ch, co.ksize)) {
+          p->fused_pool[i] = j;
+          p->skip[j] = 1;
+        }
+        break;   // the last writer of the pool's input decides
+      }
+    }
+  }
   // one eager pass (sets function attributes, validates every launch), then capture
   rc = run_all(e, p.get(), 0, e->s_comp);
   if (rc) { free_plan(p.get()); return rc; }
@@ -633,7 +662,8 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   p->launches = no;
   for (int i = 0; i < no; ++i)
     if (e->ops[i].kind == ARU_OP_COPY) p->launches += cdiv(e->ops[i].in.ch, 8) - 1;
-    else if (p->tc[i].size() > 1) p->launches += (int)p->tc[i].size() - 1;
+    else if (p->tc[i].size() > 1 && !(p->band[i].ok && p->use_band[i])) p->launches += (int)p->tc[i].size() - 1;
+  for (int i = 0; i < no; ++i) p->launches -= p->skip[i];
   if (e->use_graph) {
     for (int par = 0; par < 2; ++par) {
       cudaGraph_t g = nullptr;

@@ -114,7 +114,11 @@ void conv_band_pack(const ConvBandPlan& plan, const float* w_tf, int cin, int co
 // out_f32 != null: small-C_out head (C_out <= 4) writing dense float32 NHWC with ReLU / softmax / sigmoid instead of planes
 cudaError_t launch_conv_band(cudaStream_t st, const ConvBandPlan& plan, PV in, PV out, PV out_pre, PV res,
                              const act_t* wpack, const float* bias_pad, const Geo& g, int act, int* err_flag,
-                             float* out_f32 = nullptr, int f32_c = 0);
+                             float* out_f32 = nullptr, int f32_c = 0, PV pool = PV(), const Geo* pool_geo = nullptr);
+// conv_band_can_pool: the launch can also write the 2x2 stride-2 SAME max-pool of its ReLU'd output (pool = its view)
+inline bool conv_band_can_pool(const ConvBandPlan& plan, int act, int cin, int ks) {
+  return plan.ok && act == 1 && plan.R >= 2 && cin <= 32 && (ks == 3 || ks == 4);
+}
 
 // host-side 16-bit conversion matching act_t
 uint16_t host_f_to_act(float v);
