@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -76,6 +77,11 @@ struct Plan {
   float* out_dev[2] = {nullptr, nullptr};
   uint8_t* u8_dev[2] = {nullptr, nullptr};
   uint8_t* mask_dev[2] = {nullptr, nullptr};
+  uint8_t* page_dev[2] = {nullptr, nullptr};   // uint8 gray / BGR pages (aru_separator_pages)
+  int page_dev_channels = 0;
+  uint8_t* hor_dev[2] = {nullptr, nullptr};    // separator post-processing results
+  uint8_t* ver_dev[2] = {nullptr, nullptr};
+  void* post_scratch = nullptr;                // labels, areas, bit planes (used on the compute stream only)
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   bool d2h_pending[2] = {false, false};
@@ -219,12 +225,16 @@ void free_plan(Plan* p) {
     if (p->out_dev[i]) cudaFree(p->out_dev[i]);
     if (p->u8_dev[i]) cudaFree(p->u8_dev[i]);
     if (p->mask_dev[i]) cudaFree(p->mask_dev[i]);
+    if (p->page_dev[i]) cudaFree(p->page_dev[i]);
+    if (p->hor_dev[i]) cudaFree(p->hor_dev[i]);
+    if (p->ver_dev[i]) cudaFree(p->ver_dev[i]);
     if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
     if (p->ev_comp[i]) cudaEventDestroy(p->ev_comp[i]);
     if (p->ev_d2h[i]) cudaEventDestroy(p->ev_d2h[i]);
   }
   if (p->arena) cudaFree(p->arena);
   if (p->scratch) cudaFree(p->scratch);
+  if (p->post_scratch) cudaFree(p->post_scratch);
 }
 
 int set_dims(aru_engine* e, Plan* p, int buf, int h, int w, int op) {
@@ -726,12 +736,160 @@ int ensure_quant(aru_engine* e, Plan* p, bool u8, bool mask) {
   return ARU_OK;
 }
 
+int ensure_pages(aru_engine* e, Plan* p, int channels) {
+  if (p->page_dev[0] && p->page_dev_channels >= channels) return ARU_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (p->page_dev[i]) { CU(e, cudaStreamSynchronize(e->s_h2d)); CU(e, cudaStreamSynchronize(e->s_comp)); cudaFree(p->page_dev[i]); p->page_dev[i] = nullptr; }
+    CU(e, cudaMalloc((void**)&p->page_dev[i], (size_t)p->n * p->h * p->w * channels));
+  }
+  p->page_dev_channels = channels;
+  return ARU_OK;
+}
+
+int ensure_post(aru_engine* e, Plan* p) {
+  for (int i = 0; i < 2; ++i) {
+    if (!p->hor_dev[i]) CU(e, cudaMalloc((void**)&p->hor_dev[i], (size_t)p->n * p->h * p->w));
+    if (!p->ver_dev[i]) CU(e, cudaMalloc((void**)&p->ver_dev[i], (size_t)p->n * p->h * p->w));
+  }
+  if (!p->post_scratch) CU(e, cudaMalloc(&p->post_scratch, separator_post_scratch_bytes(p->n, p->h, p->w)));
+  return ARU_OK;
+}
+
+// int(net_output.size * (1 / net_output.size * 100)) in IEEE doubles, as Python evaluates it
+// (separator_net_post_processor.py:37, region_net_post_processor_base.py:244): 100, sometimes 99
+int cc_min_size(long long page_px) {
+  const double thr = 1.0 / (double)page_px * 100.0;
+  return (int)((double)page_px * thr);
+}
+
+// apply_threshold on the uint8 map (helper.py:75-78): u8 > threshold * 255 (double)  <=>  u8 >= floor(t) + 1
+int mask_cut(double thr) {
+  const double t = thr * 255.0;
+  if (t < 0.0) return 0;
+  if (t >= 255.0) return 256;
+  return (int)std::floor(t) + 1;
+}
+
 int pick_micro_batch(const aru_engine* e, int n, int h, int w) {
   if (e->micro_batch > 0) return std::min(n, e->micro_batch);
   const long long px = (long long)h * w;
   long long mb = (40LL << 20) / std::max<long long>(px, 1);
   mb = std::max<long long>(1, std::min<long long>(mb, 32));
   return (int)std::min<long long>(mb, n);
+}
+
+// sizes of the three structuring elements of SeparatorNetPostProcessor.post_process (sep:71,76,85):
+// int(15 * W / 1000), int(30 * H / 1500), int(10 * W / 1000) - Python float division, then truncation
+void separator_kernel_sizes(int h, int w, int* k_h1, int* k_v, int* k_h2) {
+  *k_h1 = (int)(15.0 * w / 1000.0);
+  *k_v = (int)(30.0 * h / 1500.0);
+  *k_h2 = (int)(10.0 * w / 1000.0);
+}
+
+struct HostIO {
+  const float* in_f32 = nullptr;   // float32 [n,h,w] pages (gray / 255) ...
+  const uint8_t* in_u8 = nullptr;  // ... or uint8 [n,h,w,channels] pages (gray, or BGR as cv2.imread returns them)
+  int channels = 1;
+  float* out = nullptr;            // float32 [n,h,w,c]
+  uint8_t* out_u8 = nullptr;       // uint8 [n,h,w,c]
+  uint8_t* out_mask = nullptr;     // uint8 [n,h,w]
+  uint8_t* out_h = nullptr;        // uint8 [n,h,w] horizontal separators (post_process)
+  uint8_t* out_v = nullptr;        // uint8 [n,h,w] vertical separators
+  float thr = 0.f;                 // float threshold (aru_forward) ...
+  int cut = -1;                    // ... or the integer cut of the double threshold (>= 0)
+};
+
+// Host-buffer forward: micro-batches, double-buffered device staging, copies on their own streams.
+int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
+  CU(e, cudaSetDevice(e->device));
+  const int mb = pick_micro_batch(e, n, h, w);
+  const size_t page_px = (size_t)h * w;
+  const int C = e->n_class;
+  const bool want_post = io.out_h != nullptr;
+  const bool want_mask = io.out_mask != nullptr || want_post;
+  int k1 = 0, kv = 0, k2 = 0;
+  separator_kernel_sizes(h, w, &k1, &kv, &k2);
+  int slot = 0;
+  std::vector<Plan*> used;
+  // Micro-batch schedule.  The host->device copy of the first micro-batch and the device->host copy of the last one
+  // cannot overlap with compute, so those two are half size: [mb/2, mb, ..., mb, (rest), mb/2].
+  std::vector<int> sched;
+  if (n > mb && mb >= 4) {
+    const int edge = mb / 2;
+    sched.push_back(edge);
+    int left = n - 2 * edge;
+    while (left > 0) { sched.push_back(std::min(mb, left)); left -= sched.back(); }
+    sched.push_back(edge);
+  } else {
+    for (int left = n; left > 0; left -= mb) sched.push_back(std::min(mb, left));
+  }
+  int i0 = 0;
+  for (size_t si = 0; si < sched.size(); i0 += sched[si], ++si, ++slot) {
+    const int cnt = sched[si];
+    Plan* p = nullptr;
+    int rc = get_plan(e, cnt, h, w, &p);
+    if (rc) return rc;
+    e->cur = p;
+    if (std::find(used.begin(), used.end(), p) == used.end()) used.push_back(p);
+    rc = ensure_quant(e, p, io.out_u8 != nullptr, want_mask);
+    if (rc) return rc;
+    if (io.in_u8 && (rc = ensure_pages(e, p, io.channels))) return rc;
+    if (want_post && (rc = ensure_post(e, p))) return rc;
+    const int par = slot & 1;
+    // buffers of this parity are free once the device->host copies of their previous use are done
+    if (p->d2h_pending[par]) {
+      CU(e, cudaStreamWaitEvent(e->s_h2d, p->ev_d2h[par], 0));
+      CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_d2h[par], 0));
+    }
+    if (io.in_u8)
+      CU(e, cudaMemcpyAsync(p->page_dev[par], io.in_u8 + (size_t)i0 * page_px * io.channels,
+                            (size_t)cnt * page_px * io.channels, cudaMemcpyHostToDevice, e->s_h2d));
+    else
+      CU(e, cudaMemcpyAsync(p->in_dev[par], io.in_f32 + (size_t)i0 * page_px, (size_t)cnt * page_px * sizeof(float),
+                            cudaMemcpyHostToDevice, e->s_h2d));
+    CU(e, cudaEventRecord(p->ev_h2d[par], e->s_h2d));
+    CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_h2d[par], 0));
+    if (io.in_u8) {
+      cudaError_t err = launch_pages_to_input(e->s_comp, p->page_dev[par], io.channels, (long long)cnt * page_px,
+                                              p->in_dev[par], nullptr);
+      if (err != cudaSuccess) return fail(e, ARU_ECUDA, "pages_to_input launch: %s", cudaGetErrorString(err));
+    }
+    rc = enqueue_forward(e, p, par, e->s_comp);
+    if (rc) return rc;
+    if (io.out_u8 || want_mask) {
+      cudaError_t err = launch_quantize(e->s_comp, p->out_dev[par], io.out_u8 ? p->u8_dev[par] : nullptr,
+                                        want_mask ? p->mask_dev[par] : nullptr, (long long)cnt * page_px, C, io.thr, io.cut);
+      if (err != cudaSuccess) return fail(e, ARU_ECUDA, "quantize launch: %s", cudaGetErrorString(err));
+    }
+    if (want_post) {
+      cudaError_t err = launch_separator_post(e->s_comp, p->mask_dev[par], cnt, h, w, cc_min_size((long long)page_px), k1,
+                                              kv, k2, p->post_scratch, p->hor_dev[par], p->ver_dev[par]);
+      if (err != cudaSuccess) return fail(e, ARU_ECUDA, "separator_post launch: %s", cudaGetErrorString(err));
+    }
+    CU(e, cudaEventRecord(p->ev_comp[par], e->s_comp));
+    CU(e, cudaStreamWaitEvent(e->s_d2h, p->ev_comp[par], 0));
+    if (io.out)
+      CU(e, cudaMemcpyAsync(io.out + (size_t)i0 * page_px * C, p->out_dev[par], (size_t)cnt * page_px * C * sizeof(float),
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+    if (io.out_u8)
+      CU(e, cudaMemcpyAsync(io.out_u8 + (size_t)i0 * page_px * C, p->u8_dev[par], (size_t)cnt * page_px * C,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+    if (io.out_mask)
+      CU(e, cudaMemcpyAsync(io.out_mask + (size_t)i0 * page_px, p->mask_dev[par], (size_t)cnt * page_px,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+    if (want_post) {
+      CU(e, cudaMemcpyAsync(io.out_h + (size_t)i0 * page_px, p->hor_dev[par], (size_t)cnt * page_px,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+      CU(e, cudaMemcpyAsync(io.out_v + (size_t)i0 * page_px, p->ver_dev[par], (size_t)cnt * page_px,
+                            cudaMemcpyDeviceToHost, e->s_d2h));
+    }
+    CU(e, cudaEventRecord(p->ev_d2h[par], e->s_d2h));
+    p->d2h_pending[par] = true;
+  }
+  CU(e, cudaStreamSynchronize(e->s_d2h));
+  CU(e, cudaStreamSynchronize(e->s_comp));
+  for (Plan* p : used) p->d2h_pending[0] = p->d2h_pending[1] = false;
+  return check_err_flag(e);
 }
 
 }  // namespace
@@ -940,69 +1098,118 @@ int aru_plan(aru_engine* e, int n, int h, int w) {
 int aru_forward(aru_engine* e, const float* in, int n, int h, int w, float* out, uint8_t* out_u8, uint8_t* out_mask,
                 float thr) {
   if (!e || !in || n <= 0 || h <= 0 || w <= 0) return e ? fail(e, ARU_EINVAL, "aru_forward: bad argument") : ARU_EINVAL;
+  HostIO io;
+  io.in_f32 = in;
+  io.out = out;
+  io.out_u8 = out_u8;
+  io.out_mask = out_mask;
+  io.thr = thr;
+  return forward_host(e, io, n, h, w);
+}
+
+int aru_separator_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, double thr, float* out,
+                        uint8_t* out_u8, uint8_t* out_mask, uint8_t* horizontal, uint8_t* vertical) {
+  if (!e || !pages || n <= 0 || h <= 0 || w <= 0 || (channels != 1 && channels != 3))
+    return e ? fail(e, ARU_EINVAL, "aru_separator_pages: bad argument") : ARU_EINVAL;
+  if ((horizontal == nullptr) != (vertical == nullptr))
+    return fail(e, ARU_EINVAL, "aru_separator_pages: horizontal and vertical go together");
+  if (horizontal) {
+    int k1, kv, k2;
+    separator_kernel_sizes(h, w, &k1, &kv, &k2);
+    if (k1 < 1 || kv < 1 || k2 < 1)
+      return fail(e, ARU_EINVAL, "aru_separator_pages: page %dx%d too small (structuring element %dx1 / 1x%d / %dx1; "
+                  "OpenCV rejects an empty element in the reference too)", h, w, k1, kv, k2);
+  }
+  HostIO io;
+  io.in_u8 = pages;
+  io.channels = channels;
+  io.out = out;
+  io.out_u8 = out_u8;
+  io.out_mask = out_mask;
+  io.out_h = horizontal;
+  io.out_v = vertical;
+  io.cut = mask_cut(thr);
+  return forward_host(e, io, n, h, w);
+}
+
+int aru_separator_post(aru_engine* e, const uint8_t* mask, int n, int h, int w, uint8_t* horizontal, uint8_t* vertical) {
+  if (!e || !mask || !horizontal || !vertical || n <= 0 || h <= 0 || w <= 0)
+    return e ? fail(e, ARU_EINVAL, "aru_separator_post: bad argument") : ARU_EINVAL;
+  int k1, kv, k2;
+  separator_kernel_sizes(h, w, &k1, &kv, &k2);
+  if (k1 < 1 || kv < 1 || k2 < 1)
+    return fail(e, ARU_EINVAL, "aru_separator_post: page %dx%d too small (structuring element %dx1 / 1x%d / %dx1)", h, w,
+                k1, kv, k2);
   CU(e, cudaSetDevice(e->device));
-  const int mb = pick_micro_batch(e, n, h, w);
   const size_t page_px = (size_t)h * w;
-  const int C = e->n_class;
-  int slot = 0;
-  std::vector<Plan*> used;
-  // Micro-batch schedule.  The host->device copy of the first micro-batch and the device->host copy of the last one
-  // cannot overlap with compute, so those two are half size: [mb/2, mb, ..., mb, (rest), mb/2].
-  std::vector<int> sched;
-  if (n > mb && mb >= 4) {
-    const int edge = mb / 2;
-    sched.push_back(edge);
-    int left = n - 2 * edge;
-    while (left > 0) { sched.push_back(std::min(mb, left)); left -= sched.back(); }
-    sched.push_back(edge);
-  } else {
-    for (int left = n; left > 0; left -= mb) sched.push_back(std::min(mb, left));
+  const int mb = (int)std::max<long long>(1, std::min<long long>(n, (64LL << 20) / (long long)page_px));
+  uint8_t *d_in = nullptr, *d_h = nullptr, *d_v = nullptr;
+  void* scratch = nullptr;
+  int rc = ARU_OK;
+  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_h); cudaFree(d_v); cudaFree(scratch); };
+  if (cudaMalloc((void**)&d_in, mb * page_px) || cudaMalloc((void**)&d_h, mb * page_px) ||
+      cudaMalloc((void**)&d_v, mb * page_px) || cudaMalloc(&scratch, separator_post_scratch_bytes(mb, h, w))) {
+    cleanup();
+    return fail(e, ARU_ENOMEM, "aru_separator_post: device allocation failed");
   }
-  int i0 = 0;
-  for (size_t si = 0; si < sched.size(); i0 += sched[si], ++si, ++slot) {
-    const int cnt = sched[si];
-    Plan* p = nullptr;
-    int rc = get_plan(e, cnt, h, w, &p);
-    if (rc) return rc;
-    e->cur = p;
-    if (std::find(used.begin(), used.end(), p) == used.end()) used.push_back(p);
-    rc = ensure_quant(e, p, out_u8 != nullptr, out_mask != nullptr);
-    if (rc) return rc;
-    const int par = slot & 1;
-    // buffers of this parity are free once the device->host copies of their previous use are done
-    if (p->d2h_pending[par]) {
-      CU(e, cudaStreamWaitEvent(e->s_h2d, p->ev_d2h[par], 0));
-      CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_d2h[par], 0));
-    }
-    CU(e, cudaMemcpyAsync(p->in_dev[par], in + (size_t)i0 * page_px, (size_t)cnt * page_px * sizeof(float),
-                          cudaMemcpyHostToDevice, e->s_h2d));
-    CU(e, cudaEventRecord(p->ev_h2d[par], e->s_h2d));
-    CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_h2d[par], 0));
-    rc = enqueue_forward(e, p, par, e->s_comp);
-    if (rc) return rc;
-    if (out_u8 || out_mask) {
-      cudaError_t err = launch_quantize(e->s_comp, p->out_dev[par], out_u8 ? p->u8_dev[par] : nullptr,
-                                        out_mask ? p->mask_dev[par] : nullptr, (long long)cnt * page_px, C, thr);
-      if (err != cudaSuccess) return fail(e, ARU_ECUDA, "quantize launch: %s", cudaGetErrorString(err));
-    }
-    CU(e, cudaEventRecord(p->ev_comp[par], e->s_comp));
-    CU(e, cudaStreamWaitEvent(e->s_d2h, p->ev_comp[par], 0));
-    if (out)
-      CU(e, cudaMemcpyAsync(out + (size_t)i0 * page_px * C, p->out_dev[par], (size_t)cnt * page_px * C * sizeof(float),
-                            cudaMemcpyDeviceToHost, e->s_d2h));
-    if (out_u8)
-      CU(e, cudaMemcpyAsync(out_u8 + (size_t)i0 * page_px * C, p->u8_dev[par], (size_t)cnt * page_px * C,
-                            cudaMemcpyDeviceToHost, e->s_d2h));
-    if (out_mask)
-      CU(e, cudaMemcpyAsync(out_mask + (size_t)i0 * page_px, p->mask_dev[par], (size_t)cnt * page_px,
-                            cudaMemcpyDeviceToHost, e->s_d2h));
-    CU(e, cudaEventRecord(p->ev_d2h[par], e->s_d2h));
-    p->d2h_pending[par] = true;
+  for (int i0 = 0; i0 < n && rc == ARU_OK; i0 += mb) {
+    const int cnt = std::min(mb, n - i0);
+    cudaError_t err = cudaMemcpyAsync(d_in, mask + (size_t)i0 * page_px, cnt * page_px, cudaMemcpyHostToDevice, e->s_comp);
+    if (err == cudaSuccess)
+      err = launch_separator_post(e->s_comp, d_in, cnt, h, w, cc_min_size((long long)page_px), k1, kv, k2, scratch, d_h, d_v);
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(horizontal + (size_t)i0 * page_px, d_h, cnt * page_px, cudaMemcpyDeviceToHost, e->s_comp);
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(vertical + (size_t)i0 * page_px, d_v, cnt * page_px, cudaMemcpyDeviceToHost, e->s_comp);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+    if (err != cudaSuccess) rc = fail(e, ARU_ECUDA, "aru_separator_post: %s", cudaGetErrorString(err));
   }
-  CU(e, cudaStreamSynchronize(e->s_d2h));
-  CU(e, cudaStreamSynchronize(e->s_comp));
-  for (Plan* p : used) p->d2h_pending[0] = p->d2h_pending[1] = false;
-  return check_err_flag(e);
+  cleanup();
+  return rc;
+}
+
+int aru_open_rect(aru_engine* e, const uint8_t* mask, int n, int h, int w, int kw, int kh, uint8_t* out) {
+  if (!e || !mask || !out || n <= 0 || h <= 0 || w <= 0 || kw < 1 || kh < 1 || (kw > 1 && kh > 1))
+    return e ? fail(e, ARU_EINVAL, "aru_open_rect: bad argument (one of kw, kh must be 1)") : ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  const size_t px = (size_t)n * h * w;
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  void* scratch = nullptr;
+  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(scratch); };
+  if (cudaMalloc((void**)&d_in, px) || cudaMalloc((void**)&d_out, px) ||
+      cudaMalloc(&scratch, separator_post_scratch_bytes(n, h, w))) {
+    cleanup();
+    return fail(e, ARU_ENOMEM, "aru_open_rect: device allocation failed");
+  }
+  cudaError_t err = cudaMemcpyAsync(d_in, mask, px, cudaMemcpyHostToDevice, e->s_comp);
+  if (err == cudaSuccess) err = launch_open_rect(e->s_comp, d_in, n, h, w, kw, kh, scratch, d_out);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(out, d_out, px, cudaMemcpyDeviceToHost, e->s_comp);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+  cleanup();
+  if (err != cudaSuccess) return fail(e, ARU_ECUDA, "aru_open_rect: %s", cudaGetErrorString(err));
+  return ARU_OK;
+}
+
+int aru_pages_to_input(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, float* out) {
+  if (!e || !pages || !out || n <= 0 || h <= 0 || w <= 0 || (channels != 1 && channels != 3))
+    return e ? fail(e, ARU_EINVAL, "aru_pages_to_input: bad argument") : ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  const size_t px = (size_t)n * h * w;
+  uint8_t* d_in = nullptr;
+  float* d_out = nullptr;
+  if (cudaMalloc((void**)&d_in, px * channels) || cudaMalloc((void**)&d_out, px * sizeof(float))) {
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return fail(e, ARU_ENOMEM, "aru_pages_to_input: device allocation failed");
+  }
+  cudaError_t err = cudaMemcpyAsync(d_in, pages, px * channels, cudaMemcpyHostToDevice, e->s_comp);
+  if (err == cudaSuccess) err = launch_pages_to_input(e->s_comp, d_in, channels, (long long)px, d_out, nullptr);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(out, d_out, px * sizeof(float), cudaMemcpyDeviceToHost, e->s_comp);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (err != cudaSuccess) return fail(e, ARU_ECUDA, "aru_pages_to_input: %s", cudaGetErrorString(err));
+  return ARU_OK;
 }
 
 int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, float* out, uint8_t* out_u8,
@@ -1028,7 +1235,7 @@ int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, floa
                             cudaMemcpyDeviceToDevice, st));
     if (out_u8 || out_mask) {
       cudaError_t err = launch_quantize(st, p->out_dev[0], out_u8 ? out_u8 + (size_t)i0 * page_px * C : nullptr,
-                                        out_mask ? out_mask + (size_t)i0 * page_px : nullptr, (long long)cnt * page_px, C, thr);
+                                        out_mask ? out_mask + (size_t)i0 * page_px : nullptr, (long long)cnt * page_px, C, thr, -1);
       if (err != cudaSuccess) return fail(e, ARU_ECUDA, "quantize launch: %s", cudaGetErrorString(err));
     }
   }

@@ -46,8 +46,22 @@ cudaError_t launch_upsum(cudaStream_t st, PV in, const Geo& gi, PV out, const Ge
 cudaError_t launch_upsum_f32(cudaStream_t st, const float* in, int Hi, int Wi, float* out, int N, int H, int W, int up,
                              int oy, int ox);
 cudaError_t launch_copy(cudaStream_t st, const void* in, void* out, long long bytes);
+// mask = 255 where u8[...,0] > thr*255 (float compare), or where u8[...,0] >= cut when cut >= 0
 cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uint8_t* mask, long long npix, int C,
-                            float thr);
+                            float thr, int cut = -1);
+
+// ---- integer pre / post-processing around the net (post.cu) --------------------------------------
+// uint8 gray (channels 1) or BGR (channels 3) pages -> float32 net input gray/255 (+ optional uint8 gray copy)
+cudaError_t launch_pages_to_input(cudaStream_t st, const uint8_t* pages, int channels, long long npix, float* out,
+                                  uint8_t* gray_out);
+// SeparatorNetPostProcessor.post_process on n thresholded masks of h x w: component size filter, three rectangular
+// openings and the saturating subtract; scratch >= separator_post_scratch_bytes(n, h, w)
+size_t separator_post_scratch_bytes(int n, int h, int w);
+int separator_post_launches();
+cudaError_t launch_separator_post(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int min_size, int k_h1,
+                                  int k_v, int k_h2, void* scratch, uint8_t* out_h, uint8_t* out_v);
+cudaError_t launch_open_rect(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int kw, int kh, void* scratch,
+                             uint8_t* out);
 // debug read-back: chunk-planar view -> dense float32 NHWC [N][H][W][C]
 cudaError_t launch_unpack_nhwc(cudaStream_t st, PV in, const Geo& g, float* out);
 

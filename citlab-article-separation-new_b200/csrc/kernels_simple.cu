@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(256) k_copy16(const uint4* __restrict__ in, ui
 // consumers' integer forms of the probability map: u8 = trunc(p*255) (separator_net_post_processor.py:147,
 // heading_net_post_processor.py:287), mask = 255 * (u8[...,0] > thr*255) (helper.py:75-78).
 __global__ void __launch_bounds__(256) k_quantize(const float* __restrict__ prob, uint8_t* __restrict__ u8,
-                                                  uint8_t* __restrict__ mask, long long npix, int C, float thr255) {
+                                                  uint8_t* __restrict__ mask, long long npix, int C, float thr255,
+                                                  int cut) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   uint8_t first = 0;
@@ -452,7 +453,8 @@ __global__ void __launch_bounds__(256) k_quantize(const float* __restrict__ prob
     if (c == 0) first = q;
     if (u8) u8[p * C + c] = q;
   }
-  if (mask) mask[p] = ((float)first > thr255) ? 255 : 0;
+  // helper.py:75-78: u8 > threshold*255; cut >= 0 carries the comparison as an integer (threshold given as a double)
+  if (mask) mask[p] = (cut >= 0 ? (int)first >= cut : (float)first > thr255) ? 255 : 0;
 }
 
 __global__ void __launch_bounds__(256) k_unpack_nhwc(const act_t* __restrict__ in, long long in_plane, int C, Geo g,
@@ -598,8 +600,8 @@ cudaError_t launch_copy(cudaStream_t st, const void* in, void* out, long long by
 }
 
 cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uint8_t* mask, long long np, int C,
-                            float thr) {
-  k_quantize<<<blocks_for(np, 256), 256, 0, st>>>(prob, u8, mask, np, C, thr * 255.f);
+                            float thr, int cut) {
+  k_quantize<<<blocks_for(np, 256), 256, 0, st>>>(prob, u8, mask, np, C, thr * 255.f, cut);
   return cudaGetLastError();
 }
 

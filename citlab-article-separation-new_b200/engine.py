@@ -28,6 +28,7 @@ EXPORTS = [
     "aru_abi_version", "aru_device_count", "aru_create", "aru_destroy", "aru_set_option", "aru_num_classes",
     "aru_plan", "aru_forward", "aru_forward_device", "aru_sync", "aru_launches_per_forward", "aru_read_buffer",
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
+    "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input",
 ]
 
 _lib = None
@@ -64,6 +65,10 @@ def load_library() -> ctypes.CDLL:
         lib.aru_plan.argtypes = [vp, i32, i32, i32]
         lib.aru_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, ctypes.c_float]
         lib.aru_forward_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, ctypes.c_float, vp]
+        lib.aru_separator_pages.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.c_double, vp, vp, vp, vp, vp]
+        lib.aru_separator_post.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+        lib.aru_open_rect.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+        lib.aru_pages_to_input.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         lib.aru_sync.argtypes = [vp]
         lib.aru_launches_per_forward.argtypes = [vp]
         lib.aru_read_buffer.argtypes = [vp, i32, i32, fp, sz]
@@ -215,6 +220,88 @@ class Engine:
 
     def sync(self):
         self._check(self.lib.aru_sync(self.handle))
+
+    # -- integer pre / post-processing on the device ------------------------
+    @staticmethod
+    def _as_pages(pages: np.ndarray):
+        x = np.asarray(pages)
+        if x.dtype != np.uint8:
+            raise ValueError(f"pages must be uint8 (as cv2.imread returns them), got {x.dtype}")
+        if x.ndim == 2:
+            x = x[None]
+        if x.ndim == 3 and x.shape[-1] == 3 and x.shape[0] != 3:   # one [H,W,3] BGR page
+            x = x[None]
+        if x.ndim == 3:
+            n, h, w = x.shape
+            ch = 1
+        elif x.ndim == 4 and x.shape[-1] in (1, 3):
+            n, h, w, ch = x.shape
+        else:
+            raise ValueError(f"expected uint8 [H,W], [N,H,W], [H,W,3] or [N,H,W,{{1,3}}], got shape {x.shape}")
+        return x, n, h, w, ch
+
+    def separator_pages(self, pages: np.ndarray, threshold: float = 0.05, want_prob: bool = False,
+                        want_u8: bool = False, want_mask: bool = False, want_separators: bool = True) -> dict:
+        """One iteration of ``SeparatorNetPostProcessor.run`` up to the polygon step for a batch of uint8 pages
+        (gray ``[N,H,W]`` or BGR ``[N,H,W,3]``): colour step, net, ``uint8(p*255)``, threshold, ``post_process``
+        (separator_net_post_processor.py:141-151).  Returns a dict with the requested arrays (pinned host memory):
+        ``prob`` float32 [N,H,W,C], ``u8`` uint8 [N,H,W,C], ``mask`` uint8 [N,H,W], ``horizontal`` / ``vertical``
+        uint8 [N,H,W] in {0,255}."""
+        x, n, h, w, ch = self._as_pages(pages)
+        if not x.flags.c_contiguous:
+            xin = pinned_empty(x.shape, np.uint8)
+            np.copyto(xin, x)
+            x = xin
+        c = self.n_class
+        res = {}
+        if want_prob:
+            res["prob"] = pinned_empty((n, h, w, c), np.float32)
+        if want_u8:
+            res["u8"] = pinned_empty((n, h, w, c), np.uint8)
+        if want_mask:
+            res["mask"] = pinned_empty((n, h, w), np.uint8)
+        if want_separators:
+            res["horizontal"] = pinned_empty((n, h, w), np.uint8)
+            res["vertical"] = pinned_empty((n, h, w), np.uint8)
+        ptr = lambda k: ctypes.c_void_p(res[k].ctypes.data) if k in res else None  # noqa: E731
+        self._check(self.lib.aru_separator_pages(self.handle, ctypes.c_void_p(x.ctypes.data), ch, n, h, w,
+                                                 ctypes.c_double(threshold), ptr("prob"), ptr("u8"), ptr("mask"),
+                                                 ptr("horizontal"), ptr("vertical")))
+        return res
+
+    def separator_post(self, mask: np.ndarray):
+        """``SeparatorNetPostProcessor.post_process`` (sep:25-99) on thresholded masks uint8 [N,H,W] (or [H,W]):
+        returns (horizontal, vertical) uint8 {0,255} arrays of the same shape."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        single = m.ndim == 2
+        if single:
+            m = m[None]
+        n, h, w = m.shape
+        hor, ver = np.empty_like(m), np.empty_like(m)
+        self._check(self.lib.aru_separator_post(self.handle, ctypes.c_void_p(m.ctypes.data), n, h, w,
+                                                ctypes.c_void_p(hor.ctypes.data), ctypes.c_void_p(ver.ctypes.data)))
+        return (hor[0], ver[0]) if single else (hor, ver)
+
+    def open_rect(self, mask: np.ndarray, kw: int, kh: int) -> np.ndarray:
+        """``cv2.morphologyEx(mask, MORPH_OPEN, RECT(kw, kh))`` for binary masks and kw == 1 or kh == 1."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        single = m.ndim == 2
+        if single:
+            m = m[None]
+        n, h, w = m.shape
+        out = np.empty_like(m)
+        self._check(self.lib.aru_open_rect(self.handle, ctypes.c_void_p(m.ctypes.data), n, h, w, int(kw), int(kh),
+                                           ctypes.c_void_p(out.ctypes.data)))
+        return out[0] if single else out
+
+    def pages_to_input(self, pages: np.ndarray) -> np.ndarray:
+        """``cv2.cvtColor(image, COLOR_BGR2GRAY) / 255.0`` (helper.py:31) as the float32 [N,H,W] the net receives."""
+        x, n, h, w, ch = self._as_pages(pages)
+        x = np.ascontiguousarray(x)
+        out = np.empty((n, h, w), np.float32)
+        self._check(self.lib.aru_pages_to_input(self.handle, ctypes.c_void_p(x.ctypes.data), ch, n, h, w,
+                                                ctypes.c_void_p(out.ctypes.data)))
+        return out
 
     # -- introspection -----------------------------------------------------------------------------
     def read_buffer(self, buf: int, page: int = 0) -> np.ndarray:

@@ -85,3 +85,38 @@ def synth_page(h: int, w: int, seed: int = 0) -> np.ndarray:
 def page_to_net_input(page_u8: np.ndarray) -> np.ndarray:
     """What the reference feeds the net: gray / 255.0 as float64 (net_post_processing_helper.py:31)."""
     return page_u8 / 255.0
+
+
+def synth_separator_mask(h: int, w: int, seed: int = 0, noise: float = 0.02) -> np.ndarray:
+    """uint8 [h, w] in {0,255}: what a thresholded separator map looks like - long 1-6 px wide vertical and horizontal
+    rules (some broken, some crossing, some touching the borders), diagonal strokes, text-sized blobs around the
+    100-pixel component-size limit and salt noise.  Exercises every branch of the reference's post_process
+    (separator_net_post_processor.py:25-99): components below / above the size limit, runs shorter / longer than the
+    structuring elements, horizontal-vertical crossings removed by the subtract, border-touching runs."""
+    rng = np.random.default_rng(seed)
+    m = rng.random((h, w)) < noise
+    for _ in range(int(rng.integers(3, 9))):                       # vertical rules
+        x = int(rng.integers(0, w))
+        y0, y1 = sorted(int(v) for v in rng.integers(-h // 8, h + h // 8, size=2))
+        t = int(rng.integers(1, 7))
+        m[max(y0, 0):max(y1, 0), x:x + t] = True
+        if rng.random() < 0.4 and y1 - y0 > 8:                     # a gap
+            g = int(rng.integers(max(y0, 0), max(y1, 1)))
+            m[g:g + int(rng.integers(1, 6)), x:x + t] = False
+    for _ in range(int(rng.integers(3, 9))):                       # horizontal rules
+        y = int(rng.integers(0, h))
+        x0, x1 = sorted(int(v) for v in rng.integers(-w // 8, w + w // 8, size=2))
+        t = int(rng.integers(1, 7))
+        m[y:y + t, max(x0, 0):max(x1, 0)] = True
+    for _ in range(int(rng.integers(1, 5))):                       # diagonal strokes (8-connectivity only)
+        y, x = int(rng.integers(0, h)), int(rng.integers(0, w))
+        dx = 1 if rng.random() < 0.5 else -1
+        for i in range(int(rng.integers(10, max(11, min(h, w))))):
+            yy, xx = y + i, x + dx * i
+            if 0 <= yy < h and 0 <= xx < w:
+                m[yy, xx] = True
+    for _ in range(int(rng.integers(5, 30))):                      # blobs around the size limit
+        bh, bw = int(rng.integers(2, 16)), int(rng.integers(2, 40))
+        y, x = int(rng.integers(0, max(1, h - bh))), int(rng.integers(0, max(1, w - bw)))
+        m[y:y + bh, x:x + bw] |= rng.random((min(bh, h - y), min(bw, w - x))) < 0.8
+    return np.where(m, 255, 0).astype(np.uint8)

@@ -130,6 +130,37 @@ int aru_forward(aru_engine* e, const float* in, int n, int h, int w, float* out,
 int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, float* out, uint8_t* out_u8,
                        uint8_t* out_mask, float thr, void* stream);
 
+/*
+ * The integer steps either side of the net, on the device, so that only uint8
+ * pages go up and only the two separator masks come down:
+ *
+ * aru_separator_pages = one iteration of SeparatorNetPostProcessor.run up to the polygon step
+ *   (separator_net_post_processor.py:141-151):
+ *     cv2.cvtColor(BGR2GRAY) / 255.0          (net_post_processing_helper.py:31; channels == 3, else gray pages)
+ *     get_net_output                          (helper.py:56-72)
+ *     np.array(net_output * 255, uint8)       (sep:147)
+ *     apply_threshold(net_output, threshold)  (sep:149, helper.py:75-78; `thr` is the Python double)
+ *     post_process                            (sep:25-99: component size filter base:230-251, cv2 MORPH_OPEN with
+ *                                              (int(15W/1000) x 1) and (1 x int(30H/1500)), cv2.subtract, MORPH_OPEN
+ *                                              (int(10W/1000) x 1))
+ *   pages      uint8 [n,h,w,channels] host memory (channels 1 = gray, 3 = B,G,R as cv2.imread returns them)
+ *   out        float32 [n,h,w,c] or NULL;  out_u8  uint8 [n,h,w,c] or NULL;  out_mask  uint8 [n,h,w] or NULL
+ *   horizontal / vertical   uint8 [n,h,w] in {0,255}, both or neither (NULL): post_process()["horizontal"/"vertical"]
+ * Fails with ARU_EINVAL when a structuring element would be empty (W < 100 or H < 50): OpenCV raises there too.
+ */
+int aru_separator_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, double thr, float* out,
+                        uint8_t* out_u8, uint8_t* out_mask, uint8_t* horizontal, uint8_t* vertical);
+
+/* post_process alone on n thresholded masks (uint8 [n,h,w], non-zero = foreground), host memory in and out. */
+int aru_separator_post(aru_engine* e, const uint8_t* mask, int n, int h, int w, uint8_t* horizontal, uint8_t* vertical);
+
+/* cv2.morphologyEx(mask, MORPH_OPEN, getStructuringElement(MORPH_RECT, (kw, kh))) for kw == 1 or kh == 1 on binary
+ * masks (non-zero = 255), host memory in and out; exposed for the parity tests of the morphology kernels. */
+int aru_open_rect(aru_engine* e, const uint8_t* mask, int n, int h, int w, int kw, int kh, uint8_t* out);
+
+/* The colour step alone: uint8 pages [n,h,w,channels] -> float32 [n,h,w] = gray / 255.0 (helper.py:31). */
+int aru_pages_to_input(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, float* out);
+
 /* Block until everything enqueued on the engine's stream has finished. */
 int aru_sync(aru_engine* e);
 

@@ -1,0 +1,70 @@
+"""Generates tests/golden/post_*.npz - golden vectors of the integer steps around the net, produced by the REFERENCE
+ITSELF: ``/root/reference`` is imported (tests/golden/_reference_import.py stubs its unrelated missing imports) and
+
+  * ``SeparatorNetPostProcessor.post_process`` (separator_net_post_processor.py:25-99),
+  * ``RegionNetPostProcessor.apply_cc_analysis`` (region_net_post_processor_base.py:230-251),
+  * ``apply_threshold`` (net_post_processing_helper.py:75-78) and the colour step ``cv2.cvtColor(BGR2GRAY) / 255.0``
+    (helper.py:31)
+
+run on seeded inputs.  Before a fixture is written the numpy restatement in oracle/separator_post_oracle.py must
+reproduce the reference's output bit for bit - that is what pins the oracle for this part of the path.
+Masks are stored bit-packed (np.packbits).  Run from the repo root:  python tests/golden/make_post_golden.py
+"""
+import os
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+from _reference_import import reference_separator_post_processor  # noqa: E402
+from aru_b200.synth import synth_separator_mask  # noqa: E402
+from oracle import separator_post_oracle as O  # noqa: E402
+
+CASES = [  # (name, H, W, seed, noise)
+    ("a", 150, 220, 1, 0.02),
+    ("odd", 101, 177, 2, 0.05),
+    ("wide", 64, 333, 3, 0.01),      # W not a multiple of 4 / 32, even structuring elements
+    ("tall", 400, 100, 4, 0.03),     # smallest legal width (elements 1x1)
+    ("dense", 128, 256, 5, 0.35),    # one huge noisy component
+    ("cfg1", 1024, 768, 6, 0.01),    # BASELINE config 1 size: min_size 99, elements 11x1 / 1x20 / 7x1
+]
+
+if __name__ == "__main__":
+    pp = reference_separator_post_processor()
+    # reference helper functions (the module imports tensorflow at the top, stubbed)
+    from article_separation.image_segmentation.net_post_processing.net_post_processing_helper import \
+        apply_threshold as ref_apply_threshold
+    for name, h, w, seed, noise in CASES:
+        mask = synth_separator_mask(h, w, seed, noise)
+        ref = pp.post_process(mask[:, :, None])
+        ref_cc = pp.apply_cc_analysis(mask, 1 / mask.size * 100)
+        hor, ver = O.separator_post_process(mask)
+        assert np.array_equal(O.cc_size_filter(mask, O.cc_min_size(mask.size)), ref_cc), name
+        assert np.array_equal(hor, ref["horizontal"]) and np.array_equal(ver, ref["vertical"]), name
+        np.savez_compressed(os.path.join(HERE, f"post_{name}_{h}x{w}.npz"), shape=np.array([h, w]),
+                            mask=np.packbits(mask > 0), cc=np.packbits(ref_cc > 0),
+                            horizontal=np.packbits(ref["horizontal"] > 0), vertical=np.packbits(ref["vertical"] > 0),
+                            min_size=int(mask.size * (1 / mask.size * 100)))
+        print(f"post_{name}_{h}x{w}: fg {int((mask > 0).sum())} cc {int((ref_cc > 0).sum())} "
+              f"hor {int((ref['horizontal'] > 0).sum())} ver {int((ref['vertical'] > 0).sum())}")
+
+    # colour step + threshold
+    rng = np.random.default_rng(7)
+    bgr = rng.integers(0, 256, size=(96, 130, 3), dtype=np.uint8)
+    gray = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    grey_f = gray / 255.0                                   # helper.py:31
+    assert np.array_equal(O.bgr2gray_u8(bgr), gray)
+    assert np.array_equal(O.u8_to_net_input(gray), grey_f.astype(np.float32))
+    u8 = rng.integers(0, 256, size=(64, 64), dtype=np.uint8)
+    thr_cases = {}
+    for thr in (0.05, 0.2, 0.4, 0.5, 1 / 255, 0.0):
+        t = ref_apply_threshold(u8, thr)
+        assert np.array_equal(O.apply_threshold(u8, thr), t)
+        thr_cases[f"thr_{thr!r}"] = np.packbits(t > 0)
+    np.savez_compressed(os.path.join(HERE, "post_colour_threshold.npz"), bgr=bgr, gray=gray,
+                        net_input=grey_f.astype(np.float32), u8=u8, **thr_cases)
+    print("post_colour_threshold: ok")

@@ -1,0 +1,104 @@
+"""CPU tests of oracle/separator_post_oracle.py against the golden vectors the REFERENCE ITSELF produced
+(tests/golden/make_post_golden.py ran the reference's SeparatorNetPostProcessor.post_process / apply_cc_analysis /
+apply_threshold and cv2.cvtColor in the build container) and against OpenCV where it is importable."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import separator_post_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+POST_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "post_*x*.npz")))
+
+
+def load_post_fixture(path):
+    z = np.load(path)
+    h, w = (int(v) for v in z["shape"])
+    unpack = lambda k: np.unpackbits(z[k])[:h * w].reshape(h, w) * np.uint8(255)  # noqa: E731
+    return {"h": h, "w": w, "mask": unpack("mask"), "cc": unpack("cc"), "horizontal": unpack("horizontal"),
+            "vertical": unpack("vertical"), "min_size": int(z["min_size"])}
+
+
+def test_fixtures_present():
+    assert len(POST_FIXTURES) >= 6
+
+
+@pytest.mark.parametrize("path", POST_FIXTURES, ids=[os.path.basename(p)[:-4] for p in POST_FIXTURES])
+def test_oracle_reproduces_reference_post_process(path):
+    f = load_post_fixture(path)
+    assert O.cc_min_size(f["h"] * f["w"]) == f["min_size"]
+    assert np.array_equal(O.cc_size_filter(f["mask"], f["min_size"]), f["cc"])
+    hor, ver = O.separator_post_process(f["mask"])
+    assert np.array_equal(hor, f["horizontal"])
+    assert np.array_equal(ver, f["vertical"])
+    hor3, ver3 = O.separator_post_process(np.stack([f["mask"], 255 - f["mask"]], axis=-1))   # HWC: channel 0 only
+    assert np.array_equal(hor3, hor) and np.array_equal(ver3, ver)
+
+
+def test_min_size_quirk():
+    # int(size * (1 / size * 100)) is 99 for some sizes, e.g. BASELINE config 1
+    assert O.cc_min_size(1024 * 768) == 99
+    assert O.cc_min_size(1856 * 1344) == 100
+    assert O.cc_min_size(1500 * 1125) == 100
+
+
+def test_kernel_sizes():
+    assert O.separator_kernel_sizes(1024, 768) == (11, 20, 7)
+    assert O.separator_kernel_sizes(1500, 1125) == (16, 30, 11)
+    assert O.separator_kernel_sizes(1856, 1344) == (20, 37, 13)
+    with pytest.raises(ValueError):
+        O.separator_post_process(np.zeros((49, 200), np.uint8))      # 1 x 0 element: OpenCV raises in the reference
+
+
+def test_colour_step_and_threshold_fixture():
+    z = np.load(os.path.join(GOLDEN, "post_colour_threshold.npz"))
+    assert np.array_equal(O.bgr2gray_u8(z["bgr"]), z["gray"])
+    assert np.array_equal(O.u8_to_net_input(z["gray"]), z["net_input"])
+    u8 = z["u8"]
+    for key in z.files:
+        if key.startswith("thr_"):
+            thr = float(key[4:])
+            want = np.unpackbits(z[key])[:u8.size].reshape(u8.shape) * np.uint8(255)
+            assert np.array_equal(O.apply_threshold(u8, thr), want), key
+
+
+def test_u8_to_float_is_a_plain_float32_division():
+    # float32(u8 / 255.0 computed in float64) == float32(u8) / float32(255) for every uint8: the device kernel divides in fp32
+    u = np.arange(256, dtype=np.uint8)
+    assert np.array_equal((u / 255.0).astype(np.float32), u.astype(np.float32) / np.float32(255))
+
+
+def test_quantize_truncates():
+    assert O.quantize_u8(np.array([1.0], np.float32))[0] == 255
+    assert O.quantize_u8(np.array([0.9999], np.float32))[0] == 254
+
+
+def test_morphology_against_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for _ in range(60):
+        h, w = int(rng.integers(1, 50)), int(rng.integers(1, 70))
+        img = ((rng.random((h, w)) < rng.uniform(0.4, 0.95)) * 255).astype(np.uint8)
+        k = int(rng.integers(1, 40))
+        kw, kh = (k, 1) if rng.random() < 0.5 else (1, k)
+        el = cv2.getStructuringElement(cv2.MORPH_RECT, (kw, kh))
+        assert np.array_equal(cv2.erode(img, el), O.erode_rect(img, kw, kh))
+        assert np.array_equal(cv2.dilate(img, el), O.dilate_rect(img, kw, kh))
+        assert np.array_equal(cv2.morphologyEx(img, cv2.MORPH_OPEN, el), O.open_rect(img, kw, kh))
+
+
+def test_cc_filter_against_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        h, w = int(rng.integers(5, 90)), int(rng.integers(5, 120))
+        img = ((rng.random((h, w)) < rng.uniform(0.2, 0.6)) * 255).astype(np.uint8)
+        min_size = int(rng.integers(1, 60))
+        n, lab, stats, _ = cv2.connectedComponentsWithStats(img, connectivity=8)
+        want = np.zeros_like(img)
+        for i in range(1, n):
+            if stats[i, -1] >= min_size:
+                want[lab == i] = 255
+        assert np.array_equal(O.cc_size_filter(img, min_size), want)
