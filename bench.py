@@ -297,6 +297,21 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
+
+    # ---- end to end one level up: uint8 pages in, the two separator masks out (SURVEY.md 8 f1+f2) ----
+    # = SeparatorNetPostProcessor.run up to the polygon step; only 1 B/px goes up and 2 B/px come down
+    p_host = pinned_empty((n, H, W), np.uint8)
+    p_host[...] = np.rint(pages * 255.0).astype(np.uint8)
+    for _ in range(max(1, min(args.warmup, 2))):
+        r_pages = eng.separator_pages(p_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r_pages = eng.separator_pages(p_host)
+        checksum += float(r_pages["vertical"][0, 0, 0])
+    torch.cuda.synchronize()
+    pages_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-class roofline (rank 0) ----
@@ -321,7 +336,15 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (per-layer tensors are 0.2-2.6 GB per micro-batch); no flush needed",
                        "sharding": "page-wise, one process per GPU, no collective"},
             "e2e": {"value": total_pages / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
-                    "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": e2e_s / args.steps * 1e3},
+                    "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": e2e_s / args.steps * 1e3,
+                    "call": "Engine.forward == get_net_output for a batch: float32 pages in, float32 probability maps out",
+                    "separator_pages": {
+                        "value": total_pages / pages_s, "unit": UNIT, "ms_per_step": pages_s / args.steps * 1e3,
+                        "h2d_bytes_per_step": int(p_host.nbytes),
+                        "d2h_bytes_per_step": int(r_pages["horizontal"].nbytes + r_pages["vertical"].nbytes),
+                        "call": "Engine.separator_pages == SeparatorNetPostProcessor.run up to the polygon step: uint8 "
+                                "pages in; colour step, net, uint8, threshold, component filter and openings on the "
+                                "device; horizontal + vertical uint8 masks out"}},
             "gpu_launches": int(launches * n_mb * args.steps),
             "achieved_tflops": round(value / world * gflop_page / 1e3, 2),
             "roofline": dict(dom, peaks=peaks_src,
