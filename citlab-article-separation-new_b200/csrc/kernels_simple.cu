@@ -457,6 +457,29 @@ __global__ void __launch_bounds__(256) k_quantize(const float* __restrict__ prob
   if (mask) mask[p] = (cut >= 0 ? (int)first >= cut : (float)first > thr255) ? 255 : 0;
 }
 
+// two-class maps, 4 pixels per thread: two 128-bit loads, one 64-bit and one 32-bit store
+__global__ void __launch_bounds__(256) k_quantize_c2x4(const float4* __restrict__ prob, uint2* __restrict__ u8,
+                                                       uint32_t* __restrict__ mask, long long nquad, float thr255, int cut) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nquad) return;
+  const float4 a = prob[2 * q], b = prob[2 * q + 1];
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  unsigned qv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qv[j] = (unsigned)(uint8_t)(int)(v[j] * 255.f);
+  if (u8) u8[q] = make_uint2(qv[0] | (qv[1] << 8) | (qv[2] << 16) | (qv[3] << 24),
+                             qv[4] | (qv[5] << 8) | (qv[6] << 16) | (qv[7] << 24));
+  if (mask) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned first = qv[2 * j];
+      if (cut >= 0 ? (int)first >= cut : (float)first > thr255) m |= 0xffu << (8 * j);
+    }
+    mask[q] = m;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_unpack_nhwc(const act_t* __restrict__ in, long long in_plane, int C, Geo g,
                                                      float* __restrict__ out) {
   const long long total = (long long)g.N * g.H * g.W;
@@ -601,7 +624,19 @@ cudaError_t launch_copy(cudaStream_t st, const void* in, void* out, long long by
 
 cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uint8_t* mask, long long np, int C,
                             float thr, int cut) {
-  k_quantize<<<blocks_for(np, 256), 256, 0, st>>>(prob, u8, mask, np, C, thr * 255.f, cut);
+  long long done = 0;
+  const bool aligned = (reinterpret_cast<uintptr_t>(prob) & 15) == 0 && (reinterpret_cast<uintptr_t>(u8) & 7) == 0 &&
+                       (reinterpret_cast<uintptr_t>(mask) & 3) == 0;
+  if (C == 2 && aligned && np >= 4) {
+    const long long nquad = np / 4;
+    k_quantize_c2x4<<<blocks_for(nquad, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(prob),
+                                                            reinterpret_cast<uint2*>(u8), reinterpret_cast<uint32_t*>(mask),
+                                                            nquad, thr * 255.f, cut);
+    done = nquad * 4;
+  }
+  if (done < np)
+    k_quantize<<<blocks_for(np - done, 256), 256, 0, st>>>(prob + done * C, u8 ? u8 + done * C : nullptr,
+                                                           mask ? mask + done : nullptr, np - done, C, thr * 255.f, cut);
   return cudaGetLastError();
 }
 

@@ -4,7 +4,7 @@
 //         cv2.cvtColor(image, COLOR_BGR2GRAY) / 255.0   ->  k_pages_to_input (uint8 gray or BGR in, float32 net input out)
 //   f2  SeparatorNetPostProcessor.post_process (separator_net_post_processor.py:25-99):
 //         apply_cc_analysis (region_net_post_processor_base.py:230-251): 8-connected components, keep area >= min_size
-//           -> k_cc_init / k_cc_merge / k_cc_count / k_cc_filter_pack  (union-find on pixel indices, atomicMin hooks)
+//           -> k_bits_pack, k_cc_init / k_cc_merge / k_cc_count / k_cc_filter  (union-find over in-word runs, atomicMin hooks)
 //         cv2.morphologyEx(MORPH_OPEN, RECT (kw,1)) / (1,kh), cv2.subtract, MORPH_OPEN (kw2,1)
 //           -> k_bits_h / k_bits_v / k_bits_andnot on a 1-bit-per-pixel image (32 pixels per word), k_bits_unpack
 //
@@ -38,39 +38,134 @@ __global__ void __launch_bounds__(256) k_pages_to_input(const uint8_t* __restric
   if (gray_out) gray_out[i] = (uint8_t)g;
 }
 
+// 4 pixels per thread: one 32-bit (gray) or three 32-bit (BGR) loads, one 128-bit store
+template <int CH>
+__global__ void __launch_bounds__(256) k_pages_to_input4(const uint32_t* __restrict__ pages, long long nquad,
+                                                         float4* __restrict__ out, uint32_t* __restrict__ gray_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nquad) return;
+  unsigned g[4];
+  if (CH == 1) {
+    const uint32_t v = pages[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] = (v >> (8 * j)) & 255u;
+  } else {
+    const uint32_t a = pages[i * 3], b = pages[i * 3 + 1], c = pages[i * 3 + 2];
+    const unsigned by[12] = {a & 255u, (a >> 8) & 255u, (a >> 16) & 255u, a >> 24, b & 255u, (b >> 8) & 255u,
+                             (b >> 16) & 255u, b >> 24, c & 255u, (c >> 8) & 255u, (c >> 16) & 255u, c >> 24};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      g[j] = (by[3 * j] * 3735u + by[3 * j + 1] * 19235u + by[3 * j + 2] * 9798u + (1u << 14)) >> 15;
+  }
+  out[i] = make_float4(__fdiv_rn((float)g[0], 255.f), __fdiv_rn((float)g[1], 255.f), __fdiv_rn((float)g[2], 255.f),
+                       __fdiv_rn((float)g[3], 255.f));
+  if (gray_out) gray_out[i] = g[0] | (g[1] << 8) | (g[2] << 16) | (g[3] << 24);
+}
+
 cudaError_t launch_pages_to_input(cudaStream_t st, const uint8_t* pages, int channels, long long npix, float* out,
                                   uint8_t* gray_out) {
   if (channels != 1 && channels != 3) return cudaErrorInvalidValue;
-  const unsigned blocks = (unsigned)((npix + 255) / 256);
-  if (channels == 1) k_pages_to_input<1><<<blocks, 256, 0, st>>>(pages, npix, out, gray_out);
-  else k_pages_to_input<3><<<blocks, 256, 0, st>>>(pages, npix, out, gray_out);
+  long long done = 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(pages) | reinterpret_cast<uintptr_t>(gray_out)) & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (aligned && npix >= 4) {
+    const long long nquad = npix / 4;
+    const unsigned blocks = (unsigned)((nquad + 255) / 256);
+    if (channels == 1)
+      k_pages_to_input4<1><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(pages), nquad,
+                                                   reinterpret_cast<float4*>(out), reinterpret_cast<uint32_t*>(gray_out));
+    else
+      k_pages_to_input4<3><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(pages), nquad,
+                                                   reinterpret_cast<float4*>(out), reinterpret_cast<uint32_t*>(gray_out));
+    done = nquad * 4;
+  }
+  if (done < npix) {   // tail (or unaligned buffers): one pixel per thread
+    const long long rest = npix - done;
+    const unsigned blocks = (unsigned)((rest + 255) / 256);
+    uint8_t* go = gray_out ? gray_out + done : nullptr;
+    if (channels == 1) k_pages_to_input<1><<<blocks, 256, 0, st>>>(pages + done, rest, out + done, go);
+    else k_pages_to_input<3><<<blocks, 256, 0, st>>>(pages + done * 3, rest, out + done, go);
+  }
   return cudaGetLastError();
 }
 
 // ---- f2a: connected-component size filter ---------------------------------------------------------------------------
-// One warp = 32 consecutive pixels of one row (blockDim = (32, 8), grid = (ceil(W/32), ceil(H/8), N)); a label is a page-
-// local pixel index, -1 = background.  k_cc_init points every foreground pixel at the first pixel of its run inside the
-// 32-pixel word (so horizontal runs are pre-merged), k_cc_merge hooks runs across word boundaries and to the row above
-// (only where the link is not implied by a neighbour's link), k_cc_count flattens and accumulates areas per root (one
-// atomicAdd per in-word run), k_cc_filter_pack keeps area >= min_size and writes the result as bits.
+// Works on the 1-bit image (bit b of word i of a row = pixel 32 i + b, pad bits 0), one thread per 32-pixel word.  The
+// union-find nodes are the in-word runs of ones: a label is the page-local pixel index of a run's first pixel, and the
+// int32 label / area arrays are only ever touched there (a thresholded separator map is a few percent foreground, so the
+// traffic is the 1/8 B/px bit image plus sparse sectors).  k_cc_init makes every run its own root, k_cc_merge hooks runs
+// across word boundaries and to the touching runs of the row above, (only where the link is not implied by a neighbour's own link), k_cc_count flattens and accumulates
+
 __device__ __forceinline__ int run_start(unsigned bits, int lane) {
   const unsigned zeros_below = ~bits & ((1u << lane) - 1u);
   return zeros_below ? 32 - __clz(zeros_below) : 0;
 }
 
-__global__ void __launch_bounds__(256) k_cc_init(const uint8_t* __restrict__ mask, int H, int W, int* __restrict__ label,
-                                                 int* __restrict__ area) {
+// uint8 mask (non-zero = foreground) -> bits.  A warp packs 128 pixels of one row: 4 per lane, nibbles merged by shuffles.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) k_bits_pack(const uint8_t* __restrict__ mask, int H, int W, int Wd,
+                                                   uint32_t* __restrict__ bits_out) {
   const int lane = threadIdx.x;
-  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + threadIdx.y;
+  const int y = blockIdx.y * 8 + threadIdx.y;
   if (y >= H) return;
-  const long long page = (long long)blockIdx.z * H * W;
-  const bool in = x < W;
-  const bool fg = in && mask[page + (long long)y * W + x] != 0;
-  const unsigned bits = __ballot_sync(0xffffffffu, fg);
-  if (!in) return;
-  const int idx = y * W + x;
-  label[page + idx] = fg ? idx - lane + run_start(bits, lane) : -1;
-  area[page + idx] = 0;
+  const int x = blockIdx.x * 128 + lane * 4;
+  const uint8_t* row = mask + ((long long)blockIdx.z * H + y) * W;
+  unsigned nib = 0;
+  if (VEC4) {   // W % 4 == 0: every row is 4-byte aligned and x + 3 < W whenever x < W
+    if (x < W) {
+      const uchar4 v = *reinterpret_cast<const uchar4*>(row + x);
+      nib = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
+    }
+  } else {
+    for (int j = 0; j < 4; ++j)
+      if (x + j < W && row[x + j]) nib |= 1u << j;
+  }
+  unsigned v = nib << (4 * (lane & 7));
+  v |= __shfl_xor_sync(0xffffffffu, v, 1);
+  v |= __shfl_xor_sync(0xffffffffu, v, 2);
+  v |= __shfl_xor_sync(0xffffffffu, v, 4);
+  const int wi = blockIdx.x * 4 + (lane >> 3);
+  if ((lane & 7) == 0 && wi < Wd) bits_out[((long long)blockIdx.z * H + y) * Wd + wi] = v;
+}
+
+// ---- one thread per 32-pixel word; labels exist only at the first pixel of every in-word run ----
+struct WordAt {
+  long long t;   // word index in the batch
+  int n, y, i;   // page, row, word of the row
+};
+__device__ __forceinline__ bool word_at(int N, int H, int Wd, WordAt& a) {
+  a.t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_page = (long long)H * Wd;
+  if (a.t >= per_page * N) return false;
+  a.n = (int)(a.t / per_page);
+  const long long rem = a.t - a.n * per_page;
+  a.y = (int)(rem / Wd);
+  a.i = (int)(rem - (long long)a.y * Wd);
+  return true;
+}
+// next run of ones in `rem` (a suffix of `bits`): [s, s + len); strips it from rem
+__device__ __forceinline__ void next_run(unsigned bits, unsigned& rem, int& s, int& len) {
+  s = __ffs(rem) - 1;
+  const unsigned above = ~(bits >> s);
+  len = above ? __ffs(above) - 1 : 32 - s;
+  rem = (s + len >= 32) ? 0u : (rem & ~((1u << (s + len)) - 1u));
+}
+
+__global__ void __launch_bounds__(256) k_cc_init(const uint32_t* __restrict__ bits_in, int N, int H, int W, int Wd,
+                                                 int* __restrict__ label, int* __restrict__ area) {
+  WordAt a;
+  if (!word_at(N, H, Wd, a)) return;
+  const unsigned bits = bits_in[a.t];
+  if (!bits) return;
+  const long long page = (long long)a.n * H * W;
+  const int base = a.y * W + a.i * 32;
+  unsigned rem = bits;
+  while (rem) {
+    int s, len;
+    next_run(bits, rem, s, len);
+    label[page + base + s] = base + s;
+    area[page + base + s] = 0;
+  }
 }
 
 __device__ __forceinline__ int uf_find(volatile int* L, int a) {
@@ -101,60 +196,89 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_cc_merge(int H, int W, int* __restrict__ label_all) {
-  const int lane = threadIdx.x;
-  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + threadIdx.y;
-  if (y >= H || x >= W) return;
-  int* L = label_all + (long long)blockIdx.z * H * W;
-  const int idx = y * W + x;
-  if (L[idx] < 0) return;
-  const bool wf = x > 0 && L[idx - 1] >= 0;
-  if (lane == 0 && wf) uf_union(L, idx, idx - 1);
-  if (y == 0) return;
-  const int up = idx - W;
-  const bool nf = L[up] >= 0;
-  const bool nwf = x > 0 && L[up - 1] >= 0;
-  if (nf) {
-    if (!(wf && nwf)) uf_union(L, idx, up);   // otherwise this ~ W ~ NW ~ N through the neighbours' own links
-  } else {
-    if (nwf && !wf) uf_union(L, idx, up - 1);
-    if (x + 1 < W && L[up + 1] >= 0) uf_union(L, idx, up + 1);
+// Every in-word run is hooked to (a) the run ending at bit 31 of the word to its left when it starts at bit 0, and
+// (b) every run fragment of the row above that touches it 8-connectedly: columns [s-1, s+len] of the row above, taken
+// from a 34-bit view U of that row (bit 0 = last pixel of the word up-left, bits 1..32 = the word above, bit 33 = first
+// pixel of the word up-right).
+__global__ void __launch_bounds__(256) k_cc_merge(const uint32_t* __restrict__ bits_in, int N, int H, int W, int Wd,
+                                                  int* __restrict__ label_all) {
+  WordAt a;
+  if (!word_at(N, H, Wd, a)) return;
+  const unsigned cur = bits_in[a.t];
+  if (!cur) return;
+  int* L = label_all + (long long)a.n * H * W;
+  const int base = a.y * W + a.i * 32;
+  const unsigned left = a.i > 0 ? bits_in[a.t - 1] : 0u;
+  unsigned up = 0, upl = 0, upr = 0;
+  if (a.y > 0) {
+    up = bits_in[a.t - Wd];
+    if (a.i > 0) upl = bits_in[a.t - Wd - 1];
+    if (a.i + 1 < Wd) upr = bits_in[a.t - Wd + 1];
+  }
+  const unsigned long long U = ((unsigned long long)up << 1) | (upl >> 31) | ((unsigned long long)(upr & 1u) << 33);
+  const int ubase = base - W;   // index of bit 1 of U (pixel 32 i of the row above)
+  unsigned rem = cur;
+  while (rem) {
+    int s, len;
+    next_run(cur, rem, s, len);
+    const int me = base + s;
+    if (s == 0 && (left >> 31)) uf_union(L, me, base - 32 + run_start(left, 31));
+    // bits [s, s+len+1] of U
+    unsigned long long touch = (U >> s) & ((2ull << (len + 1)) - 1ull);
+    while (touch) {
+      const int b = __ffsll((long long)touch) - 1 + s;       // bit position in U of the first pixel of a fragment
+      int other;
+      if (b == 0) other = ubase - 32 + run_start(upl, 31);
+      else if (b == 33) other = ubase + 32;
+      else other = ubase + run_start(up, b - 1);
+      uf_union(L, me, other);
+      // strip this fragment (consecutive ones from b upwards, within U)
+      const unsigned long long from = touch >> (b - s);
+      const unsigned long long inv = ~from;
+      const int flen = inv ? __ffsll((long long)inv) - 1 : 64;
+      touch = (b - s + flen >= 64) ? 0ull : (touch & ~((1ull << (b - s + flen)) - 1ull));
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) k_cc_count(int H, int W, int* __restrict__ label_all, int* __restrict__ area_all) {
-  const int lane = threadIdx.x;
-  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + threadIdx.y;
-  if (y >= H) return;
-  const long long page = (long long)blockIdx.z * H * W;
+__global__ void __launch_bounds__(256) k_cc_count(const uint32_t* __restrict__ bits_in, int N, int H, int W, int Wd,
+                                                  int* __restrict__ label_all, int* __restrict__ area_all) {
+  WordAt a;
+  if (!word_at(N, H, Wd, a)) return;
+  const unsigned bits = bits_in[a.t];
+  if (!bits) return;
+  const long long page = (long long)a.n * H * W;
   int* L = label_all + page;
-  const int idx = y * W + x;
-  const bool fg = x < W && L[idx] >= 0;
-  const unsigned bits = __ballot_sync(0xffffffffu, fg);
-  if (!fg) return;
-  const int root = uf_find(L, idx);
-  L[idx] = root;
-  if (run_start(bits, lane) == lane) {          // leader of an in-word run: all its pixels share the root
-    const unsigned above = ~(bits >> lane);     // first zero above the leader ends the run
-    const int len = above ? __ffs(above) - 1 : 32 - lane;
+  const int base = a.y * W + a.i * 32;
+  unsigned rem = bits;
+  while (rem) {
+    int s, len;
+    next_run(bits, rem, s, len);
+    const int root = uf_find(L, base + s);
+    L[base + s] = root;
     atomicAdd(&area_all[page + root], len);
   }
 }
 
-__global__ void __launch_bounds__(256) k_cc_filter_pack(int H, int W, int Wd, const int* __restrict__ label_all,
-                                                        const int* __restrict__ area_all, int min_size,
-                                                        uint32_t* __restrict__ bits_out) {
-  const int lane = threadIdx.x;
-  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + threadIdx.y;
-  if (y >= H) return;
-  const long long page = (long long)blockIdx.z * H * W;
-  bool keep = false;
-  if (x < W) {
-    const int root = label_all[page + (long long)y * W + x];
-    keep = root >= 0 && area_all[page + root] >= min_size;
+__global__ void __launch_bounds__(256) k_cc_filter(const uint32_t* __restrict__ bits_in, int N, int H, int W, int Wd,
+                                                   const int* __restrict__ label_all, const int* __restrict__ area_all,
+                                                   int min_size, uint32_t* __restrict__ bits_out) {
+  WordAt a;
+  if (!word_at(N, H, Wd, a)) return;
+  const unsigned bits = bits_in[a.t];
+  unsigned keep = 0;
+  if (bits) {
+    const long long page = (long long)a.n * H * W;
+    const int base = a.y * W + a.i * 32;
+    unsigned rem = bits;
+    while (rem) {
+      int s, len;
+      next_run(bits, rem, s, len);
+      if (area_all[page + label_all[page + base + s]] >= min_size)
+        keep |= (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
+    }
   }
-  const unsigned bits = __ballot_sync(0xffffffffu, keep);
-  if (lane == 0) bits_out[((long long)blockIdx.z * H + y) * Wd + blockIdx.x] = bits;
+  bits_out[a.t] = keep;
 }
 
 // ---- f2b: rectangular erode / dilate on the 1-bit image -------------------------------------------------------------
@@ -213,7 +337,27 @@ __global__ void __launch_bounds__(256) k_bits_andnot(const uint32_t* __restrict_
   if (t < words) out[t] = a[t] & ~b[t];
 }
 
-// bits -> uint8 {0,255}; one thread per 4 pixels of a row (one 32-bit store when the row pitch allows it)
+// bits -> uint8 {0,255}; one thread per 16 pixels of a row (one 128-bit store) when W % 16 == 0
+__global__ void __launch_bounds__(256) k_bits_unpack16(const uint32_t* __restrict__ bits, uint8_t* __restrict__ out,
+                                                       long long rows, int W, int Wd) {
+  const int per_row = W >> 4;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * per_row) return;
+  const long long row = t / per_row;
+  const int x = (int)(t - row * per_row) * 16;
+  const uint32_t h = (bits[row * Wd + (x >> 5)] >> (x & 31)) & 0xffffu;
+  uint4 v;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t nib = (h >> (4 * j)) & 15u;
+    o[j] = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) |
+           ((nib & 8u) ? 0xff000000u : 0u);
+  }
+  *reinterpret_cast<uint4*>(out + row * W + x) = v;
+}
+
+// general widths: one thread per 4 pixels of a row (one 32-bit store when the row pitch allows it)
 __global__ void __launch_bounds__(256) k_bits_unpack(const uint32_t* __restrict__ bits, uint8_t* __restrict__ out,
                                                      long long rows, int W, int Wd) {
   const int quads = (W + 3) >> 2;
@@ -232,18 +376,21 @@ __global__ void __launch_bounds__(256) k_bits_unpack(const uint32_t* __restrict_
   }
 }
 
-// uint8 mask -> bits (used when the component filter is skipped in tests of the morphology alone)
-__global__ void __launch_bounds__(256) k_bits_pack(const uint8_t* __restrict__ mask, int H, int W, int Wd,
-                                                   uint32_t* __restrict__ bits_out) {
-  const int lane = threadIdx.x;
-  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + threadIdx.y;
-  if (y >= H) return;
-  const bool fg = x < W && mask[((long long)blockIdx.z * H + y) * W + x] != 0;
-  const unsigned bits = __ballot_sync(0xffffffffu, fg);
-  if (lane == 0) bits_out[((long long)blockIdx.z * H + y) * Wd + blockIdx.x] = bits;
+static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
+
+static void bits_pack(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int Wd, uint32_t* bits) {
+  const dim3 blk(32, 8), grd((w + 127) / 128, (h + 7) / 8, n);
+  if ((w & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3) == 0) k_bits_pack<true><<<grd, blk, 0, st>>>(mask, h, w, Wd, bits);
+  else k_bits_pack<false><<<grd, blk, 0, st>>>(mask, h, w, Wd, bits);
 }
 
-static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
+static void bits_unpack(cudaStream_t st, const uint32_t* bits, uint8_t* out, int n, int h, int w, int Wd) {
+  const long long rows = (long long)n * h;
+  if ((w & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    k_bits_unpack16<<<nblk(rows * (w >> 4)), 256, 0, st>>>(bits, out, rows, w, Wd);
+  else
+    k_bits_unpack<<<nblk(rows * ((w + 3) / 4)), 256, 0, st>>>(bits, out, rows, w, Wd);
+}
 
 static void bits_open(cudaStream_t st, const uint32_t* in, uint32_t* tmp, uint32_t* out, int N, int H, int W, int Wd,
                       int k, bool horizontal) {
@@ -262,7 +409,7 @@ size_t separator_post_scratch_bytes(int n, int h, int w) {
   return 2 * px * sizeof(int) + 4 * words * sizeof(uint32_t) + 1024;
 }
 
-int separator_post_launches() { return 4 + 2 + 2 + 1 + 2 + 2; }
+int separator_post_launches() { return 5 + 2 + 2 + 1 + 2 + 2; }
 
 cudaError_t launch_separator_post(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int min_size, int k_h1,
                                   int k_v, int k_h2, void* scratch, uint8_t* out_h, uint8_t* out_v) {
@@ -274,18 +421,17 @@ cudaError_t launch_separator_post(cudaStream_t st, const uint8_t* mask, int n, i
   int* area = label + px;
   uint32_t* b0 = reinterpret_cast<uint32_t*>(area + px);
   uint32_t *b1 = b0 + words, *b2 = b1 + words, *b3 = b2 + words;
-  const dim3 blk(32, 8), grd(Wd, (h + 7) / 8, n);
-  k_cc_init<<<grd, blk, 0, st>>>(mask, h, w, label, area);
-  k_cc_merge<<<grd, blk, 0, st>>>(h, w, label);
-  k_cc_count<<<grd, blk, 0, st>>>(h, w, label, area);
-  k_cc_filter_pack<<<grd, blk, 0, st>>>(h, w, Wd, label, area, min_size, b0);
+  bits_pack(st, mask, n, h, w, Wd, b3);
+  k_cc_init<<<nblk(words), 256, 0, st>>>(b3, n, h, w, Wd, label, area);
+  k_cc_merge<<<nblk(words), 256, 0, st>>>(b3, n, h, w, Wd, label);
+  k_cc_count<<<nblk(words), 256, 0, st>>>(b3, n, h, w, Wd, label, area);
+  k_cc_filter<<<nblk(words), 256, 0, st>>>(b3, n, h, w, Wd, label, area, min_size, b0);
   bits_open(st, b0, b3, b1, n, h, w, Wd, k_h1, true);    // b1 = horizontal opening
   bits_open(st, b0, b3, b2, n, h, w, Wd, k_v, false);    // b2 = vertical opening
   k_bits_andnot<<<nblk(words), 256, 0, st>>>(b1, b2, b0, (long long)words);
   bits_open(st, b0, b3, b1, n, h, w, Wd, k_h2, true);    // b1 = cleaned horizontal mask
-  const long long rows = (long long)n * h, quads = rows * ((w + 3) / 4);
-  k_bits_unpack<<<nblk(quads), 256, 0, st>>>(b1, out_h, rows, w, Wd);
-  k_bits_unpack<<<nblk(quads), 256, 0, st>>>(b2, out_v, rows, w, Wd);
+  bits_unpack(st, b1, out_h, n, h, w, Wd);
+  bits_unpack(st, b2, out_v, n, h, w, Wd);
   return cudaGetLastError();
 }
 
@@ -297,13 +443,11 @@ cudaError_t launch_open_rect(cudaStream_t st, const uint8_t* mask, int n, int h,
   const size_t px = (size_t)n * h * w, words = (size_t)n * h * Wd;
   uint32_t* b0 = reinterpret_cast<uint32_t*>(reinterpret_cast<int*>(scratch) + 2 * px);
   uint32_t *b1 = b0 + words, *b3 = b1 + 2 * words;
-  const dim3 blk(32, 8), grd(Wd, (h + 7) / 8, n);
-  k_bits_pack<<<grd, blk, 0, st>>>(mask, h, w, Wd, b0);
+  bits_pack(st, mask, n, h, w, Wd, b0);
   const uint32_t* res = b0;
   if (kw > 1) { bits_open(st, b0, b3, b1, n, h, w, Wd, kw, true); res = b1; }
   else if (kh > 1) { bits_open(st, b0, b3, b1, n, h, w, Wd, kh, false); res = b1; }
-  const long long rows = (long long)n * h;
-  k_bits_unpack<<<nblk(rows * ((w + 3) / 4)), 256, 0, st>>>(res, out, rows, w, Wd);
+  bits_unpack(st, res, out, n, h, w, Wd);
   return cudaGetLastError();
 }
 

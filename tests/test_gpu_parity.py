@@ -74,7 +74,7 @@ def test_native_library_is_what_runs(engines):
 
 
 @pytest.mark.parametrize("path,pname", PATHS)
-@pytest.mark.parametrize("fixture", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))), ids=os.path.basename)
+@pytest.mark.parametrize("fixture", sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("post_")), ids=os.path.basename)
 def test_golden_fixtures(engines, fixture, path, pname):
     from aru_b200.engine import OPT_CONV_PATH
     from aru_b200.synth import page_to_net_input
