@@ -164,6 +164,8 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
             in_b = 4 if op.inp.ch == 1 else 2
             out_b = 4 if kernel in ("conv_small", "conv_tc_head", "conv_band_head") else 2
             bytes_ = n * (ih * iw * op.inp.ch * in_b + oh * ow * op.out.ch * out_b)
+            if kernel == "conv_stem_pool":     # only the pooled tensor is stored
+                bytes_ = n * (ih * iw * 4 + -(-oh // 2) * -(-ow // 2) * op.out.ch * 2)
             if op.res.buf >= 0:
                 bytes_ += n * oh * ow * op.out.ch * 2
             if op.out_pre.buf >= 0:

@@ -68,6 +68,7 @@ struct Plan {
   std::vector<char> use_band;           // per op: the row-banded kernel won the plan-time timing (or is the only one)
   std::vector<int> fused_pool;          // per conv op: the MAXPOOL op its row-banded launch also performs (-1: none)
   std::vector<char> skip;               // per op: performed by another op's launch
+  std::vector<char> pool_only;          // per stem conv op with a fused pool: nothing else reads its full-resolution output
   act_t* scratch = nullptr;             // partial sums of split-K launches
   size_t scratch_bytes = 0;
   std::vector<const char*> kernel;   // per op label
@@ -101,7 +102,7 @@ struct aru_engine {
   std::vector<OpWeights> opw;
   std::vector<int> kind;  // per buffer
   int input_buf = -1, output_buf = -1, n_class = 0;
-  int conv_path = 0, use_graph = 1, micro_batch = 0;
+  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0;
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   int* err_flag = nullptr;
   float* zero_bias = nullptr;
@@ -276,10 +277,12 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
       const BufPlan& bi = p->bufs[op.in.buf];
       const BufPlan& bo = p->bufs[op.out.buf];
       if (bi.kind == KIND_F32) {
-        label = "conv_stem";
+        const int pj = p->fused_pool[oi];
+        label = pj >= 0 ? (p->pool_only[oi] ? "conv_stem_pool" : "conv_stem_fpool") : "conv_stem";
         err = launch_conv_stem(st, op.ksize, f32_ptr(e, p, op.in.buf, parity), make_pv(e, p, op.out),
                                make_pv(e, p, op.out_pre), e->weights.data() + op.w_off, e->weights.data() + op.b_off,
-                               bo.geo, op.act);
+                               bo.geo, op.act, pj >= 0 ? make_pv(e, p, e->ops[pj].out) : PV(),
+                               pj >= 0 ? &p->bufs[e->ops[pj].out.buf].geo : nullptr, !p->pool_only[oi]);
       } else if (bo.kind != KIND_PLANAR && p->band[oi].ok && p->use_band[oi]) {
         label = "conv_band_head";
         err = launch_conv_band(st, p->band[oi], make_pv(e, p, op.in), PV(), PV(), PV(), ow.band_w, ow.bias, bi.geo, op.act,
@@ -430,6 +433,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   p->use_band.assign(no, 0);
   p->fused_pool.assign(no, -1);
   p->skip.assign(no, 0);
+  p->pool_only.assign(no, 0);
   p->kernel.assign(no, "?");
   for (int i = 0; i < nb; ++i) {
     p->bufs[i].kind = e->kind[i];
@@ -653,6 +657,22 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
             conv_band_can_pool(p->band[i], co.act, co.in.ch, co.ksize)) {
           p->fused_pool[i] = j;
           p->skip[j] = 1;
+        } else if (co.kind == ARU_OP_CONV && co.out.ch_off == po.in.ch_off && co.out.ch == po.in.ch &&
+                   p->bufs[co.in.buf].kind == KIND_F32 && p->bufs[co.out.buf].kind == KIND_PLANAR && co.act == ARU_ACT_RELU &&
+                   co.out_pre.buf < 0 && co.out.ch <= 16 && p->fused_pool[i] < 0) {
+          // stem convolution (1-channel float32 input, CUDA cores): the launch pools too, and when nothing but the pool
+          // reads the full-resolution tensor it is not stored at all (ARU_OPT_KEEP_ALL = 1 stores it anyway)
+          p->fused_pool[i] = j;
+          p->skip[j] = 1;
+          bool other_reader = false;
+          for (int k = 0; k < no && !other_reader; ++k) {
+            if (k == j || k == i) continue;
+            const aru_op& ro = e->ops[k];
+            other_reader = ro.in.buf == co.out.buf || ro.res.buf == co.out.buf;
+            for (int a = 0; a < ARU_MAX_SCALES && !other_reader; ++a)
+              other_reader = ro.att[a].buf == co.out.buf || ro.det[a].buf == co.out.buf;
+          }
+          p->pool_only[i] = !other_reader && !e->keep_all && co.out.buf != e->output_buf;
         }
         break;   // the last writer of the pool's input decides
       }
@@ -1073,6 +1093,16 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
       return ARU_OK;
     case ARU_OPT_USE_GRAPH:
       e->use_graph = value ? 1 : 0;
+      return ARU_OK;
+    case ARU_OPT_KEEP_ALL:
+      if (e->keep_all != (value ? 1 : 0)) {
+        cudaSetDevice(e->device);
+        cudaDeviceSynchronize();
+        for (auto& p : e->plans) free_plan(p.get());
+        e->plans.clear();
+        e->cur = nullptr;
+      }
+      e->keep_all = value ? 1 : 0;
       return ARU_OK;
     case ARU_OPT_MICRO_BATCH:
       if (value < 0 || value > 4096) return fail(e, ARU_EINVAL, "bad micro batch");

@@ -30,8 +30,11 @@ struct CombineArgs {
 
 // ---- CUDA-core kernels (kernels_simple.cu) -------------------------------------------------------
 // w_host / bias_host: HOST pointers to the TF filter [ks][ks][1][C_out] and bias [C_out] (passed as kernel parameters)
+// pool.p != null: the launch also performs the 2x2 stride-2 SAME max-pool of its ReLU'd output (pool_geo = the pooled
+// geometry); full == false then skips the store of the full-resolution tensor (nothing but the pool reads it)
 cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w_host,
-                             const float* bias_host, const Geo& g, int act);
+                             const float* bias_host, const Geo& g, int act, PV pool = PV(), const Geo* pool_geo = nullptr,
+                             bool full = true);
 cudaError_t launch_conv_direct(cudaStream_t st, int ks, PV in, PV out, PV out_pre, PV res, const act_t* w,
                                const float* bias, const Geo& g, int act);
 cudaError_t launch_conv_small(cudaStream_t st, int ks, int cout, PV in, float* out, const float* w, const float* bias,

@@ -88,6 +88,84 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float* __restrict__ in,
   }
 }
 
+// Stem conv + ReLU + 2x2 stride-2 SAME max-pool in one launch (ARU_v1.py:173-176: the attention CNN's conv1 feeds
+// nothing but its pool).  Same walk as k_conv_stem; the packed 16-bit results of an even row are kept in registers, the
+// odd row is max-ed in (packed hmax2; the maximum commutes with the rounding, so this equals pooling the stored
+// 16-bit tensor), one shfl.xor brings the neighbouring column and even lanes store the pooled pixel.  Post-ReLU values
+// are >= 0, so columns / rows beyond the image contribute zeros (TF pads the pool with -inf: same maximum).
+// FULL: also store the full-resolution tensor (needed only when something other than the pool reads it).
+static __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+#ifdef ARU_USE_BF16
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+#else
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+#endif
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+static __device__ __forceinline__ uint4 hmax2_u4(uint4 a, uint4 b) {
+  return make_uint4(hmax2_u32(a.x, b.x), hmax2_u32(a.y, b.y), hmax2_u32(a.z, b.z), hmax2_u32(a.w, b.w));
+}
+
+template <int KS, int COUT, bool FULL>
+__global__ void __launch_bounds__(128) k_conv_stem_pool(const float* __restrict__ in, act_t* __restrict__ out,
+                                                        long long out_plane, act_t* __restrict__ pool,
+                                                        long long pool_plane, const __grid_constant__ StemW sw, Geo g,
+                                                        Geo gp) {
+  constexpr int CH = (COUT + 7) / 8, PB = (KS - 1) / 2;
+  const int n = blockIdx.z, y0 = blockIdx.y * STEM_ROWS, x = blockIdx.x * 128 + threadIdx.x;
+  const bool live = x < g.W;   // dead lanes stay for the shuffles and contribute zeros
+  const float* img = in + (long long)n * g.H * g.W;
+  bool okx[KS];
+#pragma unroll
+  for (int kx = 0; kx < KS; ++kx) okx[kx] = (unsigned)(x + kx - PB) < (unsigned)g.W;
+  auto load_row = [&](int yy, float r[KS]) {
+    const bool oky = (unsigned)yy < (unsigned)g.H;
+    const float* row = img + (long long)yy * g.W + (x - PB);
+#pragma unroll
+    for (int kx = 0; kx < KS; ++kx) r[kx] = (oky && okx[kx]) ? __ldg(row + kx) : 0.f;
+  };
+  float v[KS][KS];
+#pragma unroll
+  for (int ky = 0; ky < KS - 1; ++ky) load_row(y0 + ky - PB, v[ky + 1]);
+  const int y1 = min(y0 + STEM_ROWS, g.H);
+  long long p = g.pos(n, y0, x);
+  uint4 even[CH];
+  for (int y = y0; y < y1; ++y, p += g.Wp) {
+#pragma unroll
+    for (int ky = 0; ky < KS - 1; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) v[ky][kx] = v[ky + 1][kx];
+    load_row(y + KS - 1 - PB, v[KS - 1]);
+    const bool odd = y & 1, last = y + 1 == g.H;   // STEM_ROWS is even: row pairs never straddle two blocks
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = (c * 8 + j < COUT) ? sw.b[c * 8 + j] : 0.f;
+#pragma unroll
+      for (int t = 0; t < KS * KS; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c * 8 + j < COUT) acc[j] = fmaf(v[t / KS][t % KS], sw.w[t * 16 + c * 8 + j], acc[j]);
+      const uint4 cur = pack8_fin<true>(acc, live);
+      if (FULL && live) *reinterpret_cast<uint4*>(out + (c * out_plane + p) * 8) = cur;
+      if (!odd && !last) {
+        even[c] = cur;
+      } else {
+        uint4 m = odd ? hmax2_u4(even[c], cur) : cur;
+        uint4 nb;
+        nb.x = __shfl_xor_sync(0xffffffffu, m.x, 1);
+        nb.y = __shfl_xor_sync(0xffffffffu, m.y, 1);
+        nb.z = __shfl_xor_sync(0xffffffffu, m.z, 1);
+        nb.w = __shfl_xor_sync(0xffffffffu, m.w, 1);
+        m = hmax2_u4(m, nb);
+        if (live && !(x & 1))
+          *reinterpret_cast<uint4*>(pool + (c * pool_plane + gp.pos(n, y >> 1, x >> 1)) * 8) = m;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Direct conv, chunk-planar -> chunk-planar (validation twin of conv_tc).  One thread = one pixel x
 // one output chunk.  Weights packed [tap][cin_chunk][cout_chunk][ci 8][co 8] (16-bit).
@@ -498,7 +576,7 @@ static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + 
 static inline long long npix(const Geo& g) { return (long long)g.N * g.H * g.W; }
 
 cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w_host,
-                             const float* bias_host, const Geo& g, int act) {
+                             const float* bias_host, const Geo& g, int act, PV pool, const Geo* pool_geo, bool full) {
   // w_host: the TF filter [ks][ks][1][C_out] (host memory), bias_host [C_out]; both travel in the kernel parameters
   const int cout = out.C;
   if (cout < 1 || cout > 16 || (ks != 3 && ks != 4) || g.H > 65535 || g.N > 65535) return cudaErrorInvalidValue;
@@ -509,6 +587,17 @@ cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, P
     for (int c = 0; c < cout; ++c) sw.w[t * 16 + c] = w_host[(size_t)t * cout + c];
   const dim3 grid((unsigned)cdiv(g.W, 128), (unsigned)cdiv(g.H, STEM_ROWS), (unsigned)g.N);
   const int cc = cout <= 8 ? 8 : (cout <= 12 ? 12 : 16);  // instantiated widths (padding channels have zero weights)
+  if (pool.p) {   // conv + ReLU + 2x2 max-pool (full == false: the full-resolution tensor is not stored at all)
+    if (act != 1 || out_pre.p || !pool_geo) return cudaErrorInvalidValue;
+#define ARU_STEM_POOL(KK, CC)                                                                                          \
+  if (ks == KK && cc == CC) {                                                                                          \
+    if (full) k_conv_stem_pool<KK, CC, true><<<grid, 128, 0, st>>>(in, out.p, out.plane, pool.p, pool.plane, sw, g, *pool_geo); \
+    else k_conv_stem_pool<KK, CC, false><<<grid, 128, 0, st>>>(in, out.p, out.plane, pool.p, pool.plane, sw, g, *pool_geo);     \
+  }
+    ARU_STEM_POOL(3, 8) ARU_STEM_POOL(3, 12) ARU_STEM_POOL(3, 16) ARU_STEM_POOL(4, 8) ARU_STEM_POOL(4, 12) ARU_STEM_POOL(4, 16)
+#undef ARU_STEM_POOL
+    return cudaGetLastError();
+  }
 #define ARU_STEM(KK, CC)                                                                                              \
   if (ks == KK && cc == CC)                                                                                           \
     k_conv_stem<KK, CC><<<grid, 128, 0, st>>>(in, out.p, out.plane, out_pre.p, out_pre.plane, sw, g, act);

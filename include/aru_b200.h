@@ -100,6 +100,8 @@ typedef struct aru_engine aru_engine;
                                  2 = tcgen05 position-major kernel only, 3 = row-banded kernel wherever it applies */
 #define ARU_OPT_USE_GRAPH 2   /* 1 = replay a captured CUDA graph per plan (default), 0 = plain launches */
 #define ARU_OPT_MICRO_BATCH 3 /* pages per pass through the net inside aru_forward (0 = auto) */
+#define ARU_OPT_KEEP_ALL 4    /* 1 = store every lowered tensor (per-layer checks through aru_read_buffer); 0 (default) =
+                                 a tensor read only by a pool that its producer's launch performs is not stored */
 
 int aru_abi_version(void);
 int aru_device_count(void);

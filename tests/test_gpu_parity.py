@@ -110,10 +110,11 @@ def test_parity_with_oracle(engines, oracles, net, h, w, path, pname):
 @pytest.mark.parametrize("path,pname", PATHS)
 def test_per_layer_parity(engines, oracles, path, pname):
     """Every surviving GraphDef node of the tiny net against the oracle's value of the same node."""
-    from aru_b200.engine import OPT_CONV_PATH
+    from aru_b200.engine import OPT_CONV_PATH, OPT_KEEP_ALL
     from aru_b200.synth import synth_page, page_to_net_input
     eng, orc = engines("tiny"), oracles("tiny")
     eng.set_option(OPT_CONV_PATH, path)
+    eng.set_option(OPT_KEEP_ALL, 1)     # also store tensors that only a fused pool reads
     x = page_to_net_input(synth_page(45, 39, seed=3))
     eng.forward(x)
     checked = 0
@@ -127,6 +128,7 @@ def test_per_layer_parity(engines, oracles, path, pname):
         assert np.abs(got - ref).max() <= 2e-2 * scale, f"{node} [{pname}]: {np.abs(got - ref).max():.3e} (scale {scale:.2f})"
         checked += 1
     assert checked > 40
+    eng.set_option(OPT_KEEP_ALL, 0)
 
 
 def test_batch_and_micro_batch_consistency(engines):
