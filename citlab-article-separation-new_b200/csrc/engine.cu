@@ -168,8 +168,9 @@ int pack_op_weights(aru_engine* e, int oi) {
   if (rc) return rc;
   const int ik = e->kind[op.in.buf], okind = e->kind[op.out.buf];
   if (op.kind == ARU_OP_CONV && ik == KIND_F32) {
-    // stem: [tap][cpad] (filter is [kh][kw][1][cout])
-    const int cpad = coutc * 8;
+    // stem: [tap][16] (filter is [kh][kw][1][cout], cout <= 16)
+    const int cpad = 16;
+    if (cout > 16) return fail(e, ARU_EUNSUP, "op %d: 1-channel convolution with %d > 16 output channels", oi, cout);
     std::vector<float> p((size_t)ks * ks * cpad, 0.f);
     for (int t = 0; t < ks * ks; ++t)
       for (int c = 0; c < cout; ++c) p[(size_t)t * cpad + c] = w[(size_t)t * cout + c];
@@ -282,7 +283,7 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
         err = launch_conv_stem(st, op.ksize, f32_ptr(e, p, op.in.buf, parity), make_pv(e, p, op.out),
                                make_pv(e, p, op.out_pre), e->weights.data() + op.w_off, e->weights.data() + op.b_off,
                                bo.geo, op.act, pj >= 0 ? make_pv(e, p, e->ops[pj].out) : PV(),
-                               pj >= 0 ? &p->bufs[e->ops[pj].out.buf].geo : nullptr, !p->pool_only[oi]);
+                               pj >= 0 ? &p->bufs[e->ops[pj].out.buf].geo : nullptr, !p->pool_only[oi], ow.w32, ow.bias);
       } else if (bo.kind != KIND_PLANAR && p->band[oi].ok && p->use_band[oi]) {
         label = "conv_band_head";
         err = launch_conv_band(st, p->band[oi], make_pv(e, p, op.in), PV(), PV(), PV(), ow.band_w, ow.bias, bi.geo, op.act,

@@ -34,7 +34,9 @@ struct CombineArgs {
 // geometry); full == false then skips the store of the full-resolution tensor (nothing but the pool reads it)
 cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w_host,
                              const float* bias_host, const Geo& g, int act, PV pool = PV(), const Geo* pool_geo = nullptr,
-                             bool full = true);
+                             bool full = true, const float* w_dev16 = nullptr, const float* bias_dev16 = nullptr);
+// w_dev16 / bias_dev16: device copies of the filter as [tap][16] float32 and of the bias padded to 16 (the tensor-core
+// variant of the pooled 4x4 stem gathers its per-lane fragments from them)
 cudaError_t launch_conv_direct(cudaStream_t st, int ks, PV in, PV out, PV out_pre, PV res, const act_t* w,
                                const float* bias, const Geo& g, int act);
 cudaError_t launch_conv_small(cudaStream_t st, int ks, int cout, PV in, float* out, const float* w, const float* bias,

@@ -11,6 +11,8 @@
 // frame of the activation layout (aru_common.cuh) the chunk-planar kernels need no bounds checks on
 // their reads; they only ever store to in-image positions.
 #include "aru_common.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace aru {
@@ -163,6 +165,182 @@ __global__ void __launch_bounds__(128) k_conv_stem_pool(const float* __restrict_
           *reinterpret_cast<uint4*>(pool + (c * pool_plane + gp.pos(n, y >> 1, x >> 1)) * 8) = m;
       }
     }
+  }
+}
+
+// 4x4 stem conv + ReLU + 2x2 max-pool on the tensor cores (warp-level mma.sync: the 16 taps of the 4x4 window are
+// exactly one K = 16 step).  The FFMA version above is CUDA-core bound (192 FFMA per pixel, measured 43 % of the fp32
+// peak and 3x the HBM time of the pooled output); here a warp turns 32 pixels of a row into 2 (pixel tiles of 16) x NT
+// (channel tiles of 8) m16n8k16 MMAs:
+//   A[pixel][tap]   gathered as 32-bit (two adjacent kx) loads from a 16-bit shared-memory copy of the (16+3) x (128+3)
+//                   input tile - stored twice, the second copy shifted by one element, so that the pair (c, c+1) is
+//                   4-byte aligned in one of them whatever the parity of c;
+//   B[tap][channel] the filter, four 32-bit registers per thread for the whole kernel;
+//   D[pixel][ch]    lane (g, t) holds channels 2t, 2t+1 of pixels g, g+8: bias + ReLU + 16-bit pack per lane, the row pair
+//                   is max-ed in registers, the column pair comes from lane ^ 4, and a warp store writes 4-byte pieces
+//                   that tile 16-byte position vectors contiguously.
+// Operands are rounded to the 16-bit storage type like every other layer's (fp32 accumulate).
+static __device__ __forceinline__ void mma_16816(float d[4], const uint32_t a[4], const uint32_t b[2], const float c[2]) {
+  // D = A B + C with C = (c0, c1, c0, c1): the bias of this lane's two channels, never overwritten
+#ifdef ARU_USE_BF16
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+#else
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+#endif
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c[0]), "f"(c[1]));
+}
+// two fp32 -> packed 16-bit pair, plain round-to-nearest (an overflow becomes +-inf and is clamped by finish2)
+static __device__ __forceinline__ uint32_t pack2_raw(float x, float y) {
+  act2_t h;
+#ifdef ARU_USE_BF16
+  h = __floats2bfloat162_rn(x, y);
+#else
+  h = __floats2half2_rn(x, y);
+#endif
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// saturate to the finite range and ReLU a packed pair (both commute with the maximum of the pooling window)
+static __device__ __forceinline__ uint32_t finish2_relu(uint32_t v) {
+#ifdef ARU_USE_BF16
+  return hmax2_u32(v, 0u);
+#else
+  __half2 h = __hmin2(*reinterpret_cast<__half2*>(&v), __half2half2(__ushort_as_half((unsigned short)0x7bff)));
+  h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0)));
+  return *reinterpret_cast<uint32_t*>(&h);
+#endif
+}
+static __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// Tile rows are 144 halves (72 words: the two tap rows a warp reads land 8 banks apart) and the second copy starts 16
+// banks after the first, so the 32-bit fragment loads of a warp are conflict free.
+constexpr int SM_TILE_W = 128, SM_ROWS = STEM_ROWS + 3, SM_STRIDE = 144, SM_COPY = SM_ROWS * SM_STRIDE + 48;
+
+template <int NT, bool FULL>
+__global__ void __launch_bounds__(128) k_conv_stem4_pool_mma(const float* __restrict__ in, act_t* __restrict__ out,
+                                                             long long out_plane, act_t* __restrict__ pool,
+                                                             long long pool_plane, const float* __restrict__ w_dev,
+                                                             const float* __restrict__ bias_dev, Geo g, Geo gp) {
+  // w_dev: filter [16 taps][16] (float32, device memory; per-lane fragment gathers from the constant bank would replay
+  // once per distinct address), bias_dev [16]
+  __shared__ __align__(16) act_t tile_mem[2 * SM_COPY];
+  auto tile = [&](int copy, int r, int c) -> act_t& { return tile_mem[copy * SM_COPY + r * SM_STRIDE + c]; };
+  const int n = blockIdx.z, y0 = blockIdx.y * STEM_ROWS, x0 = blockIdx.x * SM_TILE_W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const float* img = in + (long long)n * g.H * g.W;
+  // tile[.][r][c] = pixel (y0 + r - 1, x0 + c - 1); copy 1 holds element c at index c + 1.  All loads of a thread are
+  // issued before the first conversion (one exposed memory latency per block instead of one per tile row).
+  {
+    float v[SM_ROWS];
+    const int gx = x0 + tid - 1;
+    const bool okx = (unsigned)gx < (unsigned)g.W;
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) {
+      const int gy = y0 + r - 1;
+      v[r] = (okx && (unsigned)gy < (unsigned)g.H) ? __ldg(img + (long long)gy * g.W + gx) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) {
+      const act_t h = f_to_act(v[r]);
+      tile(0, r, tid) = h;
+      tile(1, r, tid + 1) = h;
+    }
+    if (tid < 3 * SM_ROWS) {   // the three extra columns 128..130
+      const int r = tid / 3, c = SM_TILE_W + tid % 3;
+      const int gy = y0 + r - 1, gx2 = x0 + c - 1;
+      const float u = ((unsigned)gy < (unsigned)g.H && (unsigned)gx2 < (unsigned)g.W) ? __ldg(img + (long long)gy * g.W + gx2) : 0.f;
+      const act_t h = f_to_act(u);
+      tile(0, r, c) = h;
+      tile(1, r, c + 1) = h;
+    }
+  }
+  // filter fragments: b[nt][0] = taps (2t, 2t+1), b[nt][1] = taps (2t+8, 2t+9) of channel 8 nt + g
+  uint32_t bw[NT][2];
+  float bias[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int ch = nt * 8 + gq;
+    bw[nt][0] = pack2(__ldg(w_dev + (2 * t) * 16 + ch), __ldg(w_dev + (2 * t + 1) * 16 + ch));
+    bw[nt][1] = pack2(__ldg(w_dev + (2 * t + 8) * 16 + ch), __ldg(w_dev + (2 * t + 9) * 16 + ch));
+    bias[nt][0] = __ldg(bias_dev + nt * 8 + 2 * t);
+    bias[nt][1] = __ldg(bias_dev + nt * 8 + 2 * t + 1);
+  }
+  __syncthreads();
+  if (y0 >= g.H) return;
+  const int ky0 = t >> 1, kx0 = 2 * (t & 1);
+  const int copy = gq & 1;                           // parity of the tile column of this lane's pairs
+  const int pl0 = warp * 32 + gq;                    // tile-local pixel column of accumulator row g of pixel tile 0
+  // byte address of A register 0 for tile row 0; + 32 B per pixel tile, + 16 B for rows g + 8, + 2 tile rows for taps 8..15
+  uint32_t ta = (uint32_t)__cvta_generic_to_shared(&tile(copy, ky0, pl0 + kx0 + copy));
+  constexpr uint32_t ROWB = SM_STRIDE * 2;
+  const int xa0 = x0 + pl0;
+  bool live[2][2], mate[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int x = xa0 + mt * 16 + h * 8;
+      live[mt][h] = x < g.W;
+      mate[mt][h] = (x ^ 1) < g.W;                    // the other column of the 2x2 window exists
+    }
+  act_t* pp = pool + gp.pos(n, y0 >> 1, xa0 >> 1) * 8 + 2 * t;   // + 64 halves per pixel tile, + 32 for rows g + 8
+  act_t* po = FULL ? out + g.pos(n, y0, xa0) * 8 + 2 * t : nullptr;
+  const int rows = min(STEM_ROWS, g.H - y0);
+  for (int r = 0; r < rows; r += 2, ta += 2 * ROWB, pp += (long long)gp.Wp * 8) {
+    const bool two = r + 1 < rows;
+    uint32_t m[2][NT][2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      if (rr == 1 && !two) break;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t base = ta + rr * ROWB + mt * 32;
+        uint32_t a[4];
+        a[0] = lds32(base);
+        a[1] = lds32(base + 16);
+        a[2] = lds32(base + 2 * ROWB);
+        a[3] = lds32(base + 2 * ROWB + 16);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          float d[4];
+          mma_16816(d, a, bw[nt], bias[nt]);
+          uint32_t c0 = pack2_raw(d[0], d[1]), c1 = pack2_raw(d[2], d[3]);
+          if (FULL) {
+            c0 = finish2_relu(c0);
+            c1 = finish2_relu(c1);
+            act_t* o = po + ((long long)nt * out_plane + (long long)rr * g.Wp + mt * 16) * 8;
+            if (live[mt][0]) *reinterpret_cast<uint32_t*>(o) = c0;
+            if (live[mt][1]) *reinterpret_cast<uint32_t*>(o + 64) = c1;
+          }
+          if (rr == 0) {
+            m[mt][nt][0] = c0;
+            m[mt][nt][1] = c1;
+          } else {
+            m[mt][nt][0] = hmax2_u32(m[mt][nt][0], c0);
+            m[mt][nt][1] = hmax2_u32(m[mt][nt][1], c1);
+          }
+        }
+      }
+    }
+    if (FULL) po += 2LL * g.Wp * 8;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v = m[mt][nt][h];
+          const uint32_t nb = __shfl_xor_sync(0xffffffffu, v, 4);   // the other column of the 2x2 window: g ^ 1
+          if (mate[mt][h]) v = hmax2_u32(v, nb);
+          if (!FULL) v = finish2_relu(v);
+          if (!(gq & 1) && live[mt][h])
+            *reinterpret_cast<uint32_t*>(pp + (long long)nt * pool_plane * 8 + mt * 64 + h * 32) = v;
+        }
   }
 }
 
@@ -575,8 +753,15 @@ __global__ void __launch_bounds__(256) k_unpack_nhwc(const act_t* __restrict__ i
 static inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 static inline long long npix(const Geo& g) { return (long long)g.N * g.H * g.W; }
 
+// ARU_STEM_FFMA=1 keeps the CUDA-core kernel for the pooled 4x4 stem (A/B comparisons)
+static bool stem_force_ffma() {
+  static const bool v = [] { const char* e = getenv("ARU_STEM_FFMA"); return e && e[0] == '1'; }();
+  return v;
+}
+
 cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, PV out_pre, const float* w_host,
-                             const float* bias_host, const Geo& g, int act, PV pool, const Geo* pool_geo, bool full) {
+                             const float* bias_host, const Geo& g, int act, PV pool, const Geo* pool_geo, bool full,
+                             const float* w_dev16, const float* bias_dev16) {
   // w_host: the TF filter [ks][ks][1][C_out] (host memory), bias_host [C_out]; both travel in the kernel parameters
   const int cout = out.C;
   if (cout < 1 || cout > 16 || (ks != 3 && ks != 4) || g.H > 65535 || g.N > 65535) return cudaErrorInvalidValue;
@@ -589,6 +774,14 @@ cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, P
   const int cc = cout <= 8 ? 8 : (cout <= 12 ? 12 : 16);  // instantiated widths (padding channels have zero weights)
   if (pool.p) {   // conv + ReLU + 2x2 max-pool (full == false: the full-resolution tensor is not stored at all)
     if (act != 1 || out_pre.p || !pool_geo) return cudaErrorInvalidValue;
+    if (ks == 4 && w_dev16 && bias_dev16 && !stem_force_ffma()) {   // the 16 taps are one K = 16 tensor-core step
+      const bool two = cout > 8;
+      if (two && full) k_conv_stem4_pool_mma<2, true><<<grid, 128, 0, st>>>(in, out.p, out.plane, pool.p, pool.plane, w_dev16, bias_dev16, g, *pool_geo);
+      else if (two) k_conv_stem4_pool_mma<2, false><<<grid, 128, 0, st>>>(in, out.p, out.plane, pool.p, pool.plane, w_dev16, bias_dev16, g, *pool_geo);
+      else if (full) k_conv_stem4_pool_mma<1, true><<<grid, 128, 0, st>>>(in, out.p, out.plane, pool.p, pool.plane, w_dev16, bias_dev16, g, *pool_geo);
+      else k_conv_stem4_pool_mma<1, false><<<grid, 128, 0, st>>>(in, out.p, out.plane, pool.p, pool.plane, w_dev16, bias_dev16, g, *pool_geo);
+      return cudaGetLastError();
+    }
 #define ARU_STEM_POOL(KK, CC)                                                                                          \
   if (ks == KK && cc == CC) {                                                                                          \
     if (full) k_conv_stem_pool<KK, CC, true><<<grid, 128, 0, st>>>(in, out.p, out.plane, pool.p, pool.plane, sw, g, *pool_geo); \
