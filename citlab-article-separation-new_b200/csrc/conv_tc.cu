@@ -529,55 +529,64 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
               walk_adv(c2, r2, g2, a.dc128, a.dr128, a.Wp, a.Hp);
             }
           }
-          uint4 rr[T];
+          // Residual vectors travel in a ring PD output chunks deep, filled before the accumulators are waited for and
+          // refilled right after each use: with one load in flight per lane the epilogue of a T = 1 pass (C_out = 64:
+          // eight chunks) was a chain of eight exposed memory latencies (measured 91 us against 52 us without residual).
+          constexpr int PD = T == 1 ? 4 : 2;
+          uint4 rr[PD][T];
           if (has_res) {
 #pragma unroll
-            for (int t = 0; t < T; ++t) rr[t] = __ldg(reinterpret_cast<const uint4*>(a.res + pt[t]));
+            for (int d = 0; d < PD; ++d)
+              if (d < a.cout_chunks) {
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                  rr[d][t] = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)d * a.res_plane * 8 + pt[t]));
+              }
           }
           mbar_wait(s_tfull + 8 * stage, stage_par, a.err_flag, 4);
           __syncwarp();
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
 #pragma unroll 1
-          for (int c = 0; c < a.cout_chunks; ++c) {
-            uint32_t v[T][8];
+          for (int c0 = 0; c0 < a.cout_chunks; c0 += PD) {
 #pragma unroll
-            for (int t = 0; t < T; ++t) tmem_ld8(taddr + (uint32_t)(t * a.npad + c * 8), v[t]);
-            uint4 rn[T];
-            if (has_res && c + 1 < a.cout_chunks) {
+            for (int d = 0; d < PD; ++d) {
+              const int c = c0 + d;
+              if (c >= a.cout_chunks) break;
+              uint32_t v[T][8];
 #pragma unroll
-              for (int t = 0; t < T; ++t)
-                rn[t] = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)(c + 1) * a.res_plane * 8 + pt[t]));
-            }
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
-            tmem_ld_wait();
-            if (c == a.cout_chunks - 1) {  // last TMEM read of this stage: hand the accumulators back
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
-            }
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-              float acc[8];
-              acc[0] = __uint_as_float(v[t][0]) + b0.x; acc[1] = __uint_as_float(v[t][1]) + b0.y;
-              acc[2] = __uint_as_float(v[t][2]) + b0.z; acc[3] = __uint_as_float(v[t][3]) + b0.w;
-              acc[4] = __uint_as_float(v[t][4]) + b1.x; acc[5] = __uint_as_float(v[t][5]) + b1.y;
-              acc[6] = __uint_as_float(v[t][6]) + b1.z; acc[7] = __uint_as_float(v[t][7]) + b1.w;
-              if (has_res) {
-                float r[8];
-                unpack8(rr[t], r);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += r[j];
+              for (int t = 0; t < T; ++t) tmem_ld8(taddr + (uint32_t)(t * a.npad + c * 8), v[t]);
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
+              tmem_ld_wait();
+              if (c == a.cout_chunks - 1) {  // last TMEM read of this stage: hand the accumulators back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
               }
-              if (has_pre)
-                *reinterpret_cast<uint4*>(a.out_pre + (long long)c * a.pre_plane * 8 + pt[t]) = pack8_fin<false>(acc, vt[t]);
-              const uint4 o = relu ? pack8_fin<true>(acc, vt[t]) : pack8_fin<false>(acc, vt[t]);
-              *reinterpret_cast<uint4*>(a.out + (long long)c * a.out_plane * 8 + pt[t]) = o;
-            }
-            if (has_res) {
 #pragma unroll
-              for (int t = 0; t < T; ++t) rr[t] = rn[t];
+              for (int t = 0; t < T; ++t) {
+                float acc[8];
+                acc[0] = __uint_as_float(v[t][0]) + b0.x; acc[1] = __uint_as_float(v[t][1]) + b0.y;
+                acc[2] = __uint_as_float(v[t][2]) + b0.z; acc[3] = __uint_as_float(v[t][3]) + b0.w;
+                acc[4] = __uint_as_float(v[t][4]) + b1.x; acc[5] = __uint_as_float(v[t][5]) + b1.y;
+                acc[6] = __uint_as_float(v[t][6]) + b1.z; acc[7] = __uint_as_float(v[t][7]) + b1.w;
+                if (has_res) {
+                  float r[8];
+                  unpack8(rr[d][t], r);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[j] += r[j];
+                }
+                if (has_pre)
+                  *reinterpret_cast<uint4*>(a.out_pre + (long long)c * a.pre_plane * 8 + pt[t]) = pack8_fin<false>(acc, vt[t]);
+                const uint4 o = relu ? pack8_fin<true>(acc, vt[t]) : pack8_fin<false>(acc, vt[t]);
+                *reinterpret_cast<uint4*>(a.out + (long long)c * a.out_plane * 8 + pt[t]) = o;
+              }
+              if (has_res && c + PD < a.cout_chunks) {
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                  rr[d][t] = __ldg(reinterpret_cast<const uint4*>(a.res + (long long)(c + PD) * a.res_plane * 8 + pt[t]));
+              }
             }
           }
           walk_adv(col, rin, pg, a.dcS, a.drS, a.Wp, a.Hp);

@@ -591,8 +591,10 @@ constexpr int COMBINE_ROWS = 16;
 // One thread = one output column walking 16 rows; grid = (ceil(W/128), ceil(H/16), N).  Column-wise source indices
 // are computed once per thread, row-wise ones are shifts (the upsample factors of the ARU topology are powers of two;
 // other factors take the division).  Templated on the number of scales so the per-scale state lives in registers.
-template <int A>
-__global__ void __launch_bounds__(128) k_combine(const __grid_constant__ CombineArgs a) {
+// FAST: one output plane and exactly one full-resolution detection map (index kf) - the ARU topology; its 16-byte
+// vectors are fetched three rows ahead so that four loads per thread are in flight (the kernel is latency bound otherwise).
+template <int A, bool FAST>
+__global__ void __launch_bounds__(128) k_combine(const __grid_constant__ CombineArgs a, int kf) {
   const Geo& g = a.geo;
   const int n = blockIdx.z, y0 = blockIdx.y * COMBINE_ROWS, x = blockIdx.x * 128 + threadIdx.x;
   if (x >= g.W) return;
@@ -605,35 +607,84 @@ __global__ void __launch_bounds__(128) k_combine(const __grid_constant__ Combine
   }
   const int y1 = min(y0 + COMBINE_ROWS, g.H);
   long long p = g.pos(n, y0, x);
+  // Upsampled sources change only every `up` rows: the attention logits (and with them the softmax weights) and the
+  // channel sums of the low-resolution detection maps are kept in registers and refreshed when their source row moves
+  // (the test is uniform over the block: all threads of a block share y).
+  float raw[A], wgt[A], lowsum[A];
+  int att_row[A], det_row[A];
+#pragma unroll
+  for (int k = 0; k < A; ++k) { att_row[k] = -1; det_row[k] = -1; raw[k] = 0.f; wgt[k] = 0.f; lowsum[k] = 0.f; }
+  const uint4* full = nullptr;   // FAST: the full-resolution detection vector of (row y, this column)
+  uint4 ahead[3];
+  if (FAST) {
+    full = reinterpret_cast<const uint4*>(a.det[kf]) + p;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ahead[j] = (y0 + j < y1) ? __ldg(full + (long long)j * g.Wp) : make_uint4(0u, 0u, 0u, 0u);
+  }
   for (int y = y0; y < y1; ++y, p += g.Wp) {
-    float s[A];
-    float m = -INFINITY;
+    uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+    if (FAST) {
+      cur = ahead[0];
+      ahead[0] = ahead[1];
+      ahead[1] = ahead[2];
+      if (y + 3 < y1) ahead[2] = __ldg(full + 3LL * g.Wp);
+      full += g.Wp;
+    }
+    bool moved = false;
 #pragma unroll
     for (int k = 0; k < A; ++k) {
-      s[k] = __ldg(att_col[k] + (long long)div_up(y + a.att_oy[k], a.att_up[k], a.att_sh[k]) * a.att_w[k]);
-      m = fmaxf(m, s[k]);
+      const int r = div_up(y + a.att_oy[k], a.att_up[k], a.att_sh[k]);
+      if (r != att_row[k]) {
+        att_row[k] = r;
+        raw[k] = __ldg(att_col[k] + (long long)r * a.att_w[k]);
+        moved = true;
+      }
     }
-    float den = 0.f;
+    if (moved) {
+      float m = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < A; ++k) {
-      s[k] = __expf(s[k] - m);
-      den += s[k];
+      for (int k = 0; k < A; ++k) m = fmaxf(m, raw[k]);
+      float den = 0.f;
+#pragma unroll
+      for (int k = 0; k < A; ++k) {
+        wgt[k] = __expf(raw[k] - m);
+        den += wgt[k];
+      }
+      const float inv = 1.f / den;
+#pragma unroll
+      for (int k = 0; k < A; ++k) wgt[k] *= inv;
     }
-    const float inv = 1.f / den;
     // low-resolution detection maps: channel sum of the source pixel (the ones-filter quirk), shared by all chunks
     float low = 0.f;
 #pragma unroll
     for (int k = 0; k < A; ++k) {
       if (a.det_up[k] != 1) {
-        const long long q = det_col[k] + (long long)div_up(y + a.det_oy[k], a.det_up[k], a.det_sh[k]) * a.det_geo[k].Wp;
-        float sum = 0.f;
-        for (int c = 0; c < a.det_chunks[k]; ++c) {
-          float d[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (c * a.det_plane[k] + q) * 8)), d);
-          sum += ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
+        const int r = div_up(y + a.det_oy[k], a.det_up[k], a.det_sh[k]);
+        if (r != det_row[k]) {
+          det_row[k] = r;
+          const long long q = det_col[k] + (long long)r * a.det_geo[k].Wp;
+          float sum = 0.f;
+          for (int c = 0; c < a.det_chunks[k]; ++c) {
+            float d[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (c * a.det_plane[k] + q) * 8)), d);
+            sum += ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
+          }
+          lowsum[k] = sum;
         }
-        low = fmaf(sum, s[k] * inv, low);
+        low = fmaf(lowsum[k], wgt[k], low);
       }
+    }
+    if (FAST) {
+      float acc[8], d[8];
+      unpack8(cur, d);
+      float wk = 0.f;
+#pragma unroll
+      for (int k = 0; k < A; ++k)
+        if (k == kf) wk = wgt[k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], wk, low);
+      *reinterpret_cast<uint4*>(a.out + p * 8) = pack8_fin<false>(acc, true);
+      continue;
     }
     for (int oc = 0; oc < a.out_chunks; ++oc) {
       float acc[8];
@@ -642,11 +693,10 @@ __global__ void __launch_bounds__(128) k_combine(const __grid_constant__ Combine
 #pragma unroll
       for (int k = 0; k < A; ++k) {
         if (a.det_up[k] == 1) {
-          const float wk = s[k] * inv;
           float d[8];
           unpack8(__ldg(reinterpret_cast<const uint4*>(a.det[k] + (oc * a.det_plane[k] + p) * 8)), d);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], wk, acc[j]);
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(d[j], wgt[k], acc[j]);
         }
       }
       *reinterpret_cast<uint4*>(a.out + (oc * a.out_plane + p) * 8) = pack8_fin<false>(acc, true);
@@ -872,16 +922,23 @@ cudaError_t launch_combine(cudaStream_t st, const CombineArgs& a_in) {
     a.det_sh[k] = log2_or_neg(a.det_up[k]);
   }
   const dim3 grid((unsigned)cdiv(a.geo.W, 128), (unsigned)cdiv(a.geo.H, COMBINE_ROWS), (unsigned)a.geo.N);
+  int kf = -1, n_full = 0;
+  for (int k = 0; k < a.A; ++k)
+    if (a.det_up[k] == 1) { kf = k; ++n_full; }
+  const bool fast = a.out_chunks == 1 && n_full == 1;
+#define ARU_COMBINE(AA)                                                    \
+  case AA:                                                                 \
+    if (fast) k_combine<AA, true><<<grid, 128, 0, st>>>(a, kf);            \
+    else k_combine<AA, false><<<grid, 128, 0, st>>>(a, kf);                \
+    break;
   switch (a.A) {
-    case 1: k_combine<1><<<grid, 128, 0, st>>>(a); break;
-    case 2: k_combine<2><<<grid, 128, 0, st>>>(a); break;
-    case 3: k_combine<3><<<grid, 128, 0, st>>>(a); break;
-    case 4: k_combine<4><<<grid, 128, 0, st>>>(a); break;
-    case 5: k_combine<5><<<grid, 128, 0, st>>>(a); break;
-    case 6: k_combine<6><<<grid, 128, 0, st>>>(a); break;
-    case 7: k_combine<7><<<grid, 128, 0, st>>>(a); break;
-    default: k_combine<8><<<grid, 128, 0, st>>>(a); break;
+    ARU_COMBINE(1) ARU_COMBINE(2) ARU_COMBINE(3) ARU_COMBINE(4) ARU_COMBINE(5) ARU_COMBINE(6) ARU_COMBINE(7)
+    default:
+      if (fast) k_combine<8, true><<<grid, 128, 0, st>>>(a, kf);
+      else k_combine<8, false><<<grid, 128, 0, st>>>(a, kf);
+      break;
   }
+#undef ARU_COMBINE
   return cudaGetLastError();
 }
 
