@@ -818,6 +818,9 @@ struct HostIO {
   uint8_t* out_v = nullptr;        // uint8 [n,h,w] vertical separators
   float thr = 0.f;                 // float threshold (aru_forward) ...
   int cut = -1;                    // ... or the integer cut of the double threshold (>= 0)
+  const int* boxes_dev = nullptr;  // device [n_boxes][5] = page, y0, y1, x0, x1 (aru_heading_pages)
+  int n_boxes = 0;
+  unsigned long long* sums_dev = nullptr;
 };
 
 // Host-buffer forward: micro-batches, double-buffered device staging, copies on their own streams.
@@ -852,7 +855,8 @@ int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
     if (rc) return rc;
     e->cur = p;
     if (std::find(used.begin(), used.end(), p) == used.end()) used.push_back(p);
-    rc = ensure_quant(e, p, io.out_u8 != nullptr, want_mask);
+    const bool want_u8 = io.out_u8 != nullptr || io.n_boxes > 0;
+    rc = ensure_quant(e, p, want_u8, want_mask);
     if (rc) return rc;
     if (io.in_u8 && (rc = ensure_pages(e, p, io.channels))) return rc;
     if (want_post && (rc = ensure_post(e, p))) return rc;
@@ -877,10 +881,14 @@ int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
     }
     rc = enqueue_forward(e, p, par, e->s_comp);
     if (rc) return rc;
-    if (io.out_u8 || want_mask) {
-      cudaError_t err = launch_quantize(e->s_comp, p->out_dev[par], io.out_u8 ? p->u8_dev[par] : nullptr,
+    if (want_u8 || want_mask) {
+      cudaError_t err = launch_quantize(e->s_comp, p->out_dev[par], want_u8 ? p->u8_dev[par] : nullptr,
                                         want_mask ? p->mask_dev[par] : nullptr, (long long)cnt * page_px, C, io.thr, io.cut);
       if (err != cudaSuccess) return fail(e, ARU_ECUDA, "quantize launch: %s", cudaGetErrorString(err));
+    }
+    if (io.n_boxes > 0) {
+      cudaError_t err = launch_box_sums(e->s_comp, p->u8_dev[par], cnt, h, w, C, i0, io.boxes_dev, io.n_boxes, io.sums_dev);
+      if (err != cudaSuccess) return fail(e, ARU_ECUDA, "box_sums launch: %s", cudaGetErrorString(err));
     }
     if (want_post) {
       cudaError_t err = launch_separator_post(e->s_comp, p->mask_dev[par], cnt, h, w, cc_min_size((long long)page_px), k1,
@@ -1161,6 +1169,79 @@ int aru_separator_pages(aru_engine* e, const uint8_t* pages, int channels, int n
   io.out_v = vertical;
   io.cut = mask_cut(thr);
   return forward_host(e, io, n, h, w);
+}
+
+static int check_boxes(aru_engine* e, const int32_t* boxes, int n_boxes, int n, int h, int w) {
+  for (int b = 0; b < n_boxes; ++b) {
+    const int32_t* q = boxes + 5 * b;
+    if (q[0] < 0 || q[0] >= n || q[1] < 0 || q[2] > h || q[3] < 0 || q[4] > w)
+      return fail(e, ARU_EINVAL, "box %d = (page %d, rows [%d,%d), columns [%d,%d)) leaves the %d pages of %dx%d", b, q[0],
+                  q[1], q[2], q[3], q[4], n, h, w);
+  }
+  return ARU_OK;
+}
+
+int aru_heading_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, const int32_t* boxes,
+                      int n_boxes, uint64_t* sums, uint8_t* out_u8) {
+  if (!e || !pages || n <= 0 || h <= 0 || w <= 0 || (channels != 1 && channels != 3) || n_boxes < 0 ||
+      (n_boxes > 0 && (!boxes || !sums)))
+    return e ? fail(e, ARU_EINVAL, "aru_heading_pages: bad argument") : ARU_EINVAL;
+  int rc = check_boxes(e, boxes, n_boxes, n, h, w);
+  if (rc) return rc;
+  CU(e, cudaSetDevice(e->device));
+  int* boxes_dev = nullptr;
+  unsigned long long* sums_dev = nullptr;
+  if (n_boxes > 0) {
+    if (cudaMalloc((void**)&boxes_dev, (size_t)n_boxes * 5 * sizeof(int)) || cudaMalloc((void**)&sums_dev, (size_t)n_boxes * 8)) {
+      cudaFree(boxes_dev);
+      return fail(e, ARU_ENOMEM, "aru_heading_pages: device allocation failed");
+    }
+    cudaMemcpyAsync(boxes_dev, boxes, (size_t)n_boxes * 5 * sizeof(int), cudaMemcpyHostToDevice, e->s_comp);
+  }
+  HostIO io;
+  io.in_u8 = pages;
+  io.channels = channels;
+  io.out_u8 = out_u8;
+  io.boxes_dev = boxes_dev;
+  io.n_boxes = n_boxes;
+  io.sums_dev = sums_dev;
+  rc = forward_host(e, io, n, h, w);
+  if (rc == ARU_OK && n_boxes > 0) {
+    cudaError_t err = cudaMemcpy(sums, sums_dev, (size_t)n_boxes * 8, cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) rc = fail(e, ARU_ECUDA, "aru_heading_pages: %s", cudaGetErrorString(err));
+  }
+  cudaFree(boxes_dev);
+  cudaFree(sums_dev);
+  return rc;
+}
+
+int aru_box_sums(aru_engine* e, const uint8_t* u8, int n, int h, int w, int c, const int32_t* boxes, int n_boxes,
+                 uint64_t* sums) {
+  if (!e || !u8 || n <= 0 || h <= 0 || w <= 0 || c <= 0 || n_boxes < 0 || (n_boxes > 0 && (!boxes || !sums)))
+    return e ? fail(e, ARU_EINVAL, "aru_box_sums: bad argument") : ARU_EINVAL;
+  if (n_boxes == 0) return ARU_OK;
+  int rc = check_boxes(e, boxes, n_boxes, n, h, w);
+  if (rc) return rc;
+  CU(e, cudaSetDevice(e->device));
+  const size_t bytes = (size_t)n * h * w * c;
+  uint8_t* d_u8 = nullptr;
+  int* boxes_dev = nullptr;
+  unsigned long long* sums_dev = nullptr;
+  auto cleanup = [&]() { cudaFree(d_u8); cudaFree(boxes_dev); cudaFree(sums_dev); };
+  if (cudaMalloc((void**)&d_u8, bytes) || cudaMalloc((void**)&boxes_dev, (size_t)n_boxes * 5 * sizeof(int)) ||
+      cudaMalloc((void**)&sums_dev, (size_t)n_boxes * 8)) {
+    cleanup();
+    return fail(e, ARU_ENOMEM, "aru_box_sums: device allocation failed");
+  }
+  cudaError_t err = cudaMemcpyAsync(d_u8, u8, bytes, cudaMemcpyHostToDevice, e->s_comp);
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(boxes_dev, boxes, (size_t)n_boxes * 5 * sizeof(int), cudaMemcpyHostToDevice, e->s_comp);
+  if (err == cudaSuccess) err = launch_box_sums(e->s_comp, d_u8, n, h, w, c, 0, boxes_dev, n_boxes, sums_dev);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(sums, sums_dev, (size_t)n_boxes * 8, cudaMemcpyDeviceToHost, e->s_comp);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+  cleanup();
+  if (err != cudaSuccess) return fail(e, ARU_ECUDA, "aru_box_sums: %s", cudaGetErrorString(err));
+  return ARU_OK;
 }
 
 int aru_separator_post(aru_engine* e, const uint8_t* mask, int n, int h, int w, uint8_t* horizontal, uint8_t* vertical) {

@@ -65,6 +65,10 @@ size_t separator_post_scratch_bytes(int n, int h, int w);
 int separator_post_launches();
 cudaError_t launch_separator_post(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int min_size, int k_h1,
                                   int k_v, int k_h2, void* scratch, uint8_t* out_h, uint8_t* out_v);
+// sums[b] = sum of channel 0 of the uint8 map over box b = (page, y0, y1, x0, x1), for the boxes whose page lies in
+// [page0, page0 + n); u8 holds those n pages as [n][h][w][c]
+cudaError_t launch_box_sums(cudaStream_t st, const uint8_t* u8, int n, int h, int w, int c, int page0, const int* boxes,
+                            int n_boxes, unsigned long long* sums);
 cudaError_t launch_open_rect(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int kw, int kh, void* scratch,
                              uint8_t* out);
 // debug read-back: chunk-planar view -> dense float32 NHWC [N][H][W][C]

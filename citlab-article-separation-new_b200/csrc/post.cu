@@ -376,6 +376,50 @@ __global__ void __launch_bounds__(256) k_bits_unpack(const uint32_t* __restrict_
   }
 }
 
+// ---- f3: per-text-line sums of the heading map ----------------------------------------------------------------------
+// HeadingNetPostProcessor.get_net_prob_for_text_line (heading_net_post_processor.py:247-270) sums net_output[ya:yb, xa:xb]
+// (channel 0 of the uint8 map / 255) inside the bounding box of every text line.  One block per box; the sum is an
+// exact integer (the caller divides by 255 and by the box area), so nothing but a few numbers per page leaves the GPU.
+// boxes: [n_boxes][5] = page, y0, y1, x0, x1 (half open, already clipped to the page); boxes of pages outside
+// [page0, page0 + n) are left to the micro-batch that holds their page.
+__global__ void __launch_bounds__(256) k_box_sums(const uint8_t* __restrict__ u8, int n, int H, int W, int C, int page0,
+                                                  const int* __restrict__ boxes, int n_boxes,
+                                                  unsigned long long* __restrict__ sums) {
+  const int b = blockIdx.x;
+  if (b >= n_boxes) return;
+  const int pg = boxes[b * 5] - page0;
+  if (pg < 0 || pg >= n) return;
+  const int y0 = boxes[b * 5 + 1], y1 = boxes[b * 5 + 2], x0 = boxes[b * 5 + 3], x1 = boxes[b * 5 + 4];
+  unsigned long long acc = 0;
+  const int bw = x1 - x0;
+  if (bw > 0 && y1 > y0) {
+    // threads cover the box row-major in chunks of 256 pixels: consecutive lanes read consecutive pixels of a row
+    const long long total = (long long)bw * (y1 - y0);
+    for (long long i = threadIdx.x; i < total; i += 256) {
+      const int r = (int)(i / bw), c = (int)(i - (long long)r * bw);
+      acc += u8[(((long long)pg * H + y0 + r) * W + x0 + c) * C];
+    }
+  }
+  __shared__ unsigned long long part[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i];
+    sums[b] = t;
+  }
+}
+
+cudaError_t launch_box_sums(cudaStream_t st, const uint8_t* u8, int n, int h, int w, int c, int page0, const int* boxes,
+                            int n_boxes, unsigned long long* sums) {
+  if (n_boxes <= 0) return cudaSuccess;
+  k_box_sums<<<n_boxes, 256, 0, st>>>(u8, n, h, w, c, page0, boxes, n_boxes, sums);
+  return cudaGetLastError();
+}
+
 static inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
 
 static void bits_pack(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int Wd, uint32_t* bits) {

@@ -28,7 +28,8 @@ EXPORTS = [
     "aru_abi_version", "aru_device_count", "aru_create", "aru_destroy", "aru_set_option", "aru_num_classes",
     "aru_plan", "aru_forward", "aru_forward_device", "aru_sync", "aru_launches_per_forward", "aru_read_buffer",
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
-    "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input",
+    "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
+    "aru_box_sums",
 ]
 
 _lib = None
@@ -69,6 +70,8 @@ def load_library() -> ctypes.CDLL:
         lib.aru_separator_post.argtypes = [vp, vp, i32, i32, i32, vp, vp]
         lib.aru_open_rect.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
         lib.aru_pages_to_input.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+        lib.aru_heading_pages.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]
+        lib.aru_box_sums.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp]
         lib.aru_sync.argtypes = [vp]
         lib.aru_launches_per_forward.argtypes = [vp]
         lib.aru_read_buffer.argtypes = [vp, i32, i32, fp, sz]
@@ -281,6 +284,48 @@ class Engine:
         self._check(self.lib.aru_separator_post(self.handle, ctypes.c_void_p(m.ctypes.data), n, h, w,
                                                 ctypes.c_void_p(hor.ctypes.data), ctypes.c_void_p(ver.ctypes.data)))
         return (hor[0], ver[0]) if single else (hor, ver)
+
+    @staticmethod
+    def clip_boxes(boxes, h: int, w: int) -> np.ndarray:
+        """[(page, ya, yb, xa, xb)] with the reference's numpy-slice semantics (``net_output[ya:yb, xa:xb]``,
+        heading_net_post_processor.py:266: negative indices count from the end, ranges are clipped, an inverted range is
+        empty) -> int32 [n_boxes, 5] half-open boxes inside the page."""
+        out = np.zeros((len(boxes), 5), np.int32)
+        for i, (pg, ya, yb, xa, xb) in enumerate(boxes):
+            y0, y1, _ = slice(int(ya), int(yb)).indices(h)
+            x0, x1, _ = slice(int(xa), int(xb)).indices(w)
+            out[i] = (int(pg), y0, max(y0, y1), x0, max(x0, x1))
+        return out
+
+    def heading_pages(self, pages: np.ndarray, boxes, want_u8: bool = False):
+        """One iteration of ``HeadingNetPostProcessor.run`` up to the network feature of every text line
+        (heading_net_post_processor.py:280-291, 247-270): colour step, net, ``uint8(p*255)`` and the sum of channel 0 over
+        ``net_output[ya:yb, xa:xb]`` for every box ``(page, ya, yb, xa, xb)`` - all on the device.
+        Returns (sums uint64 [n_boxes], clipped boxes int32 [n_boxes,5][, u8]); the reference's
+        ``get_net_prob_for_text_line`` value is ``sums / 255 / (bounding_box.width * bounding_box.height)``."""
+        x, n, h, w, ch = self._as_pages(pages)
+        x = np.ascontiguousarray(x)
+        bx = self.clip_boxes(boxes, h, w)
+        sums = np.zeros(len(bx), np.uint64)
+        u8 = pinned_empty((n, h, w, self.n_class), np.uint8) if want_u8 else None
+        self._check(self.lib.aru_heading_pages(self.handle, ctypes.c_void_p(x.ctypes.data), ch, n, h, w,
+                                               ctypes.c_void_p(bx.ctypes.data), len(bx), ctypes.c_void_p(sums.ctypes.data),
+                                               ctypes.c_void_p(u8.ctypes.data) if u8 is not None else None))
+        return (sums, bx, u8) if want_u8 else (sums, bx)
+
+    def box_sums(self, u8: np.ndarray, boxes) -> np.ndarray:
+        """Sum of channel 0 of a host uint8 map [N,H,W,C] (or [H,W,C] / [H,W]) over numpy-slice boxes."""
+        m = np.ascontiguousarray(u8, dtype=np.uint8)
+        if m.ndim == 2:
+            m = m[None, :, :, None]
+        elif m.ndim == 3:
+            m = m[None]
+        n, h, w, c = m.shape
+        bx = self.clip_boxes(boxes, h, w)
+        sums = np.zeros(len(bx), np.uint64)
+        self._check(self.lib.aru_box_sums(self.handle, ctypes.c_void_p(m.ctypes.data), n, h, w, c,
+                                          ctypes.c_void_p(bx.ctypes.data), len(bx), ctypes.c_void_p(sums.ctypes.data)))
+        return sums
 
     def open_rect(self, mask: np.ndarray, kw: int, kh: int) -> np.ndarray:
         """``cv2.morphologyEx(mask, MORPH_OPEN, RECT(kw, kh))`` for binary masks and kw == 1 or kh == 1."""

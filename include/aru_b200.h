@@ -153,6 +153,22 @@ int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, floa
 int aru_separator_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, double thr, float* out,
                         uint8_t* out_u8, uint8_t* out_mask, uint8_t* horizontal, uint8_t* vertical);
 
+/*
+ * aru_heading_pages = one iteration of HeadingNetPostProcessor.run up to the per-text-line network feature
+ *   (heading_net_post_processor.py:280-291 and get_net_prob_for_text_line :247-270): colour step, net,
+ *   np.array(net_output * 255, uint8), and for every text-line bounding box the sum of channel 0 of that uint8 map
+ *   over net_output[ya:yb, xa:xb].  The reference's value is sums[i] / 255 / (box width * box height).
+ *   boxes   int32 [n_boxes][5] = page index, y0, y1, x0, x1: half-open ranges already clipped to the page (numpy slice
+ *           semantics are the caller's, see Engine.heading_pages); a box outside its page is ARU_EINVAL
+ *   sums    uint64 [n_boxes] exact integer sums;  out_u8  uint8 [n,h,w,c] or NULL
+ */
+int aru_heading_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, const int32_t* boxes,
+                      int n_boxes, uint64_t* sums, uint8_t* out_u8);
+
+/* The box sums alone on a host uint8 map [n,h,w,c] (channel 0 is summed). */
+int aru_box_sums(aru_engine* e, const uint8_t* u8, int n, int h, int w, int c, const int32_t* boxes, int n_boxes,
+                 uint64_t* sums);
+
 /* post_process alone on n thresholded masks (uint8 [n,h,w], non-zero = foreground), host memory in and out. */
 int aru_separator_post(aru_engine* e, const uint8_t* mask, int n, int h, int w, uint8_t* horizontal, uint8_t* vertical);
 

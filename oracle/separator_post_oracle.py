@@ -1,12 +1,14 @@
 """CPU oracle (TEST INFRASTRUCTURE - never imported by the product path) for the integer steps either side
-of the ARU-Net forward pass (SURVEY.md section 8 rows a12, f1, f2).  numpy / scipy restatement of
+of the ARU-Net forward pass (SURVEY.md section 8 rows a12, f1, f2, f3).  numpy / scipy restatement of
 
   * ``load_and_scale_image``'s colour step: ``cv2.cvtColor(image, cv2.COLOR_BGR2GRAY) / 255.0``
     (net_post_processing_helper.py:28-33) -> ``bgr2gray_u8`` / ``u8_to_net_input``;
   * ``np.array(net_output * 255, dtype=np.uint8)`` and ``apply_threshold`` (separator_net_post_processor.py:147-149,
     net_post_processing_helper.py:75-78) -> ``quantize_u8`` / ``apply_threshold``;
   * ``RegionNetPostProcessor.apply_cc_analysis`` (region_net_post_processor_base.py:230-251) -> ``cc_size_filter``;
-  * ``SeparatorNetPostProcessor.post_process`` (separator_net_post_processor.py:25-99) -> ``separator_post_process``.
+  * ``SeparatorNetPostProcessor.post_process`` (separator_net_post_processor.py:25-99) -> ``separator_post_process``;
+  * ``HeadingNetPostProcessor.post_process`` / ``get_net_prob_for_text_line`` (heading_net_post_processor.py:203-209,
+    247-270) -> ``heading_post_process`` / ``box_sum_u8`` / ``net_prob_for_box``.
 
 The arithmetic of the reference lives in OpenCV (``cv2.connectedComponentsWithStats``, ``cv2.morphologyEx``,
 ``cv2.subtract``, ``cv2.cvtColor``); the OpenCV rules restated here:
@@ -140,3 +142,23 @@ def separator_post_process(mask: np.ndarray):
     horizontal = np.where(horizontal > vertical, horizontal - np.minimum(horizontal, vertical), 0).astype(np.uint8)
     horizontal = open_rect(horizontal, kh2, 1)
     return horizontal, vertical
+
+
+# ---- HeadingNetPostProcessor: network feature of a text line (head:203-209, 247-270) --------------------------------
+def heading_post_process(net_output_u8: np.ndarray) -> np.ndarray:
+    """``net_output[:, :, 0] / 255`` (head:209)."""
+    return net_output_u8[:, :, 0] / 255
+
+
+def box_sum_u8(net_output_u8: np.ndarray, ya: int, yb: int, xa: int, xb: int) -> int:
+    """Exact integer sum of channel 0 over ``[ya:yb, xa:xb]`` with numpy slice semantics (what the device returns)."""
+    ch0 = net_output_u8[:, :, 0] if net_output_u8.ndim == 3 else net_output_u8
+    return int(ch0[ya:yb, xa:xb].astype(np.int64).sum())
+
+
+def net_prob_for_box(net_output_u8: np.ndarray, x: int, y: int, width: int, height: int) -> float:
+    """``get_net_prob_for_text_line`` for a bounding box (x, y, width, height) (head:262-270):
+    ``np.sum((u8/255)[ya:yb, xa:xb]) / (width * height)``, evaluated as integer sum / 255 / area (equal to the reference's
+    float64 pairwise sum to ~1e-13 relative; the integer sum itself is exact)."""
+    s = box_sum_u8(net_output_u8, y, y + height, x, x + width)
+    return s / 255 / (width * height)

@@ -68,3 +68,50 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "post_colour_threshold.npz"), bgr=bgr, gray=gray,
                         net_input=grey_f.astype(np.float32), u8=u8, **thr_cases)
     print("post_colour_threshold: ok")
+
+    # heading mode: network feature of a text line (heading_net_post_processor.py:247-270), by the reference itself
+    from article_separation.image_segmentation.net_post_processing.heading_net_post_processor import \
+        HeadingNetPostProcessor
+    from python_util.geometry.polygon import Polygon
+
+    class _SurrP:
+        def __init__(self, xs, ys):
+            self.xs, self.ys = xs, ys
+
+        def to_polygon(self):
+            return Polygon(list(self.xs), list(self.ys), len(self.xs))
+
+    class _TextLine:
+        def __init__(self, xs, ys):
+            self.surr_p = _SurrP(xs, ys)
+
+    hp = object.__new__(HeadingNetPostProcessor)
+    rng = np.random.default_rng(11)
+    u8map = rng.integers(0, 256, size=(180, 260, 2), dtype=np.uint8)
+    post = hp.post_process(u8map)
+    sc = 0.5                                        # image is twice the size of the net output
+    polys, bboxes, probs = [], [], []
+    for i in range(40):
+        cx, cy = int(rng.integers(0, 520)), int(rng.integers(0, 360))
+        w2, h2 = int(rng.integers(4, 200)), int(rng.integers(4, 60))
+        xs = [cx - w2, cx + w2, cx + w2 + int(rng.integers(-3, 4)), cx - w2]
+        ys = [cy - h2, cy - h2 + int(rng.integers(-3, 4)), cy + h2, cy + h2]
+        if i % 7 == 0:                              # boxes hanging over the right / bottom border
+            xs = [x + 300 for x in xs]
+        xs = [max(0, x) for x in xs]                # PAGE coordinates are non-negative
+        ys = [max(0, y) for y in ys]
+        tl = _TextLine(xs, ys)
+        prob = hp.get_net_prob_for_text_line(post, tl, sc)
+        poly = tl.surr_p.to_polygon()
+        poly.rescale(sc)
+        bb = poly.get_bounding_box()
+        if bb.width * bb.height == 0 or not np.isfinite(prob):
+            continue
+        mine = O.net_prob_for_box(u8map, bb.x, bb.y, bb.width, bb.height)
+        assert abs(mine - prob) <= 1e-12 * max(1.0, abs(prob)), (i, mine, prob)
+        polys.append(xs + ys)
+        bboxes.append([bb.x, bb.y, bb.width, bb.height])
+        probs.append(prob)
+    np.savez_compressed(os.path.join(HERE, "post_heading_lines.npz"), u8=u8map, scale=sc, polygons=np.array(polys),
+                        bboxes=np.array(bboxes), probs=np.array(probs, np.float64))
+    print("post_heading_lines:", len(probs), "text lines")

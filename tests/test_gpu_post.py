@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-POST_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "post_*x*.npz")))
+POST_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "post_*_[0-9]*x[0-9]*.npz")))
 
 
 @pytest.fixture(scope="module")
@@ -164,3 +164,67 @@ def test_separator_pages_benchmark_size_properties(eng):
     assert np.array_equal(hor[0], h_ref) and np.array_equal(ver[0], v_ref)
     h2, v2 = eng.separator_post(np.ascontiguousarray(mask[:2]))
     assert np.array_equal(h2, hor[:2]) and np.array_equal(v2, ver[:2])
+
+
+def test_box_sums_match_reference_heading_feature(eng):
+    """Device box sums -> get_net_prob_for_text_line values produced by the reference itself (golden fixture)."""
+    z = np.load(os.path.join(GOLDEN, "post_heading_lines.npz"))
+    u8 = z["u8"]
+    boxes = [(0, int(y), int(y + h), int(x), int(x + w)) for x, y, w, h in z["bboxes"]]
+    sums = eng.box_sums(u8, boxes)
+    for s, (x, y, w, h), prob in zip(sums, z["bboxes"], z["probs"]):
+        got = int(s) / 255 / (int(w) * int(h))
+        assert abs(got - prob) <= 1e-12 * max(1.0, abs(prob))
+
+
+def test_box_sums_slice_semantics_and_batches(eng):
+    from oracle import separator_post_oracle as O
+    rng = np.random.default_rng(9)
+    u8 = rng.integers(0, 256, size=(3, 90, 140, 2), dtype=np.uint8)
+    boxes = [(0, 0, 90, 0, 140), (1, -5, 90, 0, 3), (2, 50, 40, 0, 10), (1, 80, 400, 130, 999), (2, 10, 11, 20, 21),
+             (0, 0, 0, 0, 0), (2, -200, 5, -300, 7)]
+    for _ in range(40):
+        ya, xa = int(rng.integers(0, 90)), int(rng.integers(0, 140))
+        boxes.append((int(rng.integers(0, 3)), ya, ya + int(rng.integers(0, 80)), xa, xa + int(rng.integers(0, 200))))
+    sums = eng.box_sums(u8, boxes)
+    for s, (pg, ya, yb, xa, xb) in zip(sums, boxes):
+        assert int(s) == O.box_sum_u8(u8[pg], ya, yb, xa, xb), (pg, ya, yb, xa, xb)
+
+
+def test_heading_pages_is_run_up_to_the_text_line_feature(eng):
+    """aru_heading_pages == colour step -> net -> uint8 -> per-box sums, micro-batched (boxes spread over the pages)."""
+    from aru_b200.engine import OPT_MICRO_BATCH
+    from aru_b200.synth import synth_page
+    from oracle import separator_post_oracle as O
+    n, h, w = 7, 192, 160
+    pages = np.stack([synth_page(h, w, seed=40 + i) for i in range(n)])
+    rng = np.random.default_rng(2)
+    boxes = []
+    for _ in range(60):
+        ya, xa = int(rng.integers(0, h)), int(rng.integers(0, w))
+        boxes.append((int(rng.integers(0, n)), ya, ya + int(rng.integers(1, 60)), xa, xa + int(rng.integers(1, 150))))
+    eng.set_option(OPT_MICRO_BATCH, 3)          # 7 pages in micro-batches of 3: boxes must find their page
+    try:
+        sums, clipped, u8 = eng.heading_pages(pages, boxes, want_u8=True)
+    finally:
+        eng.set_option(OPT_MICRO_BATCH, 0)
+    prob = eng.forward(O.u8_to_net_input(pages))
+    assert np.array_equal(u8, O.quantize_u8(prob))
+    for s, (pg, ya, yb, xa, xb) in zip(sums, boxes):
+        assert int(s) == O.box_sum_u8(u8[pg], ya, yb, xa, xb)
+    assert clipped.shape == (60, 5)
+    # BGR input with B = G = R gives the same luma, hence the same sums
+    sums3, _ = eng.heading_pages(np.stack([pages] * 3, axis=-1), boxes)
+    assert np.array_equal(sums3, sums)
+
+
+def test_heading_pages_rejects_boxes_outside_the_page(eng):
+    from aru_b200.engine import EngineError
+    import ctypes
+    pages = np.zeros((1, 64, 64), np.uint8)
+    bad = np.array([[0, 0, 65, 0, 10]], np.int32)
+    sums = np.zeros(1, np.uint64)
+    rc = eng.lib.aru_heading_pages(eng.handle, ctypes.c_void_p(pages.ctypes.data), 1, 1, 64, 64,
+                                   ctypes.c_void_p(bad.ctypes.data), 1, ctypes.c_void_p(sums.ctypes.data), None)
+    assert rc == 1   # ARU_EINVAL
+    del EngineError

@@ -10,7 +10,7 @@ import pytest
 from oracle import separator_post_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-POST_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "post_*x*.npz")))
+POST_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "post_*_[0-9]*x[0-9]*.npz")))
 
 
 def load_post_fixture(path):
@@ -102,3 +102,17 @@ def test_cc_filter_against_opencv():
             if stats[i, -1] >= min_size:
                 want[lab == i] = 255
         assert np.array_equal(O.cc_size_filter(img, min_size), want)
+
+
+def test_heading_box_feature_fixture():
+    """get_net_prob_for_text_line values computed by the reference itself (40 text lines, scaling factor 0.5)."""
+    z = np.load(os.path.join(GOLDEN, "post_heading_lines.npz"))
+    u8 = z["u8"]
+    assert len(z["probs"]) >= 30
+    for (x, y, w, h), prob in zip(z["bboxes"], z["probs"]):
+        mine = O.net_prob_for_box(u8, int(x), int(y), int(w), int(h))
+        assert abs(mine - prob) <= 1e-12 * max(1.0, abs(prob))
+    # numpy slice semantics of the box: clipped at the page border, negative start counts from the end
+    assert O.box_sum_u8(u8, 170, 400, 250, 999) == int(u8[170:, 250:, 0].astype(np.int64).sum())
+    assert O.box_sum_u8(u8, -5, 180, 0, 3) == int(u8[175:180, 0:3, 0].astype(np.int64).sum())
+    assert O.box_sum_u8(u8, 50, 40, 0, 10) == 0
