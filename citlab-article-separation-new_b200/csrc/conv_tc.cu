@@ -549,28 +549,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
 #pragma unroll 1
           for (int c0 = 0; c0 < a.cout_chunks; c0 += PD) {
+            // the TMEM reads of the whole group are issued together and waited for once
+            uint32_t v[PD][T][8];
+#pragma unroll
+            for (int d = 0; d < PD; ++d)
+              if (c0 + d < a.cout_chunks) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) tmem_ld8(taddr + (uint32_t)(t * a.npad + (c0 + d) * 8), v[d][t]);
+              }
+            tmem_ld_wait();
+            if (c0 + PD >= a.cout_chunks) {  // last TMEM read of this stage: hand the accumulators back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
+            }
 #pragma unroll
             for (int d = 0; d < PD; ++d) {
               const int c = c0 + d;
               if (c >= a.cout_chunks) break;
-              uint32_t v[T][8];
-#pragma unroll
-              for (int t = 0; t < T; ++t) tmem_ld8(taddr + (uint32_t)(t * a.npad + c * 8), v[t]);
               const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
-              tmem_ld_wait();
-              if (c == a.cout_chunks - 1) {  // last TMEM read of this stage: hand the accumulators back
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
-              }
 #pragma unroll
               for (int t = 0; t < T; ++t) {
                 float acc[8];
-                acc[0] = __uint_as_float(v[t][0]) + b0.x; acc[1] = __uint_as_float(v[t][1]) + b0.y;
-                acc[2] = __uint_as_float(v[t][2]) + b0.z; acc[3] = __uint_as_float(v[t][3]) + b0.w;
-                acc[4] = __uint_as_float(v[t][4]) + b1.x; acc[5] = __uint_as_float(v[t][5]) + b1.y;
-                acc[6] = __uint_as_float(v[t][6]) + b1.z; acc[7] = __uint_as_float(v[t][7]) + b1.w;
+                acc[0] = __uint_as_float(v[d][t][0]) + b0.x; acc[1] = __uint_as_float(v[d][t][1]) + b0.y;
+                acc[2] = __uint_as_float(v[d][t][2]) + b0.z; acc[3] = __uint_as_float(v[d][t][3]) + b0.w;
+                acc[4] = __uint_as_float(v[d][t][4]) + b1.x; acc[5] = __uint_as_float(v[d][t][5]) + b1.y;
+                acc[6] = __uint_as_float(v[d][t][6]) + b1.z; acc[7] = __uint_as_float(v[d][t][7]) + b1.w;
                 if (has_res) {
                   float r[8];
                   unpack8(rr[d][t], r);
@@ -609,26 +614,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
             const bool in_dom = ((unsigned)g2 < (unsigned)a.N) && (c2 >= 1) && (c2 <= a.W + 1) && (r2 >= 1) && (r2 <= a.H + 1);
             const int oy0 = 2 * (r2 - 1) - a.offy, ox0 = 2 * (c2 - 1) - a.offx;
             const long long po0 = (long long)a.lead_o + ((long long)g2 * a.Hpo + oy0 + 1) * a.Wpo + ox0 + 1;
-#pragma unroll 1
+            // the four output-parity classes of one channel chunk are read from TMEM together (one wait per chunk
+            // instead of one per class: the read-out was a chain of exposed TMEM latencies)
+            bool v[4];
+            long long po[4];
+#pragma unroll
             for (int cls = 0; cls < 4; ++cls) {
               const int oy = oy0 + (cls >> 1), ox = ox0 + (cls & 1);
-              const bool v = in_dom && (oy >= 0) && (oy < a.Ho) && (ox >= 0) && (ox < a.Wo);
-              const long long po = po0 + (long long)(cls >> 1) * a.Wpo + (cls & 1);
+              v[cls] = in_dom && (oy >= 0) && (oy < a.Ho) && (ox >= 0) && (ox < a.Wo);
+              po[cls] = po0 + (long long)(cls >> 1) * a.Wpo + (cls & 1);
+            }
 #pragma unroll 1
-              for (int c = 0; c < a.cls_chunks; ++c) {
-                uint32_t v8[8];
-                tmem_ld8(taddr + (uint32_t)(t * a.npad + (cls * a.cls_chunks + c) * 8), v8);
-                tmem_ld_wait();
-                if (t == T - 1 && cls == 3 && c == a.cls_chunks - 1) {
-                  tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
-                }
-                if (v) {
-                  float acc[8];
+            for (int c = 0; c < a.cls_chunks; ++c) {
+              uint32_t v8[4][8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(v8[j]) + s_bias[c * 8 + j];
-                  *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + po) * 8) =
+              for (int cls = 0; cls < 4; ++cls)
+                tmem_ld8(taddr + (uint32_t)(t * a.npad + (cls * a.cls_chunks + c) * 8), v8[cls]);
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
+              tmem_ld_wait();
+              if (t == T - 1 && c == a.cls_chunks - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
+              }
+#pragma unroll
+              for (int cls = 0; cls < 4; ++cls) {
+                if (v[cls]) {
+                  float acc[8];
+                  acc[0] = __uint_as_float(v8[cls][0]) + b0.x; acc[1] = __uint_as_float(v8[cls][1]) + b0.y;
+                  acc[2] = __uint_as_float(v8[cls][2]) + b0.z; acc[3] = __uint_as_float(v8[cls][3]) + b0.w;
+                  acc[4] = __uint_as_float(v8[cls][4]) + b1.x; acc[5] = __uint_as_float(v8[cls][5]) + b1.y;
+                  acc[6] = __uint_as_float(v8[cls][6]) + b1.z; acc[7] = __uint_as_float(v8[cls][7]) + b1.w;
+                  *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + po[cls]) * 8) =
                       a.act == 1 ? pack8_fin<true>(acc, true) : pack8_fin<false>(acc, true);
                 }
               }
