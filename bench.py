@@ -246,6 +246,9 @@ def run_b200(args):
     peaks, peaks_src = load_peaks()
     n = args.pages
     eng = Engine(synth_pb(NET), device=local)
+    if args.micro_batch:
+        from aru_b200.engine import OPT_MICRO_BATCH
+        eng.set_option(OPT_MICRO_BATCH, args.micro_batch)
     C = eng.n_class
     pages = make_pages(n, H, W)
     x_host = pinned_empty((n, H, W), np.float32)
@@ -322,7 +325,7 @@ def run_b200(args):
     line = None
     if rank == 0:
         import ctypes
-        mb_pages = min(n, max(1, min((40 << 20) // (H * W), 32)))
+        mb_pages = min(n, args.micro_batch) if args.micro_batch else min(n, max(1, min((80 << 20) // (H * W), 32)))
         classes, prof_ms, dom = class_rooflines(eng, mb_pages, H, W, peaks)
         n_mb = -(-n // mb_pages)
         gflop_page = 2.0 * aru_conv_macs(H, W) / 1e9
@@ -379,6 +382,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pages", type=int, default=PAGES_PER_STEP, help="pages per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--micro-batch", type=int, default=0, help="pages per pass through the net (0 = the engine's choice)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
