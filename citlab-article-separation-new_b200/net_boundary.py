@@ -133,8 +133,31 @@ def apply_threshold(net_output, threshold):
     return np.array((net_output > threshold) * 255, dtype=np.uint8)
 
 
-def install():
-    """Make ``import article_separation....net_post_processing_helper`` resolve to this module."""
+def separator_post_process(self, net_output):
+    """Drop-in for ``SeparatorNetPostProcessor.post_process`` (separator_net_post_processor.py:25-99): the component
+    size filter, the three rectangular openings and the subtract run on the GPU (csrc/post.cu, bit-exact against the
+    reference).  ``self`` is the post-processor (its ``pb_graph`` is the ``GraphHandle`` from ``load_graph``);
+    ``net_output`` is the thresholded uint8 [H,W,C] map.  Returns {"horizontal": mask, "vertical": mask}."""
+    eng = self.pb_graph.engine(resolve_device(getattr(self, "gpu_devices", "")))
+    horizontal, vertical = eng.separator_post(np.ascontiguousarray(net_output[:, :, 0]))
+    return {"horizontal": horizontal, "vertical": vertical}
+
+
+def separator_pages(images_bgr, pb_graph: GraphHandle, threshold=0.05, gpu_device="0", **kw):
+    """One call for ``SeparatorNetPostProcessor.run`` up to the polygon step (sep:141-151) on uint8 pages as
+    ``cv2.imread`` / ``scale_image`` return them ([N,H,W,3] BGR, or [N,H,W] gray): see ``Engine.separator_pages``."""
+    return pb_graph.engine(resolve_device(gpu_device)).separator_pages(images_bgr, threshold=threshold, **kw)
+
+
+def heading_pages(images_bgr, boxes, pb_graph: GraphHandle, gpu_device="0", **kw):
+    """``HeadingNetPostProcessor.run`` up to ``get_net_prob_for_text_line`` (head:247-291): see ``Engine.heading_pages``."""
+    return pb_graph.engine(resolve_device(gpu_device)).heading_pages(images_bgr, boxes, **kw)
+
+
+def install(patch_post_process: bool = True):
+    """Make ``import article_separation....net_post_processing_helper`` resolve to this module.  With
+    ``patch_post_process`` the reference's ``SeparatorNetPostProcessor.post_process`` (if that module is already imported,
+    or as soon as ``patch_separator_post_processor()`` is called after importing it) runs on the GPU as well."""
     me = sys.modules[__name__]
     sys.modules[REFERENCE_MODULE] = me
     parent = sys.modules.get(REFERENCE_MODULE.rsplit(".", 1)[0])
@@ -149,4 +172,17 @@ def install():
                    "apply_threshold"):
             if hasattr(mod, fn):
                 setattr(mod, fn, getattr(me, fn))
+    if patch_post_process:
+        patch_separator_post_processor()
     return me
+
+
+def patch_separator_post_processor() -> bool:
+    """Rebind ``SeparatorNetPostProcessor.post_process`` to the GPU version; returns False when the reference class has
+    not been imported (call again after importing it)."""
+    mod = sys.modules.get(REFERENCE_MODULE.rsplit(".", 1)[0] + ".separator_net_post_processor")
+    cls = getattr(mod, "SeparatorNetPostProcessor", None) if mod is not None else None
+    if cls is None:
+        return False
+    cls.post_process = separator_post_process
+    return True

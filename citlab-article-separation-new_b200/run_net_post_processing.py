@@ -12,8 +12,9 @@ Two back ends per rank:
   * the reference's own, unmodified ``SeparatorNetPostProcessor`` / ``HeadingNetPostProcessor`` when the
     reference package (and its lxml / shapely / rasterio dependencies) is importable - ``net_boundary.install()``
     makes them call the B200 engine, and PAGE-XML is written exactly as before;
-  * ``--dump_dir``: the path up to the reference's integer forms - ``load_and_scale_image`` -> net ->
-    ``uint8(p*255)`` and the thresholded mask (separator_net_post_processor.py:146-149) - written as PNGs plus a
+  * ``--dump_dir``: the path up to the polygon step - ``cv2.imread`` + ``scale_image`` on the host, then colour step ->
+    net -> ``uint8(p*255)`` -> thresholded mask -> ``post_process`` (separator_net_post_processor.py:146-151, 25-99) on
+    the device (``Engine.separator_pages``) - written as PNGs (probability, mask, horizontal, vertical) plus a
     per-rank manifest (a re-run skips pages already listed, and the parent checks every page was done: worker
     failures are silent in the reference because its futures are never awaited, reference :77,82).
 """
@@ -115,13 +116,21 @@ def run_rank(args, rank: int, world: int, local_rank: int) -> int:
     for path in shard:
         if path in done:
             continue
-        _, image_grey, sc = net_boundary.load_and_scale_image(path, fixed_height, args.scaling_factor)
-        _, u8, mask = eng.forward(image_grey, want_u8=True, want_mask=True, threshold=args.threshold)
+        # decode + resize stay on the host (cv2, helper.py:14-28); the colour step, the net and the integer
+        # post-processing run on the device: uint8 BGR goes up, uint8 maps / masks come down
+        image = cv2.imread(path)
+        image, sc = net_boundary.scale_image(image, fixed_height, args.scaling_factor)
         stem = os.path.splitext(os.path.basename(path))[0]
-        cv2.imwrite(os.path.join(args.dump_dir, stem + "_prob.png"), np.ascontiguousarray(u8[0, :, :, 0]))
+        if args.mode == "separator" and image.shape[0] >= 50 and image.shape[1] >= 100:
+            r = eng.separator_pages(image, threshold=args.threshold, want_u8=True, want_mask=True)
+            cv2.imwrite(os.path.join(args.dump_dir, stem + "_horizontal.png"), np.ascontiguousarray(r["horizontal"][0]))
+            cv2.imwrite(os.path.join(args.dump_dir, stem + "_vertical.png"), np.ascontiguousarray(r["vertical"][0]))
+        else:
+            r = eng.separator_pages(image, threshold=args.threshold, want_u8=True, want_mask=True, want_separators=False)
+        cv2.imwrite(os.path.join(args.dump_dir, stem + "_prob.png"), np.ascontiguousarray(r["u8"][0, :, :, 0]))
         if args.mode == "separator":
-            cv2.imwrite(os.path.join(args.dump_dir, stem + "_mask.png"), np.ascontiguousarray(mask[0]))
-        done[path] = {"scale": sc, "shape": list(image_grey.shape)}
+            cv2.imwrite(os.path.join(args.dump_dir, stem + "_mask.png"), np.ascontiguousarray(r["mask"][0]))
+        done[path] = {"scale": sc, "shape": list(image.shape[:2])}
         with open(manifest_path, "w") as f:
             json.dump({"rank": rank, "world": world, "pages": done}, f)
     return len(shard)

@@ -228,3 +228,54 @@ def test_heading_pages_rejects_boxes_outside_the_page(eng):
                                    ctypes.c_void_p(bad.ctypes.data), 1, ctypes.c_void_p(sums.ctypes.data), None)
     assert rc == 1   # ARU_EINVAL
     del EngineError
+
+
+def test_boundary_post_process_drop_in(built_lib):
+    """net_boundary.separator_post_process bound as SeparatorNetPostProcessor.post_process: same dict as the reference."""
+    from aru_b200 import net_boundary
+    from aru_b200.synth import synth_pb, synth_separator_mask
+    from oracle import separator_post_oracle as O
+
+    class FakeSeparatorNetPostProcessor:            # what the method needs of the reference class: pb_graph, gpu_devices
+        def __init__(self):
+            self.pb_graph = net_boundary.GraphHandle(synth_pb("tiny"))
+            self.gpu_devices = ""
+        post_process = net_boundary.separator_post_process
+
+    pp = FakeSeparatorNetPostProcessor()
+    mask = synth_separator_mask(240, 330, seed=77)
+    out = pp.post_process(np.stack([mask, 255 - mask], axis=-1))
+    h_ref, v_ref = O.separator_post_process(mask)
+    assert set(out) == {"horizontal", "vertical"}
+    assert np.array_equal(out["horizontal"], h_ref) and np.array_equal(out["vertical"], v_ref)
+
+
+def test_cli_dump_dir_writes_separator_masks(built_lib, tmp_path):
+    """The page-sharded CLI in --dump_dir mode: PNG pages in, probability / mask / horizontal / vertical PNGs out, and
+    the separator masks equal the oracle's post_process of the written mask."""
+    cv2 = pytest.importorskip("cv2")
+    from aru_b200 import run_net_post_processing as cli
+    from aru_b200.synth import synth_page, synth_pb
+    from oracle import separator_post_oracle as O
+    paths = []
+    for i in range(3):
+        gray = synth_page(300, 220, seed=60 + i)
+        p = str(tmp_path / f"page{i}.png")
+        cv2.imwrite(p, np.stack([gray, gray, gray], axis=-1))
+        paths.append(p)
+    lst = tmp_path / "pages.lst"
+    lst.write_text("\n".join(paths) + "\n")
+    pb = tmp_path / "separator.pb"
+    pb.write_bytes(synth_pb("separator"))
+    out = tmp_path / "out"
+    assert cli.main(["--path_to_image_list", str(lst), "--path_to_pb", str(pb), "--mode", "separator",
+                     "--fixed_height", "256", "--dump_dir", str(out)]) == 0
+    for i in range(3):
+        mask = cv2.imread(str(out / f"page{i}_mask.png"), cv2.IMREAD_GRAYSCALE)
+        hor = cv2.imread(str(out / f"page{i}_horizontal.png"), cv2.IMREAD_GRAYSCALE)
+        ver = cv2.imread(str(out / f"page{i}_vertical.png"), cv2.IMREAD_GRAYSCALE)
+        prob = cv2.imread(str(out / f"page{i}_prob.png"), cv2.IMREAD_GRAYSCALE)
+        assert mask.shape[0] == 256 and prob.shape == mask.shape
+        assert np.array_equal(mask, O.apply_threshold(prob, 0.05))
+        h_ref, v_ref = O.separator_post_process(mask)
+        assert np.array_equal(hor, h_ref) and np.array_equal(ver, v_ref)
