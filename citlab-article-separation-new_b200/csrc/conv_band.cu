@@ -203,6 +203,13 @@ __device__ __forceinline__ uint32_t pack2_raw(float x, float y) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// wait-time counters of the pipeline roles (ARU_BAND_DBG=16 prints them); the clock reads sit in every hot loop, so
+// they are compiled in only with -DARU_BAND_STATS
+#ifdef ARU_BAND_STATS
+#define BAND_CLK() clock64()
+#else
+#define BAND_CLK() 0LL
+#endif
 __device__ unsigned long long g_band_stats[160][8];
 
 // 16-byte read-only load that the compiler cannot sink to its use (the point is to have it in flight early)
@@ -347,19 +354,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
       const uint32_t ring_end = ring_lo + (uint32_t)a.S * slot_units;
       int q0 = 0;          // ring slot of input row 0 of the current tile
       TileRef tr = tile_ref(L0, a.n_strips, a.n_ty);
-      long long c_tempty = 0, c_full = 0, c_tot = clock64();
+      long long c_tempty = 0, c_full = 0, c_tot = BAND_CLK();
       for (int t = 0; t < n_tiles; ++t) {
         const int stage = t & 1;
-        long long c0 = clock64();
+        long long c0 = BAND_CLK();
         mbar_wait(s_tempty + 8 * stage, ((uint32_t)(t >> 1) & 1u) ^ 1u, a.err_flag, 2);
-        c_tempty += clock64() - c0;
+        c_tempty += BAND_CLK() - c0;
         const uint32_t d_tmem = tmem_base + (uint32_t)(stage * 256);
         {
           // One wait per tile: per-row barriers cost the issuer ~200 cycles each (shared-memory port contention with the
           // epilogue), and the ring is a tile ahead in steady state anyway.
-          long long c1 = clock64();
+          long long c1 = BAND_CLK();
           mbar_wait(s_full + 8 * (t & 3), (uint32_t)(t >> 2) & 1u, a.err_flag, 3);
-          c_full += clock64() - c1;
+          c_full += BAND_CLK() - c1;
           tc_fence_after();
         }
         // K steps in input-row order.  A = the window of a banded master starting at row i * cop; B = the row slot of
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
         tr = nx;
       }
       if (a.dbg & 16) {
-        g_band_stats[blockIdx.x][0] = clock64() - c_tot;
+        g_band_stats[blockIdx.x][0] = BAND_CLK() - c_tot;
         g_band_stats[blockIdx.x][1] = c_tempty;
         g_band_stats[blockIdx.x][2] = c_full;
       }
@@ -439,7 +446,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
       int tiles_done = 0;        // tiles whose completion has been observed
       int free_upto = 0;         // rows < free_upto are dead: row q may be loaded when q - S < free_upto
       TileRef tr = tile_ref(L0, a.n_strips, a.n_ty);
-      long long c_done = 0, c_ptot = clock64();
+      long long c_done = 0, c_ptot = BAND_CLK();
       for (int t = 0; t < n_tiles; ++t) {
         const bool fresh = (t == 0) || (tr.ty == 0);
         const int i0 = fresh ? 0 : a.ks - 1;
@@ -453,9 +460,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
         const int i_end = min(rows_win, a.H + a.ks - 3 - y_first + 1);
         // all slots of the new rows must be dead: the last new row is q + n_new - 1
         while (q + n_new - 1 - a.S >= free_upto) {
-          long long c2 = clock64();
+          long long c2 = BAND_CLK();
           mbar_wait_sleep(s_done + 8 * (tiles_done & 3), (uint32_t)(tiles_done >> 2) & 1u, a.err_flag, 1);
-          c_done += clock64() - c2;
+          c_done += BAND_CLK() - c2;
           ++tiles_done;
           free_upto = (tiles_done <= t) ? qs_ring[tiles_done & 7] : q;
         }
@@ -476,7 +483,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
         if (++tr.ty == a.n_ty) { tr.ty = 0; if (++tr.s == a.n_strips) { tr.s = 0; ++tr.n; } }
       }
       if (lane == 0 && (a.dbg & 16)) {
-        g_band_stats[blockIdx.x][4] = clock64() - c_ptot;
+        g_band_stats[blockIdx.x][4] = BAND_CLK() - c_ptot;
         g_band_stats[blockIdx.x][5] = c_done;
       }
     } else if (warp >= 4) {
@@ -493,9 +500,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
         long long c_tf = 0, c_se = 0;
         for (int t = 0; t < n_tiles; ++t) {
           const int stage = t & 1;
-          long long c0 = clock64();
+          long long c0 = BAND_CLK();
           mbar_wait_sleep(s_tfull + 8 * stage, (uint32_t)(t >> 1) & 1u, a.err_flag, 4);
-          c_tf += clock64() - c0;
+          c_tf += BAND_CLK() - c0;
           __syncwarp();
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(stage * 256);
@@ -503,9 +510,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
           tmem_ld32(taddr, v);
 #pragma unroll 1
           for (int sb = 0; sb < n_slabs; ++sb) {
-            long long c1 = clock64();
+            long long c1 = BAND_CLK();
             mbar_wait_sleep(s_sempty + 8 * b, bpar ^ 1u, a.err_flag, 5);
-            c_se += clock64() - c1;
+            c_se += BAND_CLK() - c1;
             uint8_t* my_st = slabs + b * SLAB_BYTES + st_off;
             tmem_ld_wait();
             if constexpr (HEAD) {
@@ -593,9 +600,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_band(const __grid_const
               rn[0] = ldg_nc_v4(a.res + res_c + gp1 + row8 + (long long)xn * 8, xnv && gv[0]);
               rn[1] = ldg_nc_v4(a.res + res_c + gp1 + (long long)xn * 8, xnv && gv[1]);
             }
-            long long c2 = clock64();
+            long long c2 = BAND_CLK();
             mbar_wait_sleep(s_sfull + 8 * b, bpar, a.err_flag, 6);
-            c_sf += clock64() - c2;
+            c_sf += BAND_CLK() - c2;
             const uint8_t* slab = slabs + b * SLAB_BYTES;
             uint4 raw[2];
             raw[0] = *reinterpret_cast<const uint4*>(slab + rs0 * SLAB_ROW + lane * 16);
