@@ -1283,6 +1283,34 @@ int aru_separator_post(aru_engine* e, const uint8_t* mask, int n, int h, int w, 
   return rc;
 }
 
+int aru_cc_filter(aru_engine* e, const uint8_t* mask, int n, int h, int w, int min_size, uint8_t* out) {
+  if (!e || !mask || !out || n <= 0 || h <= 0 || w <= 0)
+    return e ? fail(e, ARU_EINVAL, "aru_cc_filter: bad argument") : ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  const size_t page_px = (size_t)h * w;
+  const int mb = (int)std::max<long long>(1, std::min<long long>(n, (64LL << 20) / (long long)page_px));
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  void* scratch = nullptr;
+  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(scratch); };
+  if (cudaMalloc((void**)&d_in, mb * page_px) || cudaMalloc((void**)&d_out, mb * page_px) ||
+      cudaMalloc(&scratch, separator_post_scratch_bytes(mb, h, w))) {
+    cleanup();
+    return fail(e, ARU_ENOMEM, "aru_cc_filter: device allocation failed");
+  }
+  int rc = ARU_OK;
+  for (int i0 = 0; i0 < n && rc == ARU_OK; i0 += mb) {
+    const int cnt = std::min(mb, n - i0);
+    cudaError_t err = cudaMemcpyAsync(d_in, mask + (size_t)i0 * page_px, cnt * page_px, cudaMemcpyHostToDevice, e->s_comp);
+    if (err == cudaSuccess) err = launch_cc_filter(e->s_comp, d_in, cnt, h, w, min_size, scratch, d_out);
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(out + (size_t)i0 * page_px, d_out, cnt * page_px, cudaMemcpyDeviceToHost, e->s_comp);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+    if (err != cudaSuccess) rc = fail(e, ARU_ECUDA, "aru_cc_filter: %s", cudaGetErrorString(err));
+  }
+  cleanup();
+  return rc;
+}
+
 int aru_open_rect(aru_engine* e, const uint8_t* mask, int n, int h, int w, int kw, int kh, uint8_t* out) {
   if (!e || !mask || !out || n <= 0 || h <= 0 || w <= 0 || kw < 1 || kh < 1 || (kw > 1 && kh > 1))
     return e ? fail(e, ARU_EINVAL, "aru_open_rect: bad argument (one of kw, kh must be 1)") : ARU_EINVAL;

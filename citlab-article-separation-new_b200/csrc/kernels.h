@@ -69,6 +69,9 @@ cudaError_t launch_separator_post(cudaStream_t st, const uint8_t* mask, int n, i
 // [page0, page0 + n); u8 holds those n pages as [n][h][w][c]
 cudaError_t launch_box_sums(cudaStream_t st, const uint8_t* u8, int n, int h, int w, int c, int page0, const int* boxes,
                             int n_boxes, unsigned long long* sums);
+// apply_cc_analysis: keep the 8-connected components of the non-zero pixels with area >= min_size (output {0,255})
+cudaError_t launch_cc_filter(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int min_size, void* scratch,
+                             uint8_t* out);
 cudaError_t launch_open_rect(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int kw, int kh, void* scratch,
                              uint8_t* out);
 // debug read-back: chunk-planar view -> dense float32 NHWC [N][H][W][C]

@@ -479,6 +479,26 @@ cudaError_t launch_separator_post(cudaStream_t st, const uint8_t* mask, int n, i
   return cudaGetLastError();
 }
 
+// RegionNetPostProcessor.apply_cc_analysis alone (region_net_post_processor_base.py:230-251; also what
+// TextBlockNetPostProcessor.post_process consists of, text_block_net_post_processor.py:12-24)
+cudaError_t launch_cc_filter(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int min_size, void* scratch,
+                             uint8_t* out) {
+  if (n <= 0 || h <= 0 || w <= 0 || (long long)h * w >= (1LL << 31) || n > 65535) return cudaErrorInvalidValue;
+  const int Wd = (w + 31) / 32;
+  const size_t px = (size_t)n * h * w, words = (size_t)n * h * Wd;
+  int* label = reinterpret_cast<int*>(scratch);
+  int* area = label + px;
+  uint32_t* b0 = reinterpret_cast<uint32_t*>(area + px);
+  uint32_t* b1 = b0 + words;
+  bits_pack(st, mask, n, h, w, Wd, b0);
+  k_cc_init<<<nblk(words), 256, 0, st>>>(b0, n, h, w, Wd, label, area);
+  k_cc_merge<<<nblk(words), 256, 0, st>>>(b0, n, h, w, Wd, label);
+  k_cc_count<<<nblk(words), 256, 0, st>>>(b0, n, h, w, Wd, label, area);
+  k_cc_filter<<<nblk(words), 256, 0, st>>>(b0, n, h, w, Wd, label, area, min_size, b1);
+  bits_unpack(st, b1, out, n, h, w, Wd);
+  return cudaGetLastError();
+}
+
 // morphology alone (tests): open_rect(mask, kw, kh) with kw == 1 or kh == 1
 cudaError_t launch_open_rect(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int kw, int kh, void* scratch,
                              uint8_t* out) {

@@ -29,7 +29,7 @@ EXPORTS = [
     "aru_plan", "aru_forward", "aru_forward_device", "aru_sync", "aru_launches_per_forward", "aru_read_buffer",
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
     "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
-    "aru_box_sums",
+    "aru_box_sums", "aru_cc_filter",
 ]
 
 _lib = None
@@ -72,6 +72,7 @@ def load_library() -> ctypes.CDLL:
         lib.aru_pages_to_input.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         lib.aru_heading_pages.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]
         lib.aru_box_sums.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp]
+        lib.aru_cc_filter.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         lib.aru_sync.argtypes = [vp]
         lib.aru_launches_per_forward.argtypes = [vp]
         lib.aru_read_buffer.argtypes = [vp, i32, i32, fp, sz]
@@ -326,6 +327,19 @@ class Engine:
         self._check(self.lib.aru_box_sums(self.handle, ctypes.c_void_p(m.ctypes.data), n, h, w, c,
                                           ctypes.c_void_p(bx.ctypes.data), len(bx), ctypes.c_void_p(sums.ctypes.data)))
         return sums
+
+    def cc_size_filter(self, mask: np.ndarray, min_size: int) -> np.ndarray:
+        """``RegionNetPostProcessor.apply_cc_analysis`` (region_net_post_processor_base.py:230-251): keep the 8-connected
+        components of the non-zero pixels of uint8 masks [N,H,W] (or [H,W]) with area >= min_size; output {0,255}."""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        single = m.ndim == 2
+        if single:
+            m = m[None]
+        n, h, w = m.shape
+        out = np.empty_like(m)
+        self._check(self.lib.aru_cc_filter(self.handle, ctypes.c_void_p(m.ctypes.data), n, h, w, int(min_size),
+                                           ctypes.c_void_p(out.ctypes.data)))
+        return out[0] if single else out
 
     def open_rect(self, mask: np.ndarray, kw: int, kh: int) -> np.ndarray:
         """``cv2.morphologyEx(mask, MORPH_OPEN, RECT(kw, kh))`` for binary masks and kw == 1 or kh == 1."""

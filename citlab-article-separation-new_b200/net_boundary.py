@@ -143,6 +143,15 @@ def separator_post_process(self, net_output):
     return {"horizontal": horizontal, "vertical": vertical}
 
 
+def apply_cc_analysis(self, net_output, threshold):
+    """Drop-in for ``RegionNetPostProcessor.apply_cc_analysis`` (region_net_post_processor_base.py:230-251), used by the
+    separator and the text-block post-processors (text_block_net_post_processor.py:22): connected components on the GPU.
+    ``min_size = int(net_output.size * threshold)`` is evaluated here exactly as the reference does (Python floats)."""
+    eng = self.pb_graph.engine(resolve_device(getattr(self, "gpu_devices", "")))
+    min_size = int(net_output.size * threshold)
+    return eng.cc_size_filter(np.ascontiguousarray(net_output), min_size).astype(net_output.dtype, copy=False)
+
+
 def separator_pages(images_bgr, pb_graph: GraphHandle, threshold=0.05, gpu_device="0", **kw):
     """One call for ``SeparatorNetPostProcessor.run`` up to the polygon step (sep:141-151) on uint8 pages as
     ``cv2.imread`` / ``scale_image`` return them ([N,H,W,3] BGR, or [N,H,W] gray): see ``Engine.separator_pages``."""
@@ -164,7 +173,8 @@ def install(patch_post_process: bool = True):
     if parent is not None:
         setattr(parent, "net_post_processing_helper", me)
     # modules that were imported before install() hold the TF functions by name: rebind them
-    for name in ("separator_net_post_processor", "heading_net_post_processor", "region_net_post_processor_base"):
+    for name in ("separator_net_post_processor", "heading_net_post_processor", "region_net_post_processor_base",
+                 "text_block_net_post_processor"):
         mod = sys.modules.get(REFERENCE_MODULE.rsplit(".", 1)[0] + "." + name)
         if mod is None:
             continue
@@ -180,9 +190,14 @@ def install(patch_post_process: bool = True):
 def patch_separator_post_processor() -> bool:
     """Rebind ``SeparatorNetPostProcessor.post_process`` to the GPU version; returns False when the reference class has
     not been imported (call again after importing it)."""
-    mod = sys.modules.get(REFERENCE_MODULE.rsplit(".", 1)[0] + ".separator_net_post_processor")
+    pkg = REFERENCE_MODULE.rsplit(".", 1)[0]
+    base = sys.modules.get(pkg + ".region_net_post_processor_base")
+    base_cls = getattr(base, "RegionNetPostProcessor", None) if base is not None else None
+    if base_cls is not None:
+        base_cls.apply_cc_analysis = apply_cc_analysis      # separator, text-block and any other region post-processor
+    mod = sys.modules.get(pkg + ".separator_net_post_processor")
     cls = getattr(mod, "SeparatorNetPostProcessor", None) if mod is not None else None
     if cls is None:
-        return False
+        return base_cls is not None
     cls.post_process = separator_post_process
     return True

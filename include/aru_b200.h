@@ -172,6 +172,12 @@ int aru_box_sums(aru_engine* e, const uint8_t* u8, int n, int h, int w, int c, c
 /* post_process alone on n thresholded masks (uint8 [n,h,w], non-zero = foreground), host memory in and out. */
 int aru_separator_post(aru_engine* e, const uint8_t* mask, int n, int h, int w, uint8_t* horizontal, uint8_t* vertical);
 
+/* RegionNetPostProcessor.apply_cc_analysis (region_net_post_processor_base.py:230-251) alone - also the whole of
+ * TextBlockNetPostProcessor.post_process (text_block_net_post_processor.py:12-24): keep the 8-connected components of the
+ * non-zero pixels whose area is >= min_size; uint8 [n,h,w] host memory in, {0,255} out.  The reference's limit is
+ * int(net_output.size * threshold) with Python float arithmetic - computed by the caller (net_boundary.apply_cc_analysis). */
+int aru_cc_filter(aru_engine* e, const uint8_t* mask, int n, int h, int w, int min_size, uint8_t* out);
+
 /* cv2.morphologyEx(mask, MORPH_OPEN, getStructuringElement(MORPH_RECT, (kw, kh))) for kw == 1 or kh == 1 on binary
  * masks (non-zero = 255), host memory in and out; exposed for the parity tests of the morphology kernels. */
 int aru_open_rect(aru_engine* e, const uint8_t* mask, int n, int h, int w, int kw, int kh, uint8_t* out);

@@ -279,3 +279,31 @@ def test_cli_dump_dir_writes_separator_masks(built_lib, tmp_path):
         assert np.array_equal(mask, O.apply_threshold(prob, 0.05))
         h_ref, v_ref = O.separator_post_process(mask)
         assert np.array_equal(hor, h_ref) and np.array_equal(ver, v_ref)
+
+
+@pytest.mark.parametrize("path", POST_FIXTURES, ids=[os.path.basename(p)[:-4] for p in POST_FIXTURES])
+def test_cc_filter_matches_reference_apply_cc_analysis(eng, path):
+    """aru_cc_filter against the golden output of the reference's own apply_cc_analysis (= TextBlockNetPostProcessor's
+    post_process), and the boundary drop-in evaluating min_size the way the reference does."""
+    from aru_b200 import net_boundary
+    f = _load(path)
+    assert np.array_equal(eng.cc_size_filter(f["mask"], f["min_size"]), f["cc"])
+
+    class FakeRegionNetPostProcessor:
+        gpu_devices = ""
+        apply_cc_analysis = net_boundary.apply_cc_analysis
+
+    pp = FakeRegionNetPostProcessor()
+    pp.pb_graph = type("G", (), {"engine": staticmethod(lambda device: eng)})()
+    got = pp.apply_cc_analysis(f["mask"], 1 / f["mask"].size * 100)
+    assert got.dtype == np.uint8 and np.array_equal(got, f["cc"])
+
+
+def test_cc_filter_thresholds_and_batches(eng):
+    from aru_b200.synth import synth_separator_mask
+    from oracle import separator_post_oracle as O
+    masks = np.stack([synth_separator_mask(150, 210, seed=s, noise=0.08) for s in range(4)])
+    for min_size in (1, 2, 17, 100, 5000, 10 ** 7):
+        got = eng.cc_size_filter(masks, min_size)
+        for i in range(len(masks)):
+            assert np.array_equal(got[i], O.cc_size_filter(masks[i], min_size)), (min_size, i)
