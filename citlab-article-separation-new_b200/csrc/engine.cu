@@ -80,6 +80,8 @@ struct Plan {
   uint8_t* mask_dev[2] = {nullptr, nullptr};
   uint8_t* page_dev[2] = {nullptr, nullptr};   // uint8 gray / BGR pages (aru_separator_pages)
   int page_dev_channels = 0;
+  uint8_t* src_dev[2] = {nullptr, nullptr};    // unscaled uint8 pages (aru_*_images: cv2.resize on the device)
+  size_t src_dev_bytes = 0;
   uint8_t* hor_dev[2] = {nullptr, nullptr};    // separator post-processing results
   uint8_t* ver_dev[2] = {nullptr, nullptr};
   void* post_scratch = nullptr;                // labels, areas, bit planes (used on the compute stream only)
@@ -228,6 +230,7 @@ void free_plan(Plan* p) {
     if (p->u8_dev[i]) cudaFree(p->u8_dev[i]);
     if (p->mask_dev[i]) cudaFree(p->mask_dev[i]);
     if (p->page_dev[i]) cudaFree(p->page_dev[i]);
+    if (p->src_dev[i]) cudaFree(p->src_dev[i]);
     if (p->hor_dev[i]) cudaFree(p->hor_dev[i]);
     if (p->ver_dev[i]) cudaFree(p->ver_dev[i]);
     if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
@@ -810,7 +813,70 @@ void separator_kernel_sizes(int h, int w, int* k_h1, int* k_v, int* k_h2) {
   *k_h2 = (int)(10.0 * w / 1000.0);
 }
 
+// cv2.resize(image, None, fx=sc, fy=sc, interpolation=cv2.INTER_AREA) (scale_image, helper.py:14-25): destination size
+// and the (source index, weight) tables of OpenCV's area resampling, in its own double / float arithmetic.
+struct ScalePlan {
+  int sh = 0, sw = 0, dh = 0, dw = 0;
+  int fast = 0, ix = 1, iy = 1;
+  int *x_start = nullptr, *x_si = nullptr, *y_start = nullptr, *y_si = nullptr;
+  float *x_alpha = nullptr, *y_alpha = nullptr;
+};
+
+void free_scale_plan(ScalePlan* sp) {
+  cudaFree(sp->x_start); cudaFree(sp->x_si); cudaFree(sp->x_alpha);
+  cudaFree(sp->y_start); cudaFree(sp->y_si); cudaFree(sp->y_alpha);
+  *sp = ScalePlan();
+}
+
+int cv_round(double v) { return (int)std::nearbyint(v); }   // cvRound / saturate_cast<int>(double): half to even
+
+void area_table(int ssize, int dsize, double scale, std::vector<int>* start, std::vector<int>* si, std::vector<float>* alpha) {
+  start->assign(1, 0);
+  for (int dx = 0; dx < dsize; ++dx) {
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cell = std::min(scale, ssize - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) { si->push_back(sx1 - 1); alpha->push_back((float)((sx1 - fsx1) / cell)); }
+    for (int sx = sx1; sx < sx2; ++sx) { si->push_back(sx); alpha->push_back((float)(1.0 / cell)); }
+    if (fsx2 - sx2 > 1e-3) { si->push_back(sx2); alpha->push_back((float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell)); }
+    start->push_back((int)si->size());
+  }
+}
+
+int make_scale_plan(aru_engine* e, int sh, int sw, double sc, ScalePlan* sp) {
+  if (!(sc > 0.0) || sc >= 1.0)
+    return fail(e, ARU_EUNSUP, "device resize covers shrinking only (INTER_AREA, scale < 1); got scale %.6f: enlarging is "
+                "INTER_CUBIC in the reference and stays on the host", sc);
+  sp->sh = sh; sp->sw = sw;
+  sp->dw = cv_round(sw * sc);
+  sp->dh = cv_round(sh * sc);
+  if (sp->dw < 1 || sp->dh < 1) return fail(e, ARU_EINVAL, "scaled page would be empty");
+  const double scale = 1.0 / sc;
+  const int iscale = cv_round(scale);
+  if (std::fabs(scale - iscale) < 2.220446049250313e-16) {   // OpenCV's integer-scale path
+    if ((long long)sp->dw * iscale > sw || (long long)sp->dh * iscale > sh)
+      return fail(e, ARU_EUNSUP, "integer-scale area resize with a partial last cell (%dx%d / %d) is not covered on the device",
+                  sh, sw, iscale);
+    sp->fast = 1; sp->ix = sp->iy = iscale;
+    return ARU_OK;
+  }
+  std::vector<int> xs, xi, ys, yi;
+  std::vector<float> xa, ya;
+  area_table(sw, sp->dw, scale, &xs, &xi, &xa);
+  area_table(sh, sp->dh, scale, &ys, &yi, &ya);
+  int rc;
+  if ((rc = upload(e, xs, &sp->x_start)) || (rc = upload(e, xi, &sp->x_si)) || (rc = upload(e, xa, &sp->x_alpha)) ||
+      (rc = upload(e, ys, &sp->y_start)) || (rc = upload(e, yi, &sp->y_si)) || (rc = upload(e, ya, &sp->y_alpha))) {
+    free_scale_plan(sp);
+    return rc;
+  }
+  return ARU_OK;
+}
+
 struct HostIO {
+  const ScalePlan* scale = nullptr;   // in_u8 holds unscaled pages sh x sw; they are resized on the device first
   const float* in_f32 = nullptr;   // float32 [n,h,w] pages (gray / 255) ...
   const uint8_t* in_u8 = nullptr;  // ... or uint8 [n,h,w,channels] pages (gray, or BGR as cv2.imread returns them)
   int channels = 1;
@@ -862,6 +928,16 @@ int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
     rc = ensure_quant(e, p, want_u8, want_mask);
     if (rc) return rc;
     if (io.in_u8 && (rc = ensure_pages(e, p, io.channels))) return rc;
+    const size_t src_px = io.scale ? (size_t)io.scale->sh * io.scale->sw : 0;
+    if (io.scale && p->src_dev_bytes < (size_t)p->n * src_px * io.channels) {
+      CU(e, cudaStreamSynchronize(e->s_h2d));
+      CU(e, cudaStreamSynchronize(e->s_comp));
+      for (int i = 0; i < 2; ++i) {
+        if (p->src_dev[i]) { cudaFree(p->src_dev[i]); p->src_dev[i] = nullptr; }
+        CU(e, cudaMalloc((void**)&p->src_dev[i], (size_t)p->n * src_px * io.channels));
+      }
+      p->src_dev_bytes = (size_t)p->n * src_px * io.channels;
+    }
     if (want_post && (rc = ensure_post(e, p))) return rc;
     const int par = slot & 1;
     // buffers of this parity are free once the device->host copies of their previous use are done
@@ -869,7 +945,10 @@ int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
       CU(e, cudaStreamWaitEvent(e->s_h2d, p->ev_d2h[par], 0));
       CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_d2h[par], 0));
     }
-    if (io.in_u8)
+    if (io.in_u8 && io.scale)
+      CU(e, cudaMemcpyAsync(p->src_dev[par], io.in_u8 + (size_t)i0 * src_px * io.channels,
+                            (size_t)cnt * src_px * io.channels, cudaMemcpyHostToDevice, e->s_h2d));
+    else if (io.in_u8)
       CU(e, cudaMemcpyAsync(p->page_dev[par], io.in_u8 + (size_t)i0 * page_px * io.channels,
                             (size_t)cnt * page_px * io.channels, cudaMemcpyHostToDevice, e->s_h2d));
     else
@@ -877,6 +956,12 @@ int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
                             cudaMemcpyHostToDevice, e->s_h2d));
     CU(e, cudaEventRecord(p->ev_h2d[par], e->s_h2d));
     CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_h2d[par], 0));
+    if (io.scale) {
+      const ScalePlan& sp = *io.scale;
+      cudaError_t err = launch_resize_area(e->s_comp, p->src_dev[par], io.channels, cnt, sp.sh, sp.sw, p->page_dev[par], h, w,
+                                           sp.x_start, sp.x_si, sp.x_alpha, sp.y_start, sp.y_si, sp.y_alpha, sp.fast, sp.ix, sp.iy);
+      if (err != cudaSuccess) return fail(e, ARU_ECUDA, "resize_area launch: %s", cudaGetErrorString(err));
+    }
     if (io.in_u8) {
       cudaError_t err = launch_pages_to_input(e->s_comp, p->page_dev[par], io.channels, (long long)cnt * page_px,
                                               p->in_dev[par], nullptr);
@@ -1172,6 +1257,76 @@ int aru_separator_pages(aru_engine* e, const uint8_t* pages, int channels, int n
   io.out_v = vertical;
   io.cut = mask_cut(thr);
   return forward_host(e, io, n, h, w);
+}
+
+int aru_scaled_size(int src_h, int src_w, double sc, int* h, int* w) {
+  if (!h || !w || src_h <= 0 || src_w <= 0 || !(sc > 0.0)) return ARU_EINVAL;
+  *w = cv_round(src_w * sc);
+  *h = cv_round(src_h * sc);
+  return ARU_OK;
+}
+
+int aru_scale_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int src_h, int src_w, double sc, uint8_t* out) {
+  if (!e || !pages || !out || n <= 0 || src_h <= 0 || src_w <= 0 || (channels != 1 && channels != 3))
+    return e ? fail(e, ARU_EINVAL, "aru_scale_pages: bad argument") : ARU_EINVAL;
+  CU(e, cudaSetDevice(e->device));
+  ScalePlan sp;
+  int rc = make_scale_plan(e, src_h, src_w, sc, &sp);
+  if (rc) return rc;
+  const size_t src_b = (size_t)src_h * src_w * channels, dst_b = (size_t)sp.dh * sp.dw * channels;
+  const int mb = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)256 << 20) / src_b));
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  if (cudaMalloc((void**)&d_in, mb * src_b) || cudaMalloc((void**)&d_out, mb * dst_b)) {
+    cudaFree(d_in); cudaFree(d_out); free_scale_plan(&sp);
+    return fail(e, ARU_ENOMEM, "aru_scale_pages: device allocation failed");
+  }
+  for (int i0 = 0; i0 < n && rc == ARU_OK; i0 += mb) {
+    const int cnt = std::min(mb, n - i0);
+    cudaError_t err = cudaMemcpyAsync(d_in, pages + (size_t)i0 * src_b, cnt * src_b, cudaMemcpyHostToDevice, e->s_comp);
+    if (err == cudaSuccess)
+      err = launch_resize_area(e->s_comp, d_in, channels, cnt, src_h, src_w, d_out, sp.dh, sp.dw, sp.x_start, sp.x_si,
+                               sp.x_alpha, sp.y_start, sp.y_si, sp.y_alpha, sp.fast, sp.ix, sp.iy);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out + (size_t)i0 * dst_b, d_out, cnt * dst_b, cudaMemcpyDeviceToHost, e->s_comp);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+    if (err != cudaSuccess) rc = fail(e, ARU_ECUDA, "aru_scale_pages: %s", cudaGetErrorString(err));
+  }
+  cudaFree(d_in); cudaFree(d_out); free_scale_plan(&sp);
+  return rc;
+}
+
+int aru_separator_images(aru_engine* e, const uint8_t* images, int channels, int n, int src_h, int src_w, double sc,
+                         double thr, float* out, uint8_t* out_u8, uint8_t* out_mask, uint8_t* horizontal, uint8_t* vertical) {
+  if (!e || !images || n <= 0 || src_h <= 0 || src_w <= 0 || (channels != 1 && channels != 3))
+    return e ? fail(e, ARU_EINVAL, "aru_separator_images: bad argument") : ARU_EINVAL;
+  if (sc == 1.0)
+    return aru_separator_pages(e, images, channels, n, src_h, src_w, thr, out, out_u8, out_mask, horizontal, vertical);
+  if ((horizontal == nullptr) != (vertical == nullptr))
+    return fail(e, ARU_EINVAL, "aru_separator_images: horizontal and vertical go together");
+  CU(e, cudaSetDevice(e->device));
+  ScalePlan sp;
+  int rc = make_scale_plan(e, src_h, src_w, sc, &sp);
+  if (rc) return rc;
+  if (horizontal) {
+    int k1, kv, k2;
+    separator_kernel_sizes(sp.dh, sp.dw, &k1, &kv, &k2);
+    if (k1 < 1 || kv < 1 || k2 < 1) {
+      free_scale_plan(&sp);
+      return fail(e, ARU_EINVAL, "aru_separator_images: scaled page %dx%d too small for the structuring elements", sp.dh, sp.dw);
+    }
+  }
+  HostIO io;
+  io.scale = &sp;
+  io.in_u8 = images;
+  io.channels = channels;
+  io.out = out;
+  io.out_u8 = out_u8;
+  io.out_mask = out_mask;
+  io.out_h = horizontal;
+  io.out_v = vertical;
+  io.cut = mask_cut(thr);
+  rc = forward_host(e, io, n, sp.dh, sp.dw);
+  free_scale_plan(&sp);
+  return rc;
 }
 
 static int check_boxes(aru_engine* e, const int32_t* boxes, int n_boxes, int n, int h, int w) {

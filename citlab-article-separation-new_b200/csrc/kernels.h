@@ -59,6 +59,11 @@ cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uin
 // uint8 gray (channels 1) or BGR (channels 3) pages -> float32 net input gray/255 (+ optional uint8 gray copy)
 cudaError_t launch_pages_to_input(cudaStream_t st, const uint8_t* pages, int channels, long long npix, float* out,
                                   uint8_t* gray_out);
+// cv2.resize(INTER_AREA) of n uint8 pages sh x sw -> dh x dw; the (source index, weight) tables are device arrays built
+// by the engine (general scale) or unused (fast = 1: integer scales ix, iy)
+cudaError_t launch_resize_area(cudaStream_t st, const uint8_t* src, int channels, int n, int sh, int sw, uint8_t* dst,
+                               int dh, int dw, const int* x_start, const int* x_si, const float* x_alpha,
+                               const int* y_start, const int* y_si, const float* y_alpha, int fast, int ix, int iy);
 // SeparatorNetPostProcessor.post_process on n thresholded masks of h x w: component size filter, three rectangular
 // openings and the saturating subtract; scratch >= separator_post_scratch_bytes(n, h, w)
 size_t separator_post_scratch_bytes(int n, int h, int w);

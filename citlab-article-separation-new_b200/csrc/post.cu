@@ -89,6 +89,85 @@ cudaError_t launch_pages_to_input(cudaStream_t st, const uint8_t* pages, int cha
   return cudaGetLastError();
 }
 
+// ---- f1b: cv2.resize(..., INTER_AREA) of uint8 pages (scale_image, net_post_processing_helper.py:14-25, sc < 1) -------
+// OpenCV's area resampling, restated operation by operation (oracle/resize_oracle.py; bit-exact against cv2.resize):
+//   general scale: per destination column / row a table of (source index, float weight) entries (host, double
+//     arithmetic, see area_table() in engine.cu); a source row is first reduced horizontally, buf = sum_k S[sx_k]*alpha_k
+//     (float, entries in order), then rows are combined, sum = beta_0*buf_0 (+)= beta_j*buf_j; multiplies and adds are
+//     separate roundings (no FMA); the result is rounded half to even and saturated;
+//   integer scale (both axes): integer box sum; (sum + 2) >> 2 for 2x2, else round(float(sum) * (1.f / area)).
+// One thread per destination pixel; the footprint of a thread is ceil(scale)+1 source rows / columns.
+struct AreaTabs {
+  const int* x_start; const int* x_si; const float* x_alpha;   // entries of column dx: [x_start[dx], x_start[dx+1])
+  const int* y_start; const int* y_si; const float* y_alpha;
+  int fast;        // 1: integer scales ix, iy
+  int ix, iy;
+  float inv_area;  // 1.f / (ix * iy)
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_resize_area(const uint8_t* __restrict__ src, int n, int sh, int sw,
+                                                     uint8_t* __restrict__ dst, int dh, int dw, AreaTabs t) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * dh * dw) return;
+  const int dx = (int)(i % dw);
+  const long long r = i / dw;
+  const int dy = (int)(r % dh), pg = (int)(r / dh);
+  const uint8_t* S = src + (long long)pg * sh * sw * CH;
+  int res[CH];
+  if (t.fast) {
+    int sum[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) sum[c] = 0;
+    for (int yy = 0; yy < t.iy; ++yy) {
+      const uint8_t* row = S + ((long long)(dy * t.iy + yy) * sw + (long long)dx * t.ix) * CH;
+      for (int xx = 0; xx < t.ix; ++xx)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) sum[c] += row[xx * CH + c];
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      res[c] = (t.ix == 2 && t.iy == 2) ? (sum[c] + 2) >> 2 : __float2int_rn(__fmul_rn((float)sum[c], t.inv_area));
+  } else {
+    float acc[CH];
+    const int y0 = t.y_start[dy], y1 = t.y_start[dy + 1], x0 = t.x_start[dx], x1 = t.x_start[dx + 1];
+    for (int j = y0; j < y1; ++j) {
+      const uint8_t* row = S + (long long)t.y_si[j] * sw * CH;
+      const float beta = t.y_alpha[j];
+      float buf[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) buf[c] = 0.f;
+      for (int k = x0; k < x1; ++k) {
+        const uint8_t* px = row + (long long)t.x_si[k] * CH;
+        const float alpha = t.x_alpha[k];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn((float)px[c], alpha));
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float v = __fmul_rn(beta, buf[c]);
+        acc[c] = j == y0 ? v : __fadd_rn(acc[c], v);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) res[c] = y1 > y0 ? __float2int_rn(acc[c]) : 0;
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) dst[i * CH + c] = (uint8_t)min(max(res[c], 0), 255);
+}
+
+cudaError_t launch_resize_area(cudaStream_t st, const uint8_t* src, int channels, int n, int sh, int sw, uint8_t* dst,
+                               int dh, int dw, const int* x_start, const int* x_si, const float* x_alpha,
+                               const int* y_start, const int* y_si, const float* y_alpha, int fast, int ix, int iy) {
+  if (channels != 1 && channels != 3) return cudaErrorInvalidValue;
+  AreaTabs t{x_start, x_si, x_alpha, y_start, y_si, y_alpha, fast, ix, iy, fast ? 1.f / (float)(ix * iy) : 0.f};
+  const long long total = (long long)n * dh * dw;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (channels == 1) k_resize_area<1><<<blocks, 256, 0, st>>>(src, n, sh, sw, dst, dh, dw, t);
+  else k_resize_area<3><<<blocks, 256, 0, st>>>(src, n, sh, sw, dst, dh, dw, t);
+  return cudaGetLastError();
+}
+
 // ---- f2a: connected-component size filter ---------------------------------------------------------------------------
 // Works on the 1-bit image (bit b of word i of a row = pixel 32 i + b, pad bits 0), one thread per 32-pixel word.  The
 // union-find nodes are the in-word runs of ones: a label is the page-local pixel index of a run's first pixel, and the

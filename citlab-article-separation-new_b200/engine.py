@@ -29,7 +29,7 @@ EXPORTS = [
     "aru_plan", "aru_forward", "aru_forward_device", "aru_sync", "aru_launches_per_forward", "aru_read_buffer",
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
     "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
-    "aru_box_sums", "aru_cc_filter",
+    "aru_box_sums", "aru_cc_filter", "aru_scaled_size", "aru_scale_pages", "aru_separator_images",
 ]
 
 _lib = None
@@ -73,6 +73,9 @@ def load_library() -> ctypes.CDLL:
         lib.aru_heading_pages.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]
         lib.aru_box_sums.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp]
         lib.aru_cc_filter.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+        lib.aru_scaled_size.argtypes = [i32, i32, ctypes.c_double, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+        lib.aru_scale_pages.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.c_double, vp]
+        lib.aru_separator_images.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp]
         lib.aru_sync.argtypes = [vp]
         lib.aru_launches_per_forward.argtypes = [vp]
         lib.aru_read_buffer.argtypes = [vp, i32, i32, fp, sz]
@@ -271,6 +274,50 @@ class Engine:
         self._check(self.lib.aru_separator_pages(self.handle, ctypes.c_void_p(x.ctypes.data), ch, n, h, w,
                                                  ctypes.c_double(threshold), ptr("prob"), ptr("u8"), ptr("mask"),
                                                  ptr("horizontal"), ptr("vertical")))
+        return res
+
+    def scaled_size(self, h: int, w: int, sc: float):
+        """(cvRound(h*sc), cvRound(w*sc)): the size ``cv2.resize(image, None, fx=sc, fy=sc)`` produces."""
+        hh, ww = ctypes.c_int(), ctypes.c_int()
+        if self.lib.aru_scaled_size(h, w, ctypes.c_double(sc), ctypes.byref(hh), ctypes.byref(ww)) != ARU_OK:
+            raise ValueError(f"bad size / scale {h}x{w} * {sc}")
+        return hh.value, ww.value
+
+    def scale_pages(self, pages: np.ndarray, sc: float) -> np.ndarray:
+        """``scale_image`` for sc < 1 (helper.py:14-25): ``cv2.resize(image, None, fx=sc, fy=sc, INTER_AREA)`` of uint8
+        pages [N,H,W] / [N,H,W,3] (or one page) on the device, bit-exact against OpenCV."""
+        x, n, h, w, ch = self._as_pages(pages)
+        x = np.ascontiguousarray(x)
+        dh, dw = self.scaled_size(h, w, sc)
+        out = np.empty((n, dh, dw) + ((ch,) if x.ndim == 4 else ()), np.uint8)
+        self._check(self.lib.aru_scale_pages(self.handle, ctypes.c_void_p(x.ctypes.data), ch, n, h, w, ctypes.c_double(sc),
+                                             ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def separator_images(self, images: np.ndarray, sc: float, threshold: float = 0.05, want_prob: bool = False,
+                         want_u8: bool = False, want_mask: bool = False, want_separators: bool = True) -> dict:
+        """``load_and_scale_image`` after the decode + ``SeparatorNetPostProcessor.run`` up to the polygon step: the
+        unscaled uint8 images (as ``cv2.imread`` returns them, all of one size) go up, are shrunk by ``sc`` on the device
+        (INTER_AREA; ``sc == 1`` is a no-op as in the reference, ``sc > 1`` raises: enlarge on the host), and the
+        results come back at the scaled size.  Same dict as ``separator_pages``."""
+        x, n, h, w, ch = self._as_pages(images)
+        x = np.ascontiguousarray(x)
+        dh, dw = (h, w) if sc == 1.0 else self.scaled_size(h, w, sc)
+        c = self.n_class
+        res = {}
+        if want_prob:
+            res["prob"] = pinned_empty((n, dh, dw, c), np.float32)
+        if want_u8:
+            res["u8"] = pinned_empty((n, dh, dw, c), np.uint8)
+        if want_mask:
+            res["mask"] = pinned_empty((n, dh, dw), np.uint8)
+        if want_separators:
+            res["horizontal"] = pinned_empty((n, dh, dw), np.uint8)
+            res["vertical"] = pinned_empty((n, dh, dw), np.uint8)
+        ptr = lambda k: ctypes.c_void_p(res[k].ctypes.data) if k in res else None  # noqa: E731
+        self._check(self.lib.aru_separator_images(self.handle, ctypes.c_void_p(x.ctypes.data), ch, n, h, w,
+                                                  ctypes.c_double(sc), ctypes.c_double(threshold), ptr("prob"), ptr("u8"),
+                                                  ptr("mask"), ptr("horizontal"), ptr("vertical")))
         return res
 
     def separator_post(self, mask: np.ndarray):

@@ -158,6 +158,12 @@ def separator_pages(images_bgr, pb_graph: GraphHandle, threshold=0.05, gpu_devic
     return pb_graph.engine(resolve_device(gpu_device)).separator_pages(images_bgr, threshold=threshold, **kw)
 
 
+def separator_images(images_bgr, sc, pb_graph: GraphHandle, threshold=0.05, gpu_device="0", **kw):
+    """``scale_image`` (helper.py:14-25, shrinking case) + ``separator_pages`` in one device call: unscaled uint8 images of
+    one size in, results at the scaled size out; see ``Engine.separator_images``."""
+    return pb_graph.engine(resolve_device(gpu_device)).separator_images(images_bgr, sc, threshold=threshold, **kw)
+
+
 def heading_pages(images_bgr, boxes, pb_graph: GraphHandle, gpu_device="0", **kw):
     """``HeadingNetPostProcessor.run`` up to ``get_net_prob_for_text_line`` (head:247-291): see ``Engine.heading_pages``."""
     return pb_graph.engine(resolve_device(gpu_device)).heading_pages(images_bgr, boxes, **kw)

@@ -34,6 +34,7 @@ if __package__ in (None, ""):  # executed as a script: make ``aru_b200`` importa
     __package__ = "aru_b200"
 
 from . import net_boundary, sharding  # noqa: E402
+from .engine import ARU_EUNSUP, EngineError  # noqa: E402
 
 
 def build_parser() -> argparse.ArgumentParser:
@@ -80,6 +81,26 @@ def _reference_available() -> bool:
         return False
 
 
+def _run_page(eng, image, args, fixed_height):
+    """One decoded page (uint8 BGR as ``cv2.imread`` returns it) through ``load_and_scale_image``'s remaining steps, the net
+    and the integer post-processing.  Shrinking (INTER_AREA, the usual case: scans are larger than the net input), the
+    colour step, the net, uint8 / threshold and ``post_process`` run on the device; enlarging (INTER_CUBIC) is done by
+    cv2 on the host as in the reference.  Returns (result dict, scale, (H, W) of the net input)."""
+    sc = net_boundary._scaling_factor(image.shape[0], image.shape[1], args.scaling_factor, fixed_height=fixed_height)
+    want_sep = args.mode == "separator"
+    kw = dict(threshold=args.threshold, want_u8=True, want_mask=True)
+    if sc < 1.0:
+        h, w = eng.scaled_size(image.shape[0], image.shape[1], sc)
+        try:
+            return eng.separator_images(image, sc, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
+        except EngineError as err:
+            if err.code != ARU_EUNSUP:      # an integer scale with a partial last cell: resize on the host
+                raise
+    image, sc = net_boundary.scale_image(image, fixed_height, args.scaling_factor)
+    h, w = image.shape[:2]
+    return eng.separator_pages(image, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
+
+
 def run_rank(args, rank: int, world: int, local_rank: int) -> int:
     paths = net_boundary.load_image_paths(args.path_to_image_list)
     shard = sharding.shard_for_rank(paths, world, rank, _pixel_counts(paths))
@@ -116,21 +137,15 @@ def run_rank(args, rank: int, world: int, local_rank: int) -> int:
     for path in shard:
         if path in done:
             continue
-        # decode + resize stay on the host (cv2, helper.py:14-28); the colour step, the net and the integer
-        # post-processing run on the device: uint8 BGR goes up, uint8 maps / masks come down
-        image = cv2.imread(path)
-        image, sc = net_boundary.scale_image(image, fixed_height, args.scaling_factor)
+        r, sc, shape = _run_page(eng, cv2.imread(path), args, fixed_height)
         stem = os.path.splitext(os.path.basename(path))[0]
-        if args.mode == "separator" and image.shape[0] >= 50 and image.shape[1] >= 100:
-            r = eng.separator_pages(image, threshold=args.threshold, want_u8=True, want_mask=True)
-            cv2.imwrite(os.path.join(args.dump_dir, stem + "_horizontal.png"), np.ascontiguousarray(r["horizontal"][0]))
-            cv2.imwrite(os.path.join(args.dump_dir, stem + "_vertical.png"), np.ascontiguousarray(r["vertical"][0]))
-        else:
-            r = eng.separator_pages(image, threshold=args.threshold, want_u8=True, want_mask=True, want_separators=False)
         cv2.imwrite(os.path.join(args.dump_dir, stem + "_prob.png"), np.ascontiguousarray(r["u8"][0, :, :, 0]))
         if args.mode == "separator":
             cv2.imwrite(os.path.join(args.dump_dir, stem + "_mask.png"), np.ascontiguousarray(r["mask"][0]))
-        done[path] = {"scale": sc, "shape": list(image.shape[:2])}
+        if "horizontal" in r:
+            cv2.imwrite(os.path.join(args.dump_dir, stem + "_horizontal.png"), np.ascontiguousarray(r["horizontal"][0]))
+            cv2.imwrite(os.path.join(args.dump_dir, stem + "_vertical.png"), np.ascontiguousarray(r["vertical"][0]))
+        done[path] = {"scale": sc, "shape": list(shape)}
         with open(manifest_path, "w") as f:
             json.dump({"rank": rank, "world": world, "pages": done}, f)
     return len(shard)

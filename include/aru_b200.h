@@ -169,6 +169,20 @@ int aru_heading_pages(aru_engine* e, const uint8_t* pages, int channels, int n, 
 int aru_box_sums(aru_engine* e, const uint8_t* u8, int n, int h, int w, int c, const int32_t* boxes, int n_boxes,
                  uint64_t* sums);
 
+/*
+ * scale_image on the device (net_post_processing_helper.py:14-25) for the shrinking case sc < 1:
+ * cv2.resize(image, None, fx=sc, fy=sc, interpolation=cv2.INTER_AREA), bit-exact against OpenCV (general and integer
+ * scales).  sc > 1 (INTER_CUBIC in the reference) is ARU_EUNSUP: enlarge on the host.  The destination size is
+ * (cvRound(src_h*sc), cvRound(src_w*sc)) = aru_scaled_size().
+ *   aru_scale_pages       uint8 [n,src_h,src_w,channels] -> uint8 [n,h,w,channels], host memory in and out
+ *   aru_separator_images  = scale_image + aru_separator_pages in one call: the unscaled uint8 images go up, the
+ *                           outputs have the scaled size (sc == 1: no resize, as in the reference)
+ */
+int aru_scaled_size(int src_h, int src_w, double sc, int* h, int* w);
+int aru_scale_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int src_h, int src_w, double sc, uint8_t* out);
+int aru_separator_images(aru_engine* e, const uint8_t* images, int channels, int n, int src_h, int src_w, double sc,
+                         double thr, float* out, uint8_t* out_u8, uint8_t* out_mask, uint8_t* horizontal, uint8_t* vertical);
+
 /* post_process alone on n thresholded masks (uint8 [n,h,w], non-zero = foreground), host memory in and out. */
 int aru_separator_post(aru_engine* e, const uint8_t* mask, int n, int h, int w, uint8_t* horizontal, uint8_t* vertical);
 

@@ -115,3 +115,23 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "post_heading_lines.npz"), u8=u8map, scale=sc, polygons=np.array(polys),
                         bboxes=np.array(bboxes), probs=np.array(probs, np.float64))
     print("post_heading_lines:", len(probs), "text lines")
+
+    # scale_image (helper.py:14-25), shrinking case, by the reference itself (it calls cv2.resize INTER_AREA)
+    from article_separation.image_segmentation.net_post_processing.net_post_processing_helper import \
+        scale_image as ref_scale_image
+    from oracle import resize_oracle as R
+    rng = np.random.default_rng(21)
+    cases = {}
+    for name, (sh, sw, ch, fixed_height) in {"general_bgr": (173, 131, 3, 96), "general_gray": (211, 160, 1, 150),
+                                             "half_bgr": (192, 130, 3, 96), "third_bgr": (180, 123, 3, 60),
+                                             "slight_bgr": (101, 97, 3, 100)}.items():
+        img = rng.integers(0, 256, size=(sh, sw, ch) if ch == 3 else (sh, sw), dtype=np.uint8)
+        scaled, sc = ref_scale_image(img, fixed_height=fixed_height, scaling_factor=1.0)
+        assert sc < 1.0
+        mine = R.resize_area(img, sc)
+        assert mine.shape == scaled.shape and np.array_equal(mine, scaled), name
+        cases[name + "_src"] = img
+        cases[name + "_dst"] = scaled
+        cases[name + "_sc"] = np.float64(sc)
+    np.savez_compressed(os.path.join(HERE, "post_resize.npz"), **cases)
+    print("post_resize:", len(cases) // 3, "cases")

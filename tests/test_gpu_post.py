@@ -307,3 +307,44 @@ def test_cc_filter_thresholds_and_batches(eng):
         got = eng.cc_size_filter(masks, min_size)
         for i in range(len(masks)):
             assert np.array_equal(got[i], O.cc_size_filter(masks[i], min_size)), (min_size, i)
+
+
+def test_scale_pages_matches_reference_scale_image(eng):
+    """aru_scale_pages against the golden outputs of the reference's scale_image (cv2.resize INTER_AREA): general and
+    integer scales, gray and BGR."""
+    z = np.load(os.path.join(GOLDEN, "post_resize.npz"))
+    names = sorted(k[:-4] for k in z.files if k.endswith("_src"))
+    for name in names:
+        got = eng.scale_pages(z[name + "_src"], float(z[name + "_sc"]))
+        assert np.array_equal(got[0], z[name + "_dst"]), name
+
+
+def test_scale_pages_against_oracle_batches_and_sizes(eng):
+    from aru_b200.engine import EngineError
+    from oracle import resize_oracle as R
+    rng = np.random.default_rng(8)
+    for sh, sw, ch, sc in ((300, 217, 3, 0.41), (257, 199, 1, 0.77), (400, 300, 3, 0.375), (128, 96, 3, 0.5),
+                           (243, 181, 3, 1 / 3), (240, 160, 1, 0.25), (1000, 750, 3, 1500 / 4000)):
+        imgs = rng.integers(0, 256, size=(3, sh, sw, 3) if ch == 3 else (3, sh, sw), dtype=np.uint8)
+        got = eng.scale_pages(imgs, sc)
+        for i in range(3):
+            assert np.array_equal(got[i], R.resize_area(imgs[i], sc)), (sh, sw, ch, sc, i)
+    with pytest.raises(EngineError):
+        eng.scale_pages(np.zeros((64, 64), np.uint8), 1.5)       # enlarging is INTER_CUBIC: host
+
+
+def test_separator_images_is_scale_image_plus_separator_pages(eng):
+    """uint8 BGR images at scan size in; == scale_image -> colour step -> net -> uint8 -> threshold -> post_process."""
+    from aru_b200.synth import synth_page
+    from oracle import resize_oracle as R
+    n, sh, sw = 4, 700, 520
+    gray = np.stack([synth_page(sh, sw, seed=90 + i) for i in range(n)])
+    images = np.stack([gray, gray, gray], axis=-1)
+    sc = 256 / sh
+    r = eng.separator_images(images, sc, want_u8=True, want_mask=True)
+    scaled = np.stack([R.resize_area(images[i], sc) for i in range(n)])
+    r2 = eng.separator_pages(scaled, want_u8=True, want_mask=True)
+    for k in ("u8", "mask", "horizontal", "vertical"):
+        assert np.array_equal(r[k], r2[k]), k
+    r3 = eng.separator_images(scaled, 1.0, want_u8=True)          # sc == 1: no resize, as in the reference
+    assert np.array_equal(r3["u8"], r2["u8"])

@@ -116,3 +116,23 @@ def test_heading_box_feature_fixture():
     assert O.box_sum_u8(u8, 170, 400, 250, 999) == int(u8[170:, 250:, 0].astype(np.int64).sum())
     assert O.box_sum_u8(u8, -5, 180, 0, 3) == int(u8[175:180, 0:3, 0].astype(np.int64).sum())
     assert O.box_sum_u8(u8, 50, 40, 0, 10) == 0
+
+
+def test_resize_oracle_reproduces_reference_scale_image():
+    """oracle/resize_oracle.py against the outputs of the reference's own scale_image (cv2.resize INTER_AREA)."""
+    from oracle import resize_oracle as R
+    z = np.load(os.path.join(GOLDEN, "post_resize.npz"))
+    names = sorted(k[:-4] for k in z.files if k.endswith("_src"))
+    assert len(names) >= 5
+    for name in names:
+        got = R.resize_area(z[name + "_src"], float(z[name + "_sc"]))
+        assert np.array_equal(got, z[name + "_dst"]), name
+
+
+def test_resize_oracle_against_opencv():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import resize_oracle as R
+    rng = np.random.default_rng(4)
+    for sh, sw, sc in ((97, 131, 0.73), (200, 150, 0.375), (120, 90, 0.5), (150, 93, 1 / 3), (64, 64, 0.25), (333, 77, 0.9017)):
+        img = rng.integers(0, 256, size=(sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(R.resize_area(img, sc), cv2.resize(img, None, fx=sc, fy=sc, interpolation=cv2.INTER_AREA)), (sh, sw, sc)
