@@ -90,6 +90,7 @@ struct Plan {
   bool d2h_pending[2] = {false, false};
   int launches = 0;
   uint64_t last_use = 0;
+  int eager_passes[2] = {0, 0};   // passes enqueued without a graph, per parity (the graph is captured on the second)
 };
 
 }  // namespace
@@ -698,25 +699,9 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     if (e->ops[i].kind == ARU_OP_COPY) p->launches += cdiv(e->ops[i].in.ch, 8) - 1;
     else if (p->tc[i].size() > 1 && !(p->band[i].ok && p->use_band[i])) p->launches += (int)p->tc[i].size() - 1;
   for (int i = 0; i < no; ++i) p->launches -= p->skip[i];
-  if (e->use_graph) {
-    for (int par = 0; par < 2; ++par) {
-      cudaGraph_t g = nullptr;
-      CU(e, cudaStreamBeginCapture(e->s_comp, cudaStreamCaptureModeThreadLocal));
-      rc = run_all(e, p.get(), par, e->s_comp);
-      cudaError_t err = cudaStreamEndCapture(e->s_comp, &g);
-      if (rc || err != cudaSuccess) {
-        if (g) cudaGraphDestroy(g);
-        free_plan(p.get());
-        return rc ? rc : fail(e, ARU_ECUDA, "graph capture failed: %s", cudaGetErrorString(err));
-      }
-      err = cudaGraphInstantiate(&p->graph[par], g, 0);
-      cudaGraphDestroy(g);
-      if (err != cudaSuccess) {
-        free_plan(p.get());
-        return fail(e, ARU_ECUDA, "graph instantiation failed: %s", cudaGetErrorString(err));
-      }
-    }
-  }
+  // CUDA graphs are captured lazily, on the second pass of a plan and parity (enqueue_forward): pages scaled to a fixed
+  // height differ in width from scan to scan, and a shape that is met once should not pay for two captures and
+  // instantiations (they were half of the ~15 ms a new shape costs)
   *out = p.get();
   e->plans.push_back(std::move(p));
   return ARU_OK;
@@ -729,25 +714,60 @@ int get_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       *out = p.get();
       return ARU_OK;
     }
-  if (e->plans.size() >= 4) {  // evict the least recently used plan
-    size_t lru = 0;
-    for (size_t i = 1; i < e->plans.size(); ++i)
-      if (e->plans[i]->last_use < e->plans[lru]->last_use) lru = i;
+  // at most 8 plans and ~96 GB of arenas per engine; the least recently used ones go first (never the new one)
+  auto evict_lru = [&](const Plan* keep) {
+    size_t lru = e->plans.size();
+    for (size_t i = 0; i < e->plans.size(); ++i)
+      if (e->plans[i].get() != keep && (lru == e->plans.size() || e->plans[i]->last_use < e->plans[lru]->last_use)) lru = i;
+    if (lru == e->plans.size()) return false;
     cudaDeviceSynchronize();
     if (e->cur == e->plans[lru].get()) e->cur = nullptr;
     free_plan(e->plans[lru].get());
     e->plans.erase(e->plans.begin() + lru);
-  }
+    return true;
+  };
+  if (e->plans.size() >= 8) evict_lru(nullptr);
   int rc = build_plan(e, n, h, w, out);
+  if (rc == ARU_ENOMEM && evict_lru(nullptr)) {   // make room and try once more
+    while (e->plans.size() > 0 && evict_lru(nullptr)) {}
+    rc = build_plan(e, n, h, w, out);
+  }
   if (rc) return rc;
   (*out)->last_use = ++e->tick;
+  for (;;) {
+    size_t total = 0;
+    for (auto& p : e->plans) total += p->arena_bytes;
+    if (total <= ((size_t)96 << 30) || !evict_lru(*out)) break;
+  }
+  return ARU_OK;
+}
+
+int capture_graph(aru_engine* e, Plan* p, int par, cudaStream_t st) {
+  cudaGraph_t g = nullptr;
+  CU(e, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = run_all(e, p, par, st);
+  cudaError_t err = cudaStreamEndCapture(st, &g);
+  if (rc || err != cudaSuccess) {
+    if (g) cudaGraphDestroy(g);
+    return rc ? rc : fail(e, ARU_ECUDA, "graph capture failed: %s", cudaGetErrorString(err));
+  }
+  err = cudaGraphInstantiate(&p->graph[par], g, 0);
+  cudaGraphDestroy(g);
+  if (err != cudaSuccess) return fail(e, ARU_ECUDA, "graph instantiation failed: %s", cudaGetErrorString(err));
   return ARU_OK;
 }
 
 int enqueue_forward(aru_engine* e, Plan* p, int parity, cudaStream_t st) {
-  if (e->use_graph && p->graph[parity]) {
-    CU(e, cudaGraphLaunch(p->graph[parity], st));
-    return ARU_OK;
+  if (e->use_graph) {
+    if (!p->graph[parity] && p->eager_passes[parity] >= 1) {   // second pass of this plan and parity: worth a graph
+      const int rc = capture_graph(e, p, parity, st);
+      if (rc) return rc;
+    }
+    if (p->graph[parity]) {
+      CU(e, cudaGraphLaunch(p->graph[parity], st));
+      return ARU_OK;
+    }
+    ++p->eager_passes[parity];
   }
   return run_all(e, p, parity, st);
 }
@@ -903,7 +923,6 @@ int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
   int k1 = 0, kv = 0, k2 = 0;
   separator_kernel_sizes(h, w, &k1, &kv, &k2);
   int slot = 0;
-  std::vector<Plan*> used;
   // Micro-batch schedule.  The host->device copy of the first micro-batch and the device->host copy of the last one
   // cannot overlap with compute, so those two are a quarter of the size: [mb/4, mb, ..., mb, (rest), mb/4].
   std::vector<int> sched;
@@ -923,7 +942,6 @@ int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
     int rc = get_plan(e, cnt, h, w, &p);
     if (rc) return rc;
     e->cur = p;
-    if (std::find(used.begin(), used.end(), p) == used.end()) used.push_back(p);
     const bool want_u8 = io.out_u8 != nullptr || io.n_boxes > 0;
     rc = ensure_quant(e, p, want_u8, want_mask);
     if (rc) return rc;
@@ -1005,7 +1023,7 @@ int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
   }
   CU(e, cudaStreamSynchronize(e->s_d2h));
   CU(e, cudaStreamSynchronize(e->s_comp));
-  for (Plan* p : used) p->d2h_pending[0] = p->d2h_pending[1] = false;
+  for (auto& pl : e->plans) pl->d2h_pending[0] = pl->d2h_pending[1] = false;   // everything has completed
   return check_err_flag(e);
 }
 
