@@ -1391,6 +1391,46 @@ int aru_heading_pages(aru_engine* e, const uint8_t* pages, int channels, int n, 
   return rc;
 }
 
+int aru_heading_images(aru_engine* e, const uint8_t* images, int channels, int n, int src_h, int src_w, double sc,
+                       const int32_t* boxes, int n_boxes, uint64_t* sums, uint8_t* out_u8) {
+  if (!e || !images || n <= 0 || src_h <= 0 || src_w <= 0 || (channels != 1 && channels != 3) || n_boxes < 0 ||
+      (n_boxes > 0 && (!boxes || !sums)))
+    return e ? fail(e, ARU_EINVAL, "aru_heading_images: bad argument") : ARU_EINVAL;
+  if (sc == 1.0) return aru_heading_pages(e, images, channels, n, src_h, src_w, boxes, n_boxes, sums, out_u8);
+  CU(e, cudaSetDevice(e->device));
+  ScalePlan sp;
+  int rc = make_scale_plan(e, src_h, src_w, sc, &sp);
+  if (rc) return rc;
+  rc = check_boxes(e, boxes, n_boxes, n, sp.dh, sp.dw);
+  int* boxes_dev = nullptr;
+  unsigned long long* sums_dev = nullptr;
+  if (rc == ARU_OK && n_boxes > 0) {
+    if (cudaMalloc((void**)&boxes_dev, (size_t)n_boxes * 5 * sizeof(int)) || cudaMalloc((void**)&sums_dev, (size_t)n_boxes * 8))
+      rc = fail(e, ARU_ENOMEM, "aru_heading_images: device allocation failed");
+    else
+      cudaMemcpyAsync(boxes_dev, boxes, (size_t)n_boxes * 5 * sizeof(int), cudaMemcpyHostToDevice, e->s_comp);
+  }
+  if (rc == ARU_OK) {
+    HostIO io;
+    io.scale = &sp;
+    io.in_u8 = images;
+    io.channels = channels;
+    io.out_u8 = out_u8;
+    io.boxes_dev = boxes_dev;
+    io.n_boxes = n_boxes;
+    io.sums_dev = sums_dev;
+    rc = forward_host(e, io, n, sp.dh, sp.dw);
+  }
+  if (rc == ARU_OK && n_boxes > 0) {
+    cudaError_t err = cudaMemcpy(sums, sums_dev, (size_t)n_boxes * 8, cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) rc = fail(e, ARU_ECUDA, "aru_heading_images: %s", cudaGetErrorString(err));
+  }
+  cudaFree(boxes_dev);
+  cudaFree(sums_dev);
+  free_scale_plan(&sp);
+  return rc;
+}
+
 int aru_box_sums(aru_engine* e, const uint8_t* u8, int n, int h, int w, int c, const int32_t* boxes, int n_boxes,
                  uint64_t* sums) {
   if (!e || !u8 || n <= 0 || h <= 0 || w <= 0 || c <= 0 || n_boxes < 0 || (n_boxes > 0 && (!boxes || !sums)))

@@ -29,7 +29,7 @@ EXPORTS = [
     "aru_plan", "aru_forward", "aru_forward_device", "aru_sync", "aru_launches_per_forward", "aru_read_buffer",
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
     "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
-    "aru_box_sums", "aru_cc_filter", "aru_scaled_size", "aru_scale_pages", "aru_separator_images",
+    "aru_box_sums", "aru_cc_filter", "aru_scaled_size", "aru_scale_pages", "aru_separator_images", "aru_heading_images",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def load_library() -> ctypes.CDLL:
         lib.aru_scaled_size.argtypes = [i32, i32, ctypes.c_double, ctypes.POINTER(i32), ctypes.POINTER(i32)]
         lib.aru_scale_pages.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.c_double, vp]
         lib.aru_separator_images.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp]
+        lib.aru_heading_images.argtypes = [vp, vp, i32, i32, i32, i32, ctypes.c_double, vp, i32, vp, vp]
         lib.aru_sync.argtypes = [vp]
         lib.aru_launches_per_forward.argtypes = [vp]
         lib.aru_read_buffer.argtypes = [vp, i32, i32, fp, sz]
@@ -359,6 +360,22 @@ class Engine:
         self._check(self.lib.aru_heading_pages(self.handle, ctypes.c_void_p(x.ctypes.data), ch, n, h, w,
                                                ctypes.c_void_p(bx.ctypes.data), len(bx), ctypes.c_void_p(sums.ctypes.data),
                                                ctypes.c_void_p(u8.ctypes.data) if u8 is not None else None))
+        return (sums, bx, u8) if want_u8 else (sums, bx)
+
+    def heading_images(self, images: np.ndarray, sc: float, boxes, want_u8: bool = False):
+        """``heading_pages`` with ``scale_image`` (sc < 1, INTER_AREA) in front, on the device: unscaled uint8 images in;
+        ``boxes`` are in the coordinates of the scaled page (the reference rescales the text-line polygons by the same
+        factor, heading_net_post_processor.py:262-263)."""
+        x, n, h, w, ch = self._as_pages(images)
+        x = np.ascontiguousarray(x)
+        dh, dw = (h, w) if sc == 1.0 else self.scaled_size(h, w, sc)
+        bx = self.clip_boxes(boxes, dh, dw)
+        sums = np.zeros(len(bx), np.uint64)
+        u8 = pinned_empty((n, dh, dw, self.n_class), np.uint8) if want_u8 else None
+        self._check(self.lib.aru_heading_images(self.handle, ctypes.c_void_p(x.ctypes.data), ch, n, h, w,
+                                                ctypes.c_double(sc), ctypes.c_void_p(bx.ctypes.data), len(bx),
+                                                ctypes.c_void_p(sums.ctypes.data),
+                                                ctypes.c_void_p(u8.ctypes.data) if u8 is not None else None))
         return (sums, bx, u8) if want_u8 else (sums, bx)
 
     def box_sums(self, u8: np.ndarray, boxes) -> np.ndarray:

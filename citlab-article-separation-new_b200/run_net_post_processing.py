@@ -101,6 +101,35 @@ def _run_page(eng, image, args, fixed_height):
     return eng.separator_pages(image, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
 
 
+def _run_heading_page(eng, image, image_path, args, fixed_height):
+    """Heading mode for one decoded page: the net's uint8 map and, when ``<dir>/page/<stem>.xml`` exists, the network
+    feature of every TextLine - ``get_net_prob_for_text_line`` (heading_net_post_processor.py:247-270), box sums on the
+    device.  Returns (uint8 map [H,W,C], {text line id: probability} or None, scale, (H, W))."""
+    from . import page_textlines as T
+    sc = net_boundary._scaling_factor(image.shape[0], image.shape[1], args.scaling_factor, fixed_height=fixed_height)
+    page_xml = T.page_path_for_image(image_path)
+    lines = T.read_textlines(page_xml) if os.path.exists(page_xml) else []
+    boxed = [(lid, T.textline_box(pts, sc)) for lid, pts in lines if pts]
+    boxes = [(0, y, y + h, x, x + w) for _, (x, y, w, h) in boxed]
+    res = None
+    if sc < 1.0:
+        try:
+            res = eng.heading_images(image, sc, boxes, want_u8=True)
+        except EngineError as err:
+            if err.code != ARU_EUNSUP:
+                raise
+    if res is None:
+        scaled = net_boundary.scale_image(image, fixed_height, args.scaling_factor)[0]
+        res = eng.heading_pages(scaled, boxes, want_u8=True)
+    sums, _, u8 = res
+    probs = None
+    if lines:
+        probs = {lid: 0 for lid, pts in lines if not pts}          # no surrounding polygon: 0 (head:259-260)
+        for (lid, (x, y, w, h)), s_ in zip(boxed, sums):
+            probs[lid] = T.net_prob(int(s_), w, h)
+    return u8[0], probs, sc, u8.shape[1:3]
+
+
 def run_rank(args, rank: int, world: int, local_rank: int) -> int:
     paths = net_boundary.load_image_paths(args.path_to_image_list)
     shard = sharding.shard_for_rank(paths, world, rank, _pixel_counts(paths))
@@ -137,8 +166,18 @@ def run_rank(args, rank: int, world: int, local_rank: int) -> int:
     for path in shard:
         if path in done:
             continue
-        r, sc, shape = _run_page(eng, cv2.imread(path), args, fixed_height)
         stem = os.path.splitext(os.path.basename(path))[0]
+        if args.mode == "heading":
+            u8, probs, sc, shape = _run_heading_page(eng, cv2.imread(path), path, args, fixed_height)
+            cv2.imwrite(os.path.join(args.dump_dir, stem + "_prob.png"), np.ascontiguousarray(u8[:, :, 0]))
+            if probs is not None:
+                with open(os.path.join(args.dump_dir, stem + "_textlines.json"), "w") as f:
+                    json.dump(probs, f)
+            done[path] = {"scale": sc, "shape": list(shape)}
+            with open(manifest_path, "w") as f:
+                json.dump({"rank": rank, "world": world, "pages": done}, f)
+            continue
+        r, sc, shape = _run_page(eng, cv2.imread(path), args, fixed_height)
         cv2.imwrite(os.path.join(args.dump_dir, stem + "_prob.png"), np.ascontiguousarray(r["u8"][0, :, :, 0]))
         if args.mode == "separator":
             cv2.imwrite(os.path.join(args.dump_dir, stem + "_mask.png"), np.ascontiguousarray(r["mask"][0]))

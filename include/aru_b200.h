@@ -165,6 +165,10 @@ int aru_separator_pages(aru_engine* e, const uint8_t* pages, int channels, int n
 int aru_heading_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, const int32_t* boxes,
                       int n_boxes, uint64_t* sums, uint8_t* out_u8);
 
+/* scale_image (sc < 1, INTER_AREA) + aru_heading_pages in one call; boxes are in the coordinates of the scaled page. */
+int aru_heading_images(aru_engine* e, const uint8_t* images, int channels, int n, int src_h, int src_w, double sc,
+                       const int32_t* boxes, int n_boxes, uint64_t* sums, uint8_t* out_u8);
+
 /* The box sums alone on a host uint8 map [n,h,w,c] (channel 0 is summed). */
 int aru_box_sums(aru_engine* e, const uint8_t* u8, int n, int h, int w, int c, const int32_t* boxes, int n_boxes,
                  uint64_t* sums);

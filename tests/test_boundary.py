@@ -105,3 +105,26 @@ def test_install_rebinds_the_reference_modules(monkeypatch):
     assert SeparatorNetPostProcessor.post_process is net_boundary.separator_post_process
     import importlib
     assert importlib.import_module(net_boundary.REFERENCE_MODULE) is net_boundary
+
+
+def test_textline_boxes_match_reference_polygon_code(tmp_path):
+    """textline_box against the bounding boxes the reference's Polygon.rescale / get_bounding_box produced for the golden
+    text lines (tests/golden/post_heading_lines.npz), and the stdlib PAGE-XML reader."""
+    import os
+    from aru_b200 import page_textlines as T
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "post_heading_lines.npz"))
+    sc = float(z["scale"])
+    for poly, bbox in zip(z["polygons"], z["bboxes"]):
+        pts = list(zip(poly[:4].tolist(), poly[4:].tolist()))
+        assert T.textline_box(pts, sc) == tuple(int(v) for v in bbox)
+    xml = tmp_path / "page" / "scan_7.xml"
+    xml.parent.mkdir()
+    xml.write_text('<?xml version="1.0"?><PcGts xmlns="http://schema.primaresearch.org/PAGE/gts/pagecontent/2013-07-15">'
+                   '<Page imageFilename="scan_7.png" imageWidth="100" imageHeight="80"><TextRegion id="r1">'
+                   '<TextLine id="l1"><Coords points="10,20 90,22 95,60 12,58"/></TextLine>'
+                   '<TextLine id="l2"/></TextRegion></Page></PcGts>')
+    assert T.page_path_for_image(str(tmp_path / "scan_7.png")) == str(xml)
+    lines = T.read_textlines(str(xml))
+    assert lines == [("l1", [(10, 20), (90, 22), (95, 60), (12, 58)]), ("l2", None)]
+    assert T.textline_box(lines[0][1], 0.5) == (5, 10, 43, 21)      # the values the reference printed for this polygon
+    assert abs(T.net_prob(255 * 43 * 21, 43, 21) - 1.0) < 1e-15

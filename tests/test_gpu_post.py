@@ -375,3 +375,38 @@ def test_separator_masks_engine_network_vs_oracle_network(eng):
           f"{min(agree_sep):.5f}..{max(agree_sep):.5f}, identical pages {identical}/{n}")
     assert min(agree_mask) >= 0.999
     assert min(agree_sep) >= 0.995
+
+
+def test_cli_heading_mode_writes_text_line_features(built_lib, tmp_path):
+    """--mode heading --dump_dir with a PAGE-XML next to the image: per-TextLine network feature as the reference's
+    get_net_prob_for_text_line computes it (device resize + net + box sums), checked against the written uint8 map."""
+    cv2 = pytest.importorskip("cv2")
+    import json
+    from aru_b200 import page_textlines as T
+    from aru_b200 import run_net_post_processing as cli
+    from aru_b200.synth import synth_page, synth_pb
+    from oracle import separator_post_oracle as O
+    gray = synth_page(400, 300, seed=5)
+    img = tmp_path / "scan.png"
+    cv2.imwrite(str(img), gray)
+    (tmp_path / "page").mkdir()
+    lines = {"l0": "20,30 280,32 282,70 22,68", "l1": "40,200 250,205 251,260 41,255", "l2": "0,380 299,380 299,399 0,399"}
+    xml = "".join(f'<TextLine id="{k}"><Coords points="{v}"/></TextLine>' for k, v in lines.items())
+    (tmp_path / "page" / "scan.xml").write_text(
+        '<PcGts xmlns="http://schema.primaresearch.org/PAGE/gts/pagecontent/2013-07-15"><Page><TextRegion id="r">'
+        + xml + '<TextLine id="l3"/></TextRegion></Page></PcGts>')
+    lst = tmp_path / "pages.lst"
+    lst.write_text(str(img) + "\n")
+    pb = tmp_path / "heading.pb"
+    pb.write_bytes(synth_pb("heading"))
+    out = tmp_path / "out"
+    assert cli.main(["--path_to_image_list", str(lst), "--path_to_pb", str(pb), "--mode", "heading",
+                     "--fixed_height", "200", "--dump_dir", str(out)]) == 0
+    prob = cv2.imread(str(out / "scan_prob.png"), cv2.IMREAD_GRAYSCALE)
+    assert prob.shape == (200, 150)
+    got = json.loads((out / "scan_textlines.json").read_text())
+    assert set(got) == {"l0", "l1", "l2", "l3"} and got["l3"] == 0
+    for lid, pts in lines.items():
+        poly = [tuple(int(v) for v in p.split(",")) for p in pts.split()]
+        x, y, w, h = T.textline_box(poly, 0.5)
+        assert abs(got[lid] - O.net_prob_for_box(prob, x, y, w, h)) < 1e-12
