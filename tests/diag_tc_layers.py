@@ -1,4 +1,4 @@
-"""GPU diagnostic: per-layer comparison of the tcgen05 conv path against the CUDA-core path and the oracle.
+"""GPU diagnostic (test infrastructure: it uses the CPU oracle, so it lives under tests/): per-layer comparison of the tcgen05 conv path against the CUDA-core path and the oracle.
 Prints one line per lowered op; for mismatching ops a summary of where the errors are."""
 import os
 import sys
