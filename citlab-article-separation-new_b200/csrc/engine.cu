@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -429,6 +430,12 @@ int check_err_flag(aru_engine* e) {
 }
 
 int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
+  // ARU_PLAN_TRACE=1: where the time of meeting a new shape goes (stderr)
+  static const bool trace = [] { const char* v = getenv("ARU_PLAN_TRACE"); return v && v[0] == '1'; }();
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  };
   std::unique_ptr<Plan> p(new Plan);
   p->n = n; p->h = h; p->w = w;
   const int nb = (int)e->buffers.size(), no = (int)e->ops.size();
@@ -518,6 +525,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     off += (b.bytes + 255) / 256 * 256;
   }
   p->arena_bytes = std::max<size_t>(off, 256);
+  const double t_shapes = ms_since(t_begin);
   CU(e, cudaMalloc((void**)&p->arena, p->arena_bytes));
   CU(e, cudaMemsetAsync(p->arena, 0, p->arena_bytes, e->s_comp));
   const size_t in_bytes = (size_t)n * h * w * sizeof(float);
@@ -530,6 +538,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     CU(e, cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
     CU(e, cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming));
   }
+  const double t_alloc = ms_since(t_begin);
   // row-banded tensor-core plan of conv op i (+ its banded weight masters, cached per engine)
   auto plan_band = [&](int i, const Geo& geo) -> int {
     const aru_op& op = e->ops[i];
@@ -683,6 +692,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       }
     }
   }
+  const double t_kernels = ms_since(t_begin);
   // one eager pass (sets function attributes, validates every launch), then capture
   rc = run_all(e, p.get(), 0, e->s_comp);
   if (rc) { free_plan(p.get()); return rc; }
@@ -699,6 +709,10 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     if (e->ops[i].kind == ARU_OP_COPY) p->launches += cdiv(e->ops[i].in.ch, 8) - 1;
     else if (p->tc[i].size() > 1 && !(p->band[i].ok && p->use_band[i])) p->launches += (int)p->tc[i].size() - 1;
   for (int i = 0; i < no; ++i) p->launches -= p->skip[i];
+  if (trace)
+    fprintf(stderr, "plan %dx%dx%d: shapes %.2f ms, allocations %.2f ms (arena %.2f GB), kernel plans / weights / timing %.2f ms, "
+            "first pass %.2f ms\n", n, h, w, t_shapes, t_alloc - t_shapes, p->arena_bytes / 1e9, t_kernels - t_alloc,
+            ms_since(t_begin) - t_kernels);
   // CUDA graphs are captured lazily, on the second pass of a plan and parity (enqueue_forward): pages scaled to a fixed
   // height differ in width from scan to scan, and a shape that is met once should not pay for two captures and
   // instantiations (they were half of the ~15 ms a new shape costs)

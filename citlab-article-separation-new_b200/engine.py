@@ -114,9 +114,19 @@ class _PinnedPool:
                 return
         load_library().aru_host_free(ctypes.c_void_p(ptr))
 
+    @staticmethod
+    def _bucket(nbytes: int) -> int:
+        """Size class of a block: multiples of 64 KB up to 1 MB, then eighths of a power of two (<= 12.5 % slack).
+        Page-locking costs ~0.25 ms per MB, and pages scaled to a fixed height differ slightly in width from scan to
+        scan - exact-size blocks would never be reused in such a stream."""
+        if nbytes <= (1 << 20):
+            return -(-nbytes // (64 << 10)) * (64 << 10)
+        step = (1 << (nbytes.bit_length() - 1)) >> 3
+        return -(-nbytes // step) * step
+
     def empty(self, shape, dtype) -> np.ndarray:
         dtype = np.dtype(dtype)
-        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        nbytes = self._bucket(max(int(np.prod(shape)) * dtype.itemsize, 1))
         ptr = None
         with self.lock:
             lst = self.free.get(nbytes)

@@ -128,3 +128,15 @@ def test_textline_boxes_match_reference_polygon_code(tmp_path):
     assert lines == [("l1", [(10, 20), (90, 22), (95, 60), (12, 58)]), ("l2", None)]
     assert T.textline_box(lines[0][1], 0.5) == (5, 10, 43, 21)      # the values the reference printed for this polygon
     assert abs(T.net_prob(255 * 43 * 21, 43, 21) - 1.0) < 1e-15
+
+
+def test_pinned_pool_size_classes():
+    from aru_b200.engine import _PinnedPool
+    b = _PinnedPool._bucket
+    assert b(1) == 64 << 10 and b(64 << 10) == 64 << 10 and b((64 << 10) + 1) == 128 << 10
+    for n in (1 << 20, (1 << 20) + 1, 13_200_000, 13_956_000, 1_610_612_736, 3 * (1 << 30) + 5):
+        c = b(n)
+        assert c >= n and c <= n * 1.125 + (64 << 10)
+    # page widths 1088..1201 at height 1500 (float32, 2 classes) fall into a handful of classes, not one per width
+    classes = {b(1500 * w * 2 * 4) for w in range(1088, 1202)}
+    assert len(classes) <= 3
