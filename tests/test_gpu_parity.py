@@ -250,3 +250,16 @@ def test_cli_dump_matches_the_engine(tmp_path, engines):
         stem = os.path.splitext(os.path.basename(p))[0]
         assert np.array_equal(cv2.imread(str(out / f"{stem}_prob.png"), cv2.IMREAD_UNCHANGED), u8[0, :, :, 0])
         assert np.array_equal(cv2.imread(str(out / f"{stem}_mask.png"), cv2.IMREAD_UNCHANGED), mask[0])
+
+
+def test_plan_cache_eviction_and_lazy_graphs(engines):
+    """More page shapes than the plan cache holds (8), each met one to three times: a plan's first pass runs eagerly, later
+    passes replay the CUDA graph captured on the second, evicted shapes are rebuilt - the results must not depend on any
+    of it."""
+    from aru_b200.synth import synth_page, page_to_net_input
+    eng = engines("tiny")
+    pages = {w: page_to_net_input(synth_page(48, w, seed=w)).astype(np.float32) for w in range(40, 52)}
+    first = {w: eng.forward(x)[0].copy() for w, x in pages.items()}          # 12 shapes: the early ones get evicted
+    for w, x in pages.items():                                               # rebuilt (eager), then graph, then graph
+        for _ in range(3):
+            assert np.array_equal(eng.forward(x)[0], first[w]), w
