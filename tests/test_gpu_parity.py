@@ -263,3 +263,26 @@ def test_plan_cache_eviction_and_lazy_graphs(engines):
     for w, x in pages.items():                                               # rebuilt (eager), then graph, then graph
         for _ in range(3):
             assert np.array_equal(eng.forward(x)[0], first[w]), w
+
+
+@pytest.mark.parametrize("n", [9, 13, 16, 23, 37])
+def test_micro_batch_schedules_cover_every_page_once(engines, n):
+    """The host-buffer call splits n pages into a head, full passes and a (ramped) tail; whatever the split, page i of the
+    batch must equal page i run alone - for the float32 outputs (ramped tail) and for the uint8 path (plain edges)."""
+    from aru_b200.engine import OPT_CONV_PATH, OPT_MICRO_BATCH
+    from aru_b200.synth import synth_page
+    eng = engines("separator")
+    eng.set_option(OPT_CONV_PATH, 0)
+    pages = np.stack([synth_page(64, 112, seed=500 + i) for i in range(n)])
+    x = (pages / 255.0).astype(np.float32)
+    eng.set_option(OPT_MICRO_BATCH, 0)
+    alone = np.stack([eng.forward(x[i])[0] for i in range(n)])
+    try:
+        for mb in (8, 16):
+            eng.set_option(OPT_MICRO_BATCH, mb)
+            got = eng.forward(x)
+            assert np.array_equal(got, alone), (n, mb)
+            r = eng.separator_pages(pages, want_u8=True, want_separators=False)
+            assert np.array_equal(r["u8"], (alone * 255).astype(np.uint8)), (n, mb)
+    finally:
+        eng.set_option(OPT_MICRO_BATCH, 0)
