@@ -5,6 +5,13 @@
  *   article_separation/image_segmentation/net_post_processing/net_post_processing_helper.py
  *     :36-53  load_graph(path_to_pb)            -> aru_create()  (+ the Python GraphDef loader)
  *     :56-72  get_net_output(image, graph, dev) -> aru_forward() (replaces tf.Session.run)
+ * and, one level up, for the integer steps either side of it:
+ *     :14-25  scale_image (sc < 1, cv2.resize INTER_AREA)          -> aru_scale_pages(), aru_separator_images(), aru_heading_images()
+ *     :31     cv2.cvtColor(BGR2GRAY) / 255.0                        -> aru_pages_to_input(), aru_separator_pages(), aru_heading_pages()
+ *     :75-78  apply_threshold; separator_net_post_processor.py:147  -> the uint8 / mask outputs of aru_forward() / aru_separator_pages()
+ *   region_net_post_processor_base.py:230-251  apply_cc_analysis   -> aru_cc_filter()
+ *   separator_net_post_processor.py:25-99      post_process        -> aru_separator_post(), aru_separator_pages()
+ *   heading_net_post_processor.py:247-270      get_net_prob_for_text_line -> aru_heading_pages(), aru_box_sums()
  * The reference has no FFI of its own (it is Python over TensorFlow 1.x), so these entry points are
  * what a ctypes binding in that helper module would bind; INTEGRATION.md shows the stub.
  *
