@@ -410,3 +410,27 @@ def test_cli_heading_mode_writes_text_line_features(built_lib, tmp_path):
         poly = [tuple(int(v) for v in p.split(",")) for p in pts.split()]
         x, y, w, h = T.textline_box(poly, 0.5)
         assert abs(got[lid] - O.net_prob_for_box(prob, x, y, w, h)) < 1e-12
+
+
+def test_page_level_calls_with_a_one_class_sigmoid_net(built_lib):
+    """A graph whose output is a 1-channel sigmoid (n_class = 1): the page-level calls take the generic quantize path."""
+    from aru_b200.engine import Engine
+    from aru_b200.synth import synth_page, synth_pb
+    from oracle import separator_post_oracle as O
+    e = Engine(synth_pb("tiny_sigmoid"), device=0)
+    try:
+        assert e.n_class == 1
+        pages = np.stack([synth_page(120, 200, seed=70 + i) for i in range(3)])
+        prob = e.forward(O.u8_to_net_input(pages))
+        r = e.separator_pages(pages, threshold=0.4, want_u8=True, want_mask=True)
+        assert r["u8"].shape == (3, 120, 200, 1) and np.array_equal(r["u8"], O.quantize_u8(prob))
+        assert np.array_equal(r["mask"], O.apply_threshold(r["u8"][..., 0], 0.4))
+        for i in range(3):
+            h_ref, v_ref = O.separator_post_process(r["mask"][i])
+            assert np.array_equal(r["horizontal"][i], h_ref) and np.array_equal(r["vertical"][i], v_ref)
+        boxes = [(0, 10, 60, 20, 180), (2, 0, 120, 0, 200), (1, 100, 130, 150, 260)]
+        sums, _ = e.heading_pages(pages, boxes)
+        for s, (pg, ya, yb, xa, xb) in zip(sums, boxes):
+            assert int(s) == O.box_sum_u8(r["u8"][pg], ya, yb, xa, xb)
+    finally:
+        e.close()
