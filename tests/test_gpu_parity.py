@@ -197,6 +197,13 @@ def test_full_size_page_against_oracle(engines, oracles):
     _check(engines("separator").forward(x)[0], oracles("separator").run(x)[0], "separator 1024x768")
 
 
+def test_full_size_page_heading_net_against_oracle(engines, oracles):
+    """BASELINE config 2: the same 1024x768 page through the heading net."""
+    from aru_b200.synth import synth_page, page_to_net_input
+    x = page_to_net_input(synth_page(1024, 768, 0))
+    _check(engines("heading").forward(x)[0], oracles("heading").run(x)[0], "heading 1024x768")
+
+
 def test_benchmark_size_properties(engines):
     """BASELINE config 3 shape (1856x1344): batch independence and determinism at full size."""
     from aru_b200.synth import synth_page, page_to_net_input
