@@ -70,6 +70,9 @@ struct Plan {
   std::vector<int> fused_pool;          // per conv op: the MAXPOOL op its row-banded launch also performs (-1: none)
   std::vector<char> skip;               // per op: performed by another op's launch
   std::vector<char> pool_only;          // per stem conv op with a fused pool: nothing else reads its full-resolution output
+  std::vector<int> pair_first;          // per conv op k: the conv op i whose launch it absorbs (conv_band2.cu), -1: none
+  std::vector<ConvBand2Plan> pair;      // per conv op k with pair_first[k] >= 0
+  std::vector<char> pair_store0;        // per conv op k: the stage-0 (op i) activated output must also be stored
   act_t* scratch = nullptr;             // partial sums of split-K launches
   size_t scratch_bytes = 0;
   std::vector<const char*> kernel;   // per op label
@@ -92,6 +95,10 @@ struct Plan {
   int launches = 0;
   uint64_t last_use = 0;
   int eager_passes[2] = {0, 0};   // passes enqueued without a graph, per parity (the graph is captured on the second)
+  Plan() = default;
+  Plan(const Plan&) = delete;
+  Plan& operator=(const Plan&) = delete;
+  ~Plan();   // releases the arena, staging buffers, events and graphs (every error return of build_plan relies on it)
 };
 
 }  // namespace
@@ -106,7 +113,7 @@ struct aru_engine {
   std::vector<OpWeights> opw;
   std::vector<int> kind;  // per buffer
   int input_buf = -1, output_buf = -1, n_class = 0;
-  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0;
+  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0;
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   int* err_flag = nullptr;
   float* zero_bias = nullptr;
@@ -223,26 +230,24 @@ int get_tc_image(aru_engine* e, int oi, const ConvTcPlan& tp, int begin, int chu
 }
 
 // ---- planning ------------------------------------------------------------------------------------
+// Idempotent: every pointer is cleared, so the explicit calls on error paths and the destructor can both run.
 void free_plan(Plan* p) {
   if (!p) return;
+  auto dev_free = [](auto*& q) { if (q) { cudaFree(q); q = nullptr; } };
+  auto ev_free = [](cudaEvent_t& ev) { if (ev) { cudaEventDestroy(ev); ev = nullptr; } };
   for (int i = 0; i < 2; ++i) {
-    if (p->graph[i]) cudaGraphExecDestroy(p->graph[i]);
-    if (p->in_dev[i]) cudaFree(p->in_dev[i]);
-    if (p->out_dev[i]) cudaFree(p->out_dev[i]);
-    if (p->u8_dev[i]) cudaFree(p->u8_dev[i]);
-    if (p->mask_dev[i]) cudaFree(p->mask_dev[i]);
-    if (p->page_dev[i]) cudaFree(p->page_dev[i]);
-    if (p->src_dev[i]) cudaFree(p->src_dev[i]);
-    if (p->hor_dev[i]) cudaFree(p->hor_dev[i]);
-    if (p->ver_dev[i]) cudaFree(p->ver_dev[i]);
-    if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
-    if (p->ev_comp[i]) cudaEventDestroy(p->ev_comp[i]);
-    if (p->ev_d2h[i]) cudaEventDestroy(p->ev_d2h[i]);
+    if (p->graph[i]) { cudaGraphExecDestroy(p->graph[i]); p->graph[i] = nullptr; }
+    dev_free(p->in_dev[i]); dev_free(p->out_dev[i]); dev_free(p->u8_dev[i]); dev_free(p->mask_dev[i]);
+    dev_free(p->page_dev[i]); dev_free(p->src_dev[i]); dev_free(p->hor_dev[i]); dev_free(p->ver_dev[i]);
+    ev_free(p->ev_h2d[i]); ev_free(p->ev_comp[i]); ev_free(p->ev_d2h[i]);
   }
-  if (p->arena) cudaFree(p->arena);
-  if (p->scratch) cudaFree(p->scratch);
-  if (p->post_scratch) cudaFree(p->post_scratch);
+  dev_free(p->arena); dev_free(p->scratch); dev_free(p->post_scratch);
+  p->src_dev_bytes = 0;
 }
+
+}  // namespace
+Plan::~Plan() { free_plan(this); }
+namespace {
 
 int set_dims(aru_engine* e, Plan* p, int buf, int h, int w, int op) {
   BufPlan& b = p->bufs[buf];
@@ -301,6 +306,19 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
         label = "conv_small";
         err = launch_conv_small(st, op.ksize, op.out.ch, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), ow.w32,
                                 ow.bias, bi.geo, op.act);
+      } else if (p->skip[oi]) {
+        label = "pair_fused";   // performed by the launch of the convolution that consumes it (conv_band2.cu)
+      } else if (p->pair_first[oi] >= 0) {
+        // two chained convolutions in one launch: op `fi` (stage 0) feeds this op through a shared-memory row FIFO
+        const int fi = p->pair_first[oi];
+        const aru_op& o0 = e->ops[fi];
+        const int pj = p->fused_pool[oi];
+        label = pj >= 0 ? "conv_band2_pool" : "conv_band2";
+        err = launch_conv_band2(st, p->pair[oi], make_pv(e, p, o0.in), p->pair_store0[oi] ? make_pv(e, p, o0.out) : PV(),
+                                make_pv(e, p, o0.out_pre), make_pv(e, p, op.out), make_pv(e, p, op.res), e->opw[fi].band_w,
+                                e->opw[fi].bias, o0.act, ow.band_w, ow.bias, op.act, bo.geo, e->err_flag,
+                                pj >= 0 ? make_pv(e, p, e->ops[pj].out) : PV(),
+                                pj >= 0 ? &p->bufs[e->ops[pj].out.buf].geo : nullptr);
       } else if (p->band[oi].ok && p->use_band[oi]) {
         const int pj = p->fused_pool[oi];
         label = pj >= 0 ? "conv_band_pool" : "conv_band";
@@ -446,6 +464,9 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   p->fused_pool.assign(no, -1);
   p->skip.assign(no, 0);
   p->pool_only.assign(no, 0);
+  p->pair_first.assign(no, -1);
+  p->pair.resize(no);
+  p->pair_store0.assign(no, 0);
   p->kernel.assign(no, "?");
   for (int i = 0; i < nb; ++i) {
     p->bufs[i].kind = e->kind[i];
@@ -540,10 +561,9 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   }
   const double t_alloc = ms_since(t_begin);
   // row-banded tensor-core plan of conv op i (+ its banded weight masters, cached per engine)
-  auto plan_band = [&](int i, const Geo& geo) -> int {
+  // banded weight masters of conv op i (they depend on the filter and on (ks, C_in, C_out) only; cached per engine)
+  auto band_weights = [&](int i, const ConvBandPlan& bp) -> int {
     const aru_op& op = e->ops[i];
-    ConvBandPlan bp = conv_band_plan(op.ksize, op.in.ch, op.out.ch, geo, e->num_sms, e->max_smem);
-    if (!bp.ok) return ARU_OK;
     OpWeights& ow = e->opw[i];
     if (!ow.band_w || ow.band_bytes != bp.wpack_bytes) {
       if (ow.band_w) { cudaFree(ow.band_w); ow.band_w = nullptr; }
@@ -555,6 +575,14 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       ow.band_w = reinterpret_cast<act_t*>(dev);
       ow.band_bytes = bp.wpack_bytes;
     }
+    return ARU_OK;
+  };
+  auto plan_band = [&](int i, const Geo& geo) -> int {
+    const aru_op& op = e->ops[i];
+    ConvBandPlan bp = conv_band_plan(op.ksize, op.in.ch, op.out.ch, geo, e->num_sms, e->max_smem);
+    if (!bp.ok) return ARU_OK;
+    int rc2 = band_weights(i, bp);
+    if (rc2) return rc2;
     p->band[i] = bp;
     p->use_band[i] = 1;
     return ARU_OK;
@@ -616,11 +644,15 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     }
   }
   if (p->scratch_bytes) CU(e, cudaMalloc((void**)&p->scratch, p->scratch_bytes));
-  // Ops both tensor-core kernels cover: time each on this plan's geometry and keep the faster (the timing does not
-  // depend on the data; ARU_AUTOTUNE=0 keeps the row-banded kernel wherever it applies).
+  // Ops both tensor-core kernels cover.
   {
+    // Default: a fixed rule (row-banded kernel for C_out <= 16, position-major above), so that a page gives the same
+    // bits in every process, rank and run - the two kernels round differently and masks near the 13/255 cut would
+    // flip.  ARU_AUTOTUNE=1 times both on this plan's geometry and keeps the faster (benchmarking only).
     const char* env = getenv("ARU_AUTOTUNE");
-    const bool tune = !(env && env[0] == '0');
+    const bool tune = env && env[0] == '1';
+    for (int i = 0; i < no && !tune; ++i)
+      if (p->band[i].ok && !p->tc[i].empty()) p->use_band[i] = p->band[i].cop <= 16 ? 1 : 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     for (int i = 0; i < no && tune; ++i) {
       if (!p->band[i].ok || p->tc[i].empty()) continue;
@@ -656,6 +688,47 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
     if ((rc = check_err_flag(e))) { free_plan(p.get()); return rc; }
   }
+  // Pairs of chained 3x3 convolutions with C_out = 8 / 16 run as one launch (conv_band2.cu): greedy in program order,
+  // op i -> its only consumer k.  The launch happens at k's position, so nothing between i and k may read i's outputs.
+  const char* fuse_env = getenv("ARU_FUSE_PAIRS");
+  if (e->conv_path == 0 && (e->fuse_pairs || (fuse_env && fuse_env[0] == '1'))) {
+    const bool fuse = true;
+    auto reads = [&](const aru_op& ro, int buf) {
+      if (ro.in.buf == buf || ro.res.buf == buf) return true;
+      if (ro.kind == ARU_OP_COMBINE)
+        for (int a = 0; a < ro.n_scales; ++a)
+          if (ro.att[a].buf == buf || ro.det[a].buf == buf) return true;
+      return false;
+    };
+    auto planar_conv3 = [&](const aru_op& o) {
+      return o.kind == ARU_OP_CONV && o.ksize == 3 && p->bufs[o.in.buf].kind == KIND_PLANAR &&
+             p->bufs[o.out.buf].kind == KIND_PLANAR && (o.act == ARU_ACT_NONE || o.act == ARU_ACT_RELU);
+    };
+    for (int i = 0; i < no && fuse; ++i) {
+      const aru_op& o0 = e->ops[i];
+      if (!planar_conv3(o0) || o0.res.buf >= 0 || p->skip[i] || p->pair_first[i] >= 0) continue;
+      // consumers of o0.out
+      int k = -1, n_readers = 0;
+      for (int j = i + 1; j < no; ++j)
+        if (reads(e->ops[j], o0.out.buf)) { if (k < 0) k = j; ++n_readers; }
+      if (k < 0) continue;
+      const aru_op& o1 = e->ops[k];
+      if (!planar_conv3(o1) || o1.out_pre.buf >= 0 || o1.in.buf != o0.out.buf || o1.in.ch_off != o0.out.ch_off ||
+          o1.in.ch != o0.out.ch || o1.out.ch != o0.out.ch || o1.res.buf == o0.out.buf)
+        continue;
+      bool clean = true;
+      for (int j = i + 1; j < k && clean; ++j)
+        clean = !(o0.out_pre.buf >= 0 && reads(e->ops[j], o0.out_pre.buf));
+      if (!clean) continue;
+      ConvBand2Plan pp = conv_band2_plan(o0.in.ch, o0.out.ch, o1.out.ch, p->bufs[o1.out.buf].geo, e->num_sms, e->max_smem);
+      if (!pp.ok) continue;
+      if ((rc = band_weights(i, pp.st0)) || (rc = band_weights(k, pp.st1))) { free_plan(p.get()); return rc; }
+      p->pair[k] = pp;
+      p->pair_first[k] = i;
+      p->pair_store0[k] = (n_readers > 1 || e->keep_all || o0.out.buf == e->output_buf) ? 1 : 0;
+      p->skip[i] = 1;
+    }
+  }
   // max-pools whose input is the ReLU'd output of a row-banded convolution are written by that launch
   {
     const char* env = getenv("ARU_FUSE_POOL");
@@ -666,8 +739,12 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       for (int i = j - 1; i >= 0; --i) {
         const aru_op& co = e->ops[i];
         if (co.out.buf != po.in.buf) continue;
-        if (co.kind == ARU_OP_CONV && co.out.ch_off == po.in.ch_off && co.out.ch == po.in.ch && p->band[i].ok &&
-            p->use_band[i] && p->fused_pool[i] < 0 && p->bufs[co.out.buf].kind == KIND_PLANAR &&
+        if (co.kind == ARU_OP_CONV && co.out.ch_off == po.in.ch_off && co.out.ch == po.in.ch && p->pair_first[i] >= 0 &&
+            p->fused_pool[i] < 0 && co.act == ARU_ACT_RELU) {
+          p->fused_pool[i] = j;
+          p->skip[j] = 1;
+        } else if (co.kind == ARU_OP_CONV && co.out.ch_off == po.in.ch_off && co.out.ch == po.in.ch && p->band[i].ok &&
+            p->use_band[i] && p->fused_pool[i] < 0 && p->bufs[co.out.buf].kind == KIND_PLANAR && !p->skip[i] &&
             conv_band_can_pool(p->band[i], co.act, co.in.ch, co.ksize)) {
           p->fused_pool[i] = j;
           p->skip[j] = 1;
@@ -927,7 +1004,23 @@ struct HostIO {
 };
 
 // Host-buffer forward: micro-batches, double-buffered device staging, copies on their own streams.
+int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w);
 int forward_host(aru_engine* e, const HostIO& io, int n, int h, int w) {
+  const int rc = forward_host_impl(e, io, n, h, w);
+  if (rc != ARU_OK) {
+    // A failure in the middle of the schedule leaves copies of earlier micro-batches in flight: drain the three streams
+    // before the caller may recycle its (pinned) buffers, and forget the pending flags.
+    const std::string msg = e->error;
+    cudaStreamSynchronize(e->s_h2d);
+    cudaStreamSynchronize(e->s_comp);
+    cudaStreamSynchronize(e->s_d2h);
+    cudaGetLastError();
+    for (auto& pl : e->plans) pl->d2h_pending[0] = pl->d2h_pending[1] = false;
+    e->error = msg;
+  }
+  return rc;
+}
+int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w) {
   CU(e, cudaSetDevice(e->device));
   const int mb = pick_micro_batch(e, n, h, w);
   const size_t page_px = (size_t)h * w;
@@ -1229,7 +1322,6 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
       if (e->conv_path != (int)value) {  // plans bake the kernel choice in
         cudaSetDevice(e->device);
         cudaDeviceSynchronize();
-        for (auto& p : e->plans) free_plan(p.get());
         e->plans.clear();
         e->cur = nullptr;
       }
@@ -1242,11 +1334,19 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
       if (e->keep_all != (value ? 1 : 0)) {
         cudaSetDevice(e->device);
         cudaDeviceSynchronize();
-        for (auto& p : e->plans) free_plan(p.get());
         e->plans.clear();
         e->cur = nullptr;
       }
       e->keep_all = value ? 1 : 0;
+      return ARU_OK;
+    case ARU_OPT_FUSE_PAIRS:
+      if (e->fuse_pairs != (value ? 1 : 0)) {
+        cudaSetDevice(e->device);
+        cudaDeviceSynchronize();
+        e->plans.clear();
+        e->cur = nullptr;
+      }
+      e->fuse_pairs = value ? 1 : 0;
       return ARU_OK;
     case ARU_OPT_MICRO_BATCH:
       if (value < 0 || value > 4096) return fail(e, ARU_EINVAL, "bad micro batch");

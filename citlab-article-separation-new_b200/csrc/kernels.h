@@ -151,6 +151,31 @@ inline bool conv_band_can_pool(const ConvBandPlan& plan, int act, int cin, int k
   return plan.ok && act == 1 && plan.R >= 2 && cin <= 32 && (ks == 3 || ks == 4);
 }
 
+// ---- two chained 3x3 convolutions in one launch (conv_band2.cu) ---------------------------------
+// conv (cin -> c) [+ pre-activation export] -> act -> conv (c -> c) [+ residual] -> act [-> 2x2 max-pool], c = 8 / 16;
+// the intermediate lives in a shared-memory row FIFO.  st0 / st1 describe the banded masters of the two stages
+// (conv_band_pack's layout).
+struct ConvBand2Plan {
+  bool ok = false;
+  int cin_chunks = 0, cop = 0, R = 0, J = 0;
+  int N = 0;             // UMMA N of both stages (multiple of 16, <= 128)
+  int n_out = 0;         // valid output columns per strip = N - 2
+  int n_strips = 0, n_ty = 0;
+  int S = 0;             // row slots of the input ring (even)
+  int RS = 0;            // row slots of the intermediate FIFO = 2R + 2
+  int nbuf0 = 2, nbuf1 = 2, acc_stride = 128;   // TMEM accumulator buffers per stage and their column stride
+  int grid = 0;
+  long long tiles = 0;
+  size_t smem_bytes = 0;
+  ConvBandPlan st0, st1;
+  const char* why = "";
+};
+ConvBand2Plan conv_band2_plan(int cin, int cmid, int cout, const Geo& g, int num_sms, size_t max_smem);
+// out0 / pre0: optional global copies of the stage-0 result (activated / pre-activation); res: stage-1 residual operand
+cudaError_t launch_conv_band2(cudaStream_t st, const ConvBand2Plan& plan, PV in, PV out0, PV pre0, PV out, PV res,
+                              const act_t* wpack0, const float* bias0, int act0, const act_t* wpack1, const float* bias1,
+                              int act1, const Geo& g, int* err_flag, PV pool = PV(), const Geo* pool_geo = nullptr);
+
 // host-side 16-bit conversion matching act_t
 uint16_t host_f_to_act(float v);
 

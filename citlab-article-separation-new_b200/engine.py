@@ -21,7 +21,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libaru_b200.so")
 
 ARU_OK, ARU_EINVAL, ARU_ECUDA, ARU_ENOMEM, ARU_EUNSUP, ARU_ENODEV = 0, 1, 2, 3, 4, 5
-OPT_CONV_PATH, OPT_USE_GRAPH, OPT_MICRO_BATCH, OPT_KEEP_ALL = 1, 2, 3, 4
+OPT_CONV_PATH, OPT_USE_GRAPH, OPT_MICRO_BATCH, OPT_KEEP_ALL, OPT_FUSE_PAIRS = 1, 2, 3, 4, 5
 
 # every symbol include/aru_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = [

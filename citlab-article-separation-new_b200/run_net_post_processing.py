@@ -143,11 +143,15 @@ def run_rank(args, rank: int, world: int, local_rank: int) -> int:
         if args.mode == "separator":
             from article_separation.image_segmentation.net_post_processing.separator_net_post_processor import \
                 SeparatorNetPostProcessor
+            # install() ran before this import, when the class did not exist yet: bind the device post-processing now
+            if not net_boundary.patch_separator_post_processor():
+                raise SystemExit("could not bind SeparatorNetPostProcessor.post_process to the B200 engine")
             SeparatorNetPostProcessor(shard, args.path_to_pb, fixed_height, args.scaling_factor, args.threshold,
                                       gpu_devices="").run()
         else:
             from article_separation.image_segmentation.net_post_processing.heading_net_post_processor import \
                 HeadingNetPostProcessor
+            net_boundary.patch_separator_post_processor()   # RegionNetPostProcessor.apply_cc_analysis on the device
             HeadingNetPostProcessor(shard, args.path_to_pb, fixed_height, args.scaling_factor,
                                     {"net": 0.8, "stroke_width": 0.0, "text_height": 0.2}, 0.4,
                                     {"net_thresh": 1.0, "stroke_width_thresh": 1.0, "text_height_thresh": 0.9,

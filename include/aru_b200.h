@@ -102,13 +102,22 @@ typedef struct aru_graph_desc {
 typedef struct aru_engine aru_engine;
 
 /* engine options (aru_set_option) */
-#define ARU_OPT_CONV_PATH 1   /* 0 = auto (tcgen05; where both the row-banded and the position-major kernel apply, the
-                                     faster one by a plan-time timing), 1 = force the CUDA-core kernels (validation),
-                                 2 = tcgen05 position-major kernel only, 3 = row-banded kernel wherever it applies */
+#define ARU_OPT_CONV_PATH 1   /* 0 = auto (tcgen05: row-banded kernel for C_out <= 16, position-major kernel above - a
+                                     fixed rule, so results do not depend on the process; ARU_AUTOTUNE=1 in the
+                                     environment times both per layer instead),
+                                 1 = force the CUDA-core kernels (validation), 2 = tcgen05 position-major kernel only,
+                                 3 = row-banded kernel wherever it applies, one launch per layer */
 #define ARU_OPT_USE_GRAPH 2   /* 1 = replay a captured CUDA graph per plan (default), 0 = plain launches */
 #define ARU_OPT_MICRO_BATCH 3 /* pages per pass through the net inside aru_forward (0 = auto) */
 #define ARU_OPT_KEEP_ALL 4    /* 1 = store every lowered tensor (per-layer checks through aru_read_buffer); 0 (default) =
                                  a tensor read only by a pool that its producer's launch performs is not stored */
+
+#define ARU_OPT_FUSE_PAIRS 5  /* 1 = with ARU_OPT_CONV_PATH 0, two chained 3x3 convolutions with C_out = 8 / 16 (conv1 ->
+                                 convR_0, convR_1 -> convR_2 of a residual block, ARU_v1.py:212-227) run as one launch with
+                                 the intermediate in a shared-memory row FIFO (conv_band2.cu); 0 (default) = one launch per
+                                 layer.  Measured slower than the per-layer kernels on B200 (the banded-weight MMAs make the
+                                 shared-memory port the limit), kept selectable and parity-tested.
+                                 ARU_FUSE_PAIRS=1 in the environment turns it on as well. */
 
 int aru_abi_version(void);
 int aru_device_count(void);

@@ -131,6 +131,68 @@ def test_per_layer_parity(engines, oracles, path, pname):
     eng.set_option(OPT_KEEP_ALL, 0)
 
 
+@pytest.mark.parametrize("net,n,h,w", [
+    ("separator", 1, 257, 130),     # odd sizes, one strip at every level
+    ("separator", 2, 150, 613),     # several strips (W > 126) and a batch: strip halo columns, page boundaries
+    ("separator", 3, 420, 300),     # more row tiles than TMEM buffers, several CTAs per strip segment
+    ("heading", 1, 90, 68),
+    ("aru_s6a5", 1, 129, 97),
+    ("ru", 1, 333, 101),
+    ("tiny", 1, 9, 200), ("tiny", 1, 1, 1),
+])
+def test_fused_conv_pairs_against_one_launch_per_layer(engines, oracles, net, n, h, w):
+    """conv_band2.cu (two chained 3x3 convolutions per launch, intermediate in a shared-memory row FIFO) against the
+    same layers run one launch each (ARU_OPT_FUSE_PAIRS 0): same 16-bit operands and fp32 accumulation; the vertical
+    tap pairs group rows with the other parity, so the two agree to fp32 summation order (<= 5e-3 on the probabilities,
+    like the other kernel paths) - and each of them is within BASELINE's tolerance of the oracle."""
+    from aru_b200.engine import OPT_CONV_PATH, OPT_FUSE_PAIRS
+    from aru_b200.synth import synth_page, page_to_net_input
+    eng = engines(net)
+    eng.set_option(OPT_CONV_PATH, 0)
+    x = np.stack([page_to_net_input(synth_page(h, w, seed=7 * h + w + i)) for i in range(n)]).astype(np.float32)
+    try:
+        eng.set_option(OPT_FUSE_PAIRS, 1)
+        fused = eng.forward(x).copy()
+        names = [k for _, k, _ in eng.profile_ops(1)]
+        if net != "tiny" or min(h, w) > 1:
+            assert any(k.startswith("conv_band2") for k in names), names
+        eng.set_option(OPT_FUSE_PAIRS, 0)
+        plain = eng.forward(x).copy()
+        assert not any(k.startswith("conv_band2") for _, k, _ in eng.profile_ops(1))
+    finally:
+        eng.set_option(OPT_FUSE_PAIRS, 0)
+    assert np.abs(fused - plain).max() <= 5e-3, float(np.abs(fused - plain).max())
+    ref = oracles(net).run(x)
+    for i in range(n):
+        _check(fused[i], ref[i], f"{net} {h}x{w} page {i} [fused pairs]")
+    # a page gives the same bits alone and inside a batch (tiles are partitioned differently over the CTAs), run to run
+    eng.set_option(OPT_FUSE_PAIRS, 1)
+    try:
+        if n > 1:
+            assert np.array_equal(eng.forward(x[n - 1])[0], fused[n - 1])
+        assert np.array_equal(eng.forward(x), fused)
+    finally:
+        eng.set_option(OPT_FUSE_PAIRS, 0)
+
+
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_two_fresh_engines_give_identical_bits(built_lib, fuse):
+    """Kernel selection is a fixed rule (no plan-time timing): two engines, two plans, same pages -> same bits, at the
+    benchmark size (many tiles per CTA: the steady state of the kernels' pipelines), with and without fused conv pairs."""
+    from aru_b200.engine import Engine, OPT_FUSE_PAIRS
+    from aru_b200.synth import synth_pb, synth_page, page_to_net_input
+    x = np.stack([page_to_net_input(synth_page(1856, 1344, s)) for s in range(2)]).astype(np.float32)
+    outs = []
+    for _ in range(2):
+        eng = Engine(synth_pb("separator"), device=0)
+        eng.set_option(OPT_FUSE_PAIRS, fuse)
+        outs.append(eng.forward(x).copy())
+        outs.append(eng.forward(x).copy())
+        eng.close()
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+
+
 def test_batch_and_micro_batch_consistency(engines):
     """forward([p0..p4]) == forward(pi) per page, bit-exact, for any micro-batch split (pages are independent)."""
     from aru_b200.engine import OPT_CONV_PATH, OPT_MICRO_BATCH
