@@ -116,14 +116,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    # the driver's --steps / --warmup are honoured (one page of the workload per step: ~0.7 s on 16-32 host threads);
+    # only a run that would not end within a few minutes is cut, and then it says so
+    steps, warmup = max(1, min(args.steps, 200)), max(0, min(args.warmup, 50))
     pps, s_per_step, cores, threads = cpu_pages_per_s(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"separator net (synthetic .pb, S=5 A=3), {PAGES_PER_STEP} pages of {H}x{W} per GPU per step",
-                   "sample": f"1 page of {H}x{W} per step"},
+                   "sample": f"1 page of {H}x{W} per step" + ("" if (steps, warmup) == (args.steps, args.warmup) else
+                                                                f" (asked for {args.steps}/{args.warmup} steps/warm-up, capped)")},
         "cpu_baseline": {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{steps} x 1 page of {H}x{W}, PyTorch-CPU fp32 oracle of the same GraphDef "
                                    f"(TF1 is not installable here), {threads} threads on {cores} host cores"},
@@ -154,8 +157,21 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
         return dims[buf]
 
     classes, shapes = {}, {}
+    writer = {}      # buffer -> class entries of the launch that wrote it (a fused pool's output is its producer's work)
+    pending = {}     # buffer -> (flops, bytes) of a convolution performed by its consumer's launch (conv_band2.cu)
     for op, (_, kernel, ms) in zip(prog.ops, prof):
         flops = bytes_ = 0.0
+        if kernel == "pool_fused":
+            oh, ow = hw(op.out.buf)
+            for ent in writer.get(op.inp.buf, ()):
+                ent["bytes"] += n * oh * ow * op.inp.ch * 2
+            continue
+        if kernel == "pair_fused":
+            oh, ow = hw(op.out.buf)
+            ih, iw = hw(op.inp.buf)
+            pending[op.out.buf] = (2.0 * n * oh * ow * op.ksize * op.ksize * op.inp.ch * op.out.ch,
+                                   n * (ih * iw * op.inp.ch * 2 + (oh * ow * op.out.ch * 2 if op.out_pre.buf >= 0 else 0)))
+            continue
         if op.kind in (P.OP_CONV, P.OP_DECONV):
             oh, ow = hw(op.out.buf)
             ih, iw = hw(op.inp.buf)
@@ -164,12 +180,16 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
             in_b = 4 if op.inp.ch == 1 else 2
             out_b = 4 if kernel in ("conv_small", "conv_tc_head", "conv_band_head") else 2
             bytes_ = n * (ih * iw * op.inp.ch * in_b + oh * ow * op.out.ch * out_b)
-            if kernel == "conv_stem_pool":     # only the pooled tensor is stored
-                bytes_ = n * (ih * iw * 4 + -(-oh // 2) * -(-ow // 2) * op.out.ch * 2)
+            if kernel == "conv_stem_pool":     # only the pooled tensor is stored (added by the pool_fused op that follows)
+                bytes_ = n * ih * iw * 4
             if op.res.buf >= 0:
                 bytes_ += n * oh * ow * op.out.ch * 2
             if op.out_pre.buf >= 0:
                 bytes_ += n * oh * ow * op.out.ch * 2
+            if kernel.startswith("conv_band2") and op.inp.buf in pending:
+                f0, b0 = pending.pop(op.inp.buf)
+                flops += f0
+                bytes_ += b0 - n * ih * iw * op.inp.ch * in_b     # the intermediate never leaves the SM
         elif op.kind in (P.OP_MAXPOOL, P.OP_AVGPOOL):
             oh, ow = hw(op.out.buf)
             ih, iw = hw(op.inp.buf)
@@ -184,11 +204,13 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
                 bytes_ += n * (ah * aw * 4 + dh * dw * d.ch * 2)
         c = classes.setdefault(kernel, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
         c["ms"] += ms; c["flops"] += flops; c["bytes"] += bytes_; c["launches"] += 1
+        writer[op.out.buf] = [c]
         if op.kind in (P.OP_CONV, P.OP_DECONV):
             key = (f"{kernel} {op.ksize}x{op.ksize} {op.inp.ch}->{op.out.ch} {oh}x{ow} n{n}"
                    + ("+res" if op.res.buf >= 0 else "") + ("+pre" if op.out_pre.buf >= 0 else ""))
             sgrp = shapes.setdefault(key, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
             sgrp["ms"] += ms; sgrp["flops"] += flops; sgrp["bytes"] += bytes_; sgrp["launches"] += 1
+            writer[op.out.buf].append(sgrp)
     total_ms = sum(c["ms"] for c in classes.values())
     out = []
     for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
@@ -245,6 +267,10 @@ def run_b200(args):
 
     peaks, peaks_src = load_peaks()
     n = args.pages
+    from aru_b200.engine import bind_host_to_device
+    # each rank's page-locked buffers must be local to its GPU's NUMA node (Engine() binds too; done first here because
+    # nothing may be page-locked before it)
+    numa_node = bind_host_to_device(local) if os.environ.get("ARU_NUMA_BIND", "1") != "0" else -1
     eng = Engine(synth_pb(NET), device=local)
     if args.micro_batch:
         from aru_b200.engine import OPT_MICRO_BATCH
@@ -303,6 +329,20 @@ def run_b200(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
 
+    # ---- the contract-minimal return: float32 pages in, uint8 maps out - what every caller of get_net_output does with
+    # the float map first (np.array(net_output * 255, dtype=np.uint8), separator_net_post_processor.py:147,
+    # heading_net_post_processor.py:287, region_net_post_processor_base.py:52): 4 B/px up, n_class B/px down ----
+    for _ in range(max(1, min(args.warmup, 2))):
+        u8_host = eng.forward(x_host, want_u8=True, want_prob=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        u8_host = eng.forward(x_host, want_u8=True, want_prob=False)
+        checksum += float(u8_host[0, 0, 0, 0])
+    torch.cuda.synchronize()
+    u8_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+
     # ---- end to end one level up: uint8 pages in, the two separator masks out (SURVEY.md 8 f1+f2) ----
     # = SeparatorNetPostProcessor.run up to the polygon step; only 1 B/px goes up and 2 B/px come down
     p_host = pinned_empty((n, H, W), np.uint8)
@@ -316,6 +356,19 @@ def run_b200(args):
         checksum += float(r_pages["vertical"][0, 0, 0])
     torch.cuda.synchronize()
     pages_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+
+    # ---- what the unmodified caller does: one pageable float64 page per get_net_output call (helper.py:31,56-72) ----
+    n_single = min(n, 8)
+    singles = [pages[i].astype(np.float64) for i in range(n_single)]
+    eng.forward(singles[0]); eng.forward(singles[0])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for pg in singles:
+            checksum += float(eng.forward(pg)[0, 0, 0, 0])
+    torch.cuda.synchronize()
+    single_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -342,14 +395,22 @@ def run_b200(args):
                        "sharding": "page-wise, one process per GPU, no collective"},
             "e2e": {"value": total_pages / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
                     "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": e2e_s / args.steps * 1e3,
-                    "call": "Engine.forward == get_net_output for a batch: float32 pages in, float32 probability maps out",
-                    "separator_pages": {
-                        "value": total_pages / pages_s, "unit": UNIT, "ms_per_step": pages_s / args.steps * 1e3,
-                        "h2d_bytes_per_step": int(p_host.nbytes),
-                        "d2h_bytes_per_step": int(r_pages["horizontal"].nbytes + r_pages["vertical"].nbytes),
-                        "call": "Engine.separator_pages == SeparatorNetPostProcessor.run up to the polygon step: uint8 "
-                                "pages in; colour step, net, uint8, threshold, component filter and openings on the "
-                                "device; horizontal + vertical uint8 masks out"}},
+                    "call": "Engine.forward == get_net_output for a batch: float32 pages in, float32 probability maps out"},
+            "e2e_uint8": {"value": total_pages / u8_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
+                          "d2h_bytes_per_step": int(u8_host.nbytes), "ms_per_step": u8_s / args.steps * 1e3,
+                          "call": "Engine.forward(want_u8=True, want_prob=False): float32 pages in, np.array(p * 255, uint8) "
+                                  "out - the first thing every caller of get_net_output computes (sep:147, head:287, base:52)"},
+            "e2e_masks": {"value": total_pages / pages_s, "unit": UNIT, "h2d_bytes_per_step": int(p_host.nbytes),
+                          "d2h_bytes_per_step": int(r_pages["horizontal"].nbytes + r_pages["vertical"].nbytes),
+                          "ms_per_step": pages_s / args.steps * 1e3,
+                          "call": "Engine.separator_pages == SeparatorNetPostProcessor.run up to the polygon step: uint8 "
+                                  "pages in; colour step, net, uint8, threshold, component filter and openings on the "
+                                  "device; horizontal + vertical uint8 masks out"},
+            "e2e_pageable": {"value": world * n_single * args.steps / single_s, "unit": UNIT,
+                             "ms_per_page": single_s / (n_single * args.steps) * 1e3,
+                             "call": "one pageable float64 [H,W] page per Engine.forward call (what get_net_output receives "
+                                     "from load_and_scale_image, helper.py:31): conversion, page-locked staging and one "
+                                     "single-page pass per call"},
             "gpu_launches": int(launches * n_mb * args.steps),
             "achieved_tflops": round(value / world * gflop_page / 1e3, 2),
             "roofline": dict(dom, peaks=peaks_src,
@@ -357,6 +418,8 @@ def run_b200(args):
                                   "its launches; traffic = ncu dram read+write bytes of the same launch (profiles/ncu_traffic.json)"),
             "roofline_by_class": classes,
             "clocks": clocks,
+            "numa": {"node": numa_node, "cpus": len(os.sched_getaffinity(0)),
+                     "bound": os.environ.get("ARU_NUMA_BIND", "1") != "0"},
         }
         # bounded CPU baseline on the host cores of this box
         if world == 1 and not args.no_cpu:

@@ -6,8 +6,12 @@
 // net from a plain per-page loop, separator_net_post_processor.py:141).  There is no CPU fallback: without
 // a CUDA device aru_create fails with ARU_ENODEV.
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -1167,6 +1171,57 @@ int aru_device_count(void) {
 
 const char* aru_last_error(const aru_engine* e) { return e ? e->error.c_str() : g_error.c_str(); }
 
+// One process per GPU: the host buffers a rank page-locks must live on the NUMA node its GPU hangs off, or the
+// host<->device copies of the ranks on the other socket cross the inter-socket link and the 8-GPU end-to-end rate
+// collapses (profiles/r02*_host_bw_probe*.json).  Linux: the PCI device's local_cpulist / numa_node in sysfs.
+int aru_bind_host_to_device(int device, int* numa_node) {
+  if (numa_node) *numa_node = -1;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return ARU_ECUDA; }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  auto read_line = [&](const char* leaf, char* buf, size_t n) -> bool {
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/%s", bus, leaf);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    const bool ok = fgets(buf, (int)n, f) != nullptr;
+    fclose(f);
+    return ok;
+  };
+  char line[4096];
+  int node = -1;
+  if (read_line("numa_node", line, sizeof line)) node = atoi(line);
+  if (numa_node) *numa_node = node;
+  if (!read_line("local_cpulist", line, sizeof line)) return ARU_EUNSUP;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int n_cpus = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k < 1) continue;
+    if (k == 1) b = a;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); ++n_cpus; }
+  }
+  if (n_cpus == 0) return ARU_EUNSUP;
+  // keep the CPUs the process was allowed to use (containers, taskset): intersect, and give up if nothing is left
+  cpu_set_t cur, both;
+  if (sched_getaffinity(0, sizeof cur, &cur) == 0) {
+    CPU_AND(&both, &cur, &set);
+    if (CPU_COUNT(&both) == 0) return ARU_EUNSUP;
+    set = both;
+  }
+  if (sched_setaffinity(0, sizeof set, &set) != 0) return ARU_EUNSUP;
+#ifdef SYS_set_mempolicy
+  if (node >= 0 && node < 1024) {   // MPOL_PREFERRED = 1: new pages (and what cudaHostAlloc pins) come from the local node
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1UL << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1, mask, (unsigned long)(8 * sizeof mask));
+  }
+#endif
+  return ARU_OK;
+}
+
 int aru_create(const aru_graph_desc* g, int device, aru_engine** out) {
   if (!g || !out) return fail(nullptr, ARU_EINVAL, "aru_create: null argument");
   *out = nullptr;
@@ -1179,6 +1234,11 @@ int aru_create(const aru_graph_desc* g, int device, aru_engine** out) {
   if (device < 0 || device >= ndev) return fail(nullptr, ARU_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
   std::unique_ptr<aru_engine> e(new aru_engine);
   e->device = device;
+  {
+    // ARU_NUMA_BIND=0 leaves the calling thread's CPU affinity / memory policy alone
+    const char* nb = getenv("ARU_NUMA_BIND");
+    if (!(nb && nb[0] == '0')) aru_bind_host_to_device(device, nullptr);
+  }
   cudaError_t err = cudaSetDevice(device);
   if (err != cudaSuccess) return fail(nullptr, ARU_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(err));
   cudaDeviceProp prop;

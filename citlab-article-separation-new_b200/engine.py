@@ -30,6 +30,7 @@ EXPORTS = [
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
     "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
     "aru_box_sums", "aru_cc_filter", "aru_scaled_size", "aru_scale_pages", "aru_separator_images", "aru_heading_images",
+    "aru_bind_host_to_device",
 ]
 
 _lib = None
@@ -89,6 +90,7 @@ def load_library() -> ctypes.CDLL:
         lib.aru_host_alloc.argtypes = [ctypes.POINTER(vp), sz]
         lib.aru_host_free.argtypes = [vp]
         lib.aru_host_free.restype = None
+        lib.aru_bind_host_to_device.argtypes = [i32, ctypes.POINTER(i32)]
         del u8p
         _lib = lib
         return lib
@@ -149,6 +151,15 @@ PINNED = _PinnedPool()
 
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     return PINNED.empty(shape, dtype)
+
+
+def bind_host_to_device(device: int) -> int:
+    """Pin this thread to the CPUs next to CUDA device ``device`` and prefer its NUMA node for new (page-locked) memory;
+    returns the node (-1 when unknown / not applied).  ``Engine()`` does this itself unless ``ARU_NUMA_BIND=0``; call it
+    first when pinned buffers are allocated before the engine exists."""
+    node = ctypes.c_int(-1)
+    rc = load_library().aru_bind_host_to_device(int(device), ctypes.byref(node))
+    return node.value if rc == ARU_OK else -1
 
 
 # ------------------------------------------------------------------------------------------------

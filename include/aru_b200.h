@@ -122,6 +122,12 @@ typedef struct aru_engine aru_engine;
 int aru_abi_version(void);
 int aru_device_count(void);
 
+/* One process per GPU: pin the calling thread to the CPUs of the NUMA node CUDA device `device` is
+ * attached to and prefer that node for new pages, so that the buffers the rank page-locks afterwards are local to its
+ * GPU (sysfs local_cpulist / numa_node of the PCI device).  aru_create() calls it unless ARU_NUMA_BIND=0 is set.
+ * *numa_node receives the node (-1: unknown); ARU_EUNSUP when the topology cannot be read or applied (nothing changed). */
+int aru_bind_host_to_device(int device, int* numa_node);
+
 /* load_graph: build an engine for `g` on CUDA device `device`. Fails with ARU_ENODEV without a GPU. */
 int aru_create(const aru_graph_desc* g, int device, aru_engine** out);
 void aru_destroy(aru_engine* e);
