@@ -329,15 +329,17 @@ def run_b200(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
 
-    # ---- the contract-minimal return: float32 pages in, uint8 maps out - what every caller of get_net_output does with
-    # the float map first (np.array(net_output * 255, dtype=np.uint8), separator_net_post_processor.py:147,
-    # heading_net_post_processor.py:287, region_net_post_processor_base.py:52): 4 B/px up, n_class B/px down ----
+    # ---- the contract-minimal call: uint8 pages in (as cv2.imread / scale_image give them), channel 0 of
+    # np.array(net_output * 255, dtype=np.uint8) out - all any caller of get_net_output keeps of the float map
+    # (separator_net_post_processor.py:33,147, heading_net_post_processor.py:209,287): 1 B/px up, 1 B/px down ----
+    p_host = pinned_empty((n, H, W), np.uint8)
+    p_host[...] = np.rint(pages * 255.0).astype(np.uint8)
     for _ in range(max(1, min(args.warmup, 2))):
-        u8_host = eng.forward(x_host, want_u8=True, want_prob=False)
+        u8_host = eng.separator_pages(p_host, want_u8=True, want_separators=False, u8_channels=1)["u8"]
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        u8_host = eng.forward(x_host, want_u8=True, want_prob=False)
+        u8_host = eng.separator_pages(p_host, want_u8=True, want_separators=False, u8_channels=1)["u8"]
         checksum += float(u8_host[0, 0, 0, 0])
     torch.cuda.synchronize()
     u8_s = max_over_ranks(time.perf_counter() - t0)
@@ -345,8 +347,6 @@ def run_b200(args):
 
     # ---- end to end one level up: uint8 pages in, the two separator masks out (SURVEY.md 8 f1+f2) ----
     # = SeparatorNetPostProcessor.run up to the polygon step; only 1 B/px goes up and 2 B/px come down
-    p_host = pinned_empty((n, H, W), np.uint8)
-    p_host[...] = np.rint(pages * 255.0).astype(np.uint8)
     for _ in range(max(1, min(args.warmup, 2))):
         r_pages = eng.separator_pages(p_host)
     barrier()
@@ -396,10 +396,11 @@ def run_b200(args):
             "e2e": {"value": total_pages / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
                     "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": e2e_s / args.steps * 1e3,
                     "call": "Engine.forward == get_net_output for a batch: float32 pages in, float32 probability maps out"},
-            "e2e_uint8": {"value": total_pages / u8_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
+            "e2e_uint8": {"value": total_pages / u8_s, "unit": UNIT, "h2d_bytes_per_step": int(p_host.nbytes),
                           "d2h_bytes_per_step": int(u8_host.nbytes), "ms_per_step": u8_s / args.steps * 1e3,
-                          "call": "Engine.forward(want_u8=True, want_prob=False): float32 pages in, np.array(p * 255, uint8) "
-                                  "out - the first thing every caller of get_net_output computes (sep:147, head:287, base:52)"},
+                          "call": "Engine.separator_pages(want_u8=True, u8_channels=1): uint8 pages in; colour step, net and "
+                                  "np.array(p * 255, uint8)[..., 0] on the device; the uint8 channel-0 map out - the part of "
+                                  "get_net_output's result its callers keep (sep:33,147, head:209,287)"},
             "e2e_masks": {"value": total_pages / pages_s, "unit": UNIT, "h2d_bytes_per_step": int(p_host.nbytes),
                           "d2h_bytes_per_step": int(r_pages["horizontal"].nbytes + r_pages["vertical"].nbytes),
                           "ms_per_step": pages_s / args.steps * 1e3,

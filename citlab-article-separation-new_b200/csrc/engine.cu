@@ -117,7 +117,7 @@ struct aru_engine {
   std::vector<OpWeights> opw;
   std::vector<int> kind;  // per buffer
   int input_buf = -1, output_buf = -1, n_class = 0;
-  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0;
+  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0, u8_channels = 0;
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   int* err_flag = nullptr;
   float* zero_bias = nullptr;
@@ -1029,6 +1029,8 @@ int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w) {
   const int mb = pick_micro_batch(e, n, h, w);
   const size_t page_px = (size_t)h * w;
   const int C = e->n_class;
+  // channels of the uint8 map that are produced / copied out (ARU_OPT_U8_CHANNELS; the box sums read channel 0 only)
+  const int Cu = (e->u8_channels > 0 && e->u8_channels < C) ? e->u8_channels : C;
   const bool want_post = io.out_h != nullptr;
   const bool want_mask = io.out_mask != nullptr || want_post;
   int k1 = 0, kv = 0, k2 = 0;
@@ -1115,11 +1117,11 @@ int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w) {
     if (rc) return rc;
     if (want_u8 || want_mask) {
       cudaError_t err = launch_quantize(e->s_comp, p->out_dev[par], want_u8 ? p->u8_dev[par] : nullptr,
-                                        want_mask ? p->mask_dev[par] : nullptr, (long long)cnt * page_px, C, io.thr, io.cut);
+                                        want_mask ? p->mask_dev[par] : nullptr, (long long)cnt * page_px, C, io.thr, io.cut, Cu);
       if (err != cudaSuccess) return fail(e, ARU_ECUDA, "quantize launch: %s", cudaGetErrorString(err));
     }
     if (io.n_boxes > 0) {
-      cudaError_t err = launch_box_sums(e->s_comp, p->u8_dev[par], cnt, h, w, C, i0, io.boxes_dev, io.n_boxes, io.sums_dev);
+      cudaError_t err = launch_box_sums(e->s_comp, p->u8_dev[par], cnt, h, w, Cu, i0, io.boxes_dev, io.n_boxes, io.sums_dev);
       if (err != cudaSuccess) return fail(e, ARU_ECUDA, "box_sums launch: %s", cudaGetErrorString(err));
     }
     if (want_post) {
@@ -1133,7 +1135,7 @@ int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w) {
       CU(e, cudaMemcpyAsync(io.out + (size_t)i0 * page_px * C, p->out_dev[par], (size_t)cnt * page_px * C * sizeof(float),
                             cudaMemcpyDeviceToHost, e->s_d2h));
     if (io.out_u8)
-      CU(e, cudaMemcpyAsync(io.out_u8 + (size_t)i0 * page_px * C, p->u8_dev[par], (size_t)cnt * page_px * C,
+      CU(e, cudaMemcpyAsync(io.out_u8 + (size_t)i0 * page_px * Cu, p->u8_dev[par], (size_t)cnt * page_px * Cu,
                             cudaMemcpyDeviceToHost, e->s_d2h));
     if (io.out_mask)
       CU(e, cudaMemcpyAsync(io.out_mask + (size_t)i0 * page_px, p->mask_dev[par], (size_t)cnt * page_px,
@@ -1407,6 +1409,10 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
         e->cur = nullptr;
       }
       e->fuse_pairs = value ? 1 : 0;
+      return ARU_OK;
+    case ARU_OPT_U8_CHANNELS:
+      if (value < 0 || value > 64) return fail(e, ARU_EINVAL, "bad number of uint8 channels");
+      e->u8_channels = (int)value;
       return ARU_OK;
     case ARU_OPT_MICRO_BATCH:
       if (value < 0 || value > 4096) return fail(e, ARU_EINVAL, "bad micro batch");

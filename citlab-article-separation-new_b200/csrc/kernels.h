@@ -52,8 +52,9 @@ cudaError_t launch_upsum_f32(cudaStream_t st, const float* in, int Hi, int Wi, f
                              int oy, int ox);
 cudaError_t launch_copy(cudaStream_t st, const void* in, void* out, long long bytes);
 // mask = 255 where u8[...,0] > thr*255 (float compare), or where u8[...,0] >= cut when cut >= 0
+// u8_channels > 0: only that many leading channels are written, u8 is [npix][u8_channels] (0: all C)
 cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uint8_t* mask, long long npix, int C,
-                            float thr, int cut = -1);
+                            float thr, int cut = -1, int u8_channels = 0);
 
 // ---- integer pre / post-processing around the net (post.cu) --------------------------------------
 // uint8 gray (channels 1) or BGR (channels 3) pages -> float32 net input gray/255 (+ optional uint8 gray copy)

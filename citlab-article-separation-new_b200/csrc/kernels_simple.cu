@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(256) k_copy16(const uint4* __restrict__ in, ui
 // heading_net_post_processor.py:287), mask = 255 * (u8[...,0] > thr*255) (helper.py:75-78).
 __global__ void __launch_bounds__(256) k_quantize(const float* __restrict__ prob, uint8_t* __restrict__ u8,
                                                   uint8_t* __restrict__ mask, long long npix, int C, float thr255,
-                                                  int cut) {
+                                                  int cut, int Cw) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   uint8_t first = 0;
@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(256) k_quantize(const float* __restrict__ prob
     const float v = prob[p * C + c] * 255.f;
     const uint8_t q = (uint8_t)(int)v;
     if (c == 0) first = q;
-    if (u8) u8[p * C + c] = q;
+    if (u8 && c < Cw) u8[p * Cw + c] = q;    // Cw leading channels only (the consumers read channel 0, sep:33, head:209)
   }
   // helper.py:75-78: u8 > threshold*255; cut >= 0 carries the comparison as an integer (threshold given as a double)
   if (mask) mask[p] = (cut >= 0 ? (int)first >= cut : (float)first > thr255) ? 255 : 0;
@@ -962,11 +962,12 @@ cudaError_t launch_copy(cudaStream_t st, const void* in, void* out, long long by
 }
 
 cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uint8_t* mask, long long np, int C,
-                            float thr, int cut) {
+                            float thr, int cut, int u8_channels) {
+  const int Cw = (u8_channels > 0 && u8_channels < C) ? u8_channels : C;
   long long done = 0;
   const bool aligned = (reinterpret_cast<uintptr_t>(prob) & 15) == 0 && (reinterpret_cast<uintptr_t>(u8) & 7) == 0 &&
                        (reinterpret_cast<uintptr_t>(mask) & 3) == 0;
-  if (C == 2 && aligned && np >= 4) {
+  if (C == 2 && Cw == C && aligned && np >= 4) {
     const long long nquad = np / 4;
     k_quantize_c2x4<<<blocks_for(nquad, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(prob),
                                                             reinterpret_cast<uint2*>(u8), reinterpret_cast<uint32_t*>(mask),
@@ -974,8 +975,8 @@ cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uin
     done = nquad * 4;
   }
   if (done < np)
-    k_quantize<<<blocks_for(np - done, 256), 256, 0, st>>>(prob + done * C, u8 ? u8 + done * C : nullptr,
-                                                           mask ? mask + done : nullptr, np - done, C, thr * 255.f, cut);
+    k_quantize<<<blocks_for(np - done, 256), 256, 0, st>>>(prob + done * C, u8 ? u8 + done * Cw : nullptr,
+                                                           mask ? mask + done : nullptr, np - done, C, thr * 255.f, cut, Cw);
   return cudaGetLastError();
 }
 

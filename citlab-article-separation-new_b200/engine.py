@@ -18,10 +18,11 @@ from .graphdef import parse_graphdef
 from .program import CGraphDesc, Program, lower_graph
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libaru_b200.so")
+# ARU_B200_LIB selects another build of the same library (the bf16 variant the parity suite also runs)
+LIB_PATH = os.environ.get("ARU_B200_LIB") or os.path.join(_PKG_DIR, "libaru_b200.so")
 
 ARU_OK, ARU_EINVAL, ARU_ECUDA, ARU_ENOMEM, ARU_EUNSUP, ARU_ENODEV = 0, 1, 2, 3, 4, 5
-OPT_CONV_PATH, OPT_USE_GRAPH, OPT_MICRO_BATCH, OPT_KEEP_ALL, OPT_FUSE_PAIRS = 1, 2, 3, 4, 5
+OPT_CONV_PATH, OPT_USE_GRAPH, OPT_MICRO_BATCH, OPT_KEEP_ALL, OPT_FUSE_PAIRS, OPT_U8_CHANNELS = 1, 2, 3, 4, 5, 6
 
 # every symbol include/aru_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = [
@@ -220,10 +221,19 @@ class Engine:
             raise ValueError(f"expected [H,W], [N,H,W] or [N,H,W,1], got shape {x.shape}")
         return x
 
+    def _u8_channels(self, k: int) -> int:
+        """Select how many leading channels the uint8 outputs hold (0 = all); returns the resulting channel count."""
+        k = int(k)
+        if k < 0 or k > self.n_class:
+            raise ValueError(f"u8_channels must be 0..{self.n_class}")
+        self.set_option(OPT_U8_CHANNELS, k)
+        return k if 0 < k < self.n_class else self.n_class
+
     def forward(self, images: np.ndarray, want_u8: bool = False, want_mask: bool = False, threshold: float = 0.05,
-                want_prob: bool = True):
+                want_prob: bool = True, u8_channels: int = 0):
         """images: float [N,H,W] in [0,1] (any float dtype; pinned float32 is zero-copy).
-        Returns prob float32 [N,H,W,C] (pinned), plus uint8 / mask arrays when requested."""
+        Returns prob float32 [N,H,W,C] (pinned), plus uint8 / mask arrays when requested.  ``u8_channels=1`` returns only
+        channel 0 of the uint8 map ([N,H,W,1]) - the one every consumer reads (sep:33, head:209)."""
         x = self._as_batch(images)
         n, h, w = x.shape
         if not (x.dtype == np.float32 and x.flags.c_contiguous):
@@ -232,7 +242,8 @@ class Engine:
             x = xin
         c = self.n_class
         prob = pinned_empty((n, h, w, c), np.float32) if want_prob else None
-        u8 = pinned_empty((n, h, w, c), np.uint8) if want_u8 else None
+        cu = self._u8_channels(u8_channels)
+        u8 = pinned_empty((n, h, w, cu), np.uint8) if want_u8 else None
         mask = pinned_empty((n, h, w), np.uint8) if want_mask else None
         ptr = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None  # noqa: E731
         self._check(self.lib.aru_forward(self.handle, ptr(x), n, h, w, ptr(prob), ptr(u8), ptr(mask),
@@ -270,7 +281,8 @@ class Engine:
         return x, n, h, w, ch
 
     def separator_pages(self, pages: np.ndarray, threshold: float = 0.05, want_prob: bool = False,
-                        want_u8: bool = False, want_mask: bool = False, want_separators: bool = True) -> dict:
+                        want_u8: bool = False, want_mask: bool = False, want_separators: bool = True,
+                        u8_channels: int = 0) -> dict:
         """One iteration of ``SeparatorNetPostProcessor.run`` up to the polygon step for a batch of uint8 pages
         (gray ``[N,H,W]`` or BGR ``[N,H,W,3]``): colour step, net, ``uint8(p*255)``, threshold, ``post_process``
         (separator_net_post_processor.py:141-151).  Returns a dict with the requested arrays (pinned host memory):
@@ -285,8 +297,9 @@ class Engine:
         res = {}
         if want_prob:
             res["prob"] = pinned_empty((n, h, w, c), np.float32)
+        cu = self._u8_channels(u8_channels)
         if want_u8:
-            res["u8"] = pinned_empty((n, h, w, c), np.uint8)
+            res["u8"] = pinned_empty((n, h, w, cu), np.uint8)
         if want_mask:
             res["mask"] = pinned_empty((n, h, w), np.uint8)
         if want_separators:
@@ -322,6 +335,7 @@ class Engine:
         unscaled uint8 images (as ``cv2.imread`` returns them, all of one size) go up, are shrunk by ``sc`` on the device
         (INTER_AREA; ``sc == 1`` is a no-op as in the reference, ``sc > 1`` raises: enlarge on the host), and the
         results come back at the scaled size.  Same dict as ``separator_pages``."""
+        self._u8_channels(0)
         x, n, h, w, ch = self._as_pages(images)
         x = np.ascontiguousarray(x)
         dh, dw = (h, w) if sc == 1.0 else self.scaled_size(h, w, sc)
@@ -373,6 +387,7 @@ class Engine:
         ``net_output[ya:yb, xa:xb]`` for every box ``(page, ya, yb, xa, xb)`` - all on the device.
         Returns (sums uint64 [n_boxes], clipped boxes int32 [n_boxes,5][, u8]); the reference's
         ``get_net_prob_for_text_line`` value is ``sums / 255 / (bounding_box.width * bounding_box.height)``."""
+        self._u8_channels(0)
         x, n, h, w, ch = self._as_pages(pages)
         x = np.ascontiguousarray(x)
         bx = self.clip_boxes(boxes, h, w)
@@ -387,6 +402,7 @@ class Engine:
         """``heading_pages`` with ``scale_image`` (sc < 1, INTER_AREA) in front, on the device: unscaled uint8 images in;
         ``boxes`` are in the coordinates of the scaled page (the reference rescales the text-line polygons by the same
         factor, heading_net_post_processor.py:262-263)."""
+        self._u8_channels(0)
         x, n, h, w, ch = self._as_pages(images)
         x = np.ascontiguousarray(x)
         dh, dw = (h, w) if sc == 1.0 else self.scaled_size(h, w, sc)

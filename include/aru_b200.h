@@ -119,6 +119,10 @@ typedef struct aru_engine aru_engine;
                                  shared-memory port the limit), kept selectable and parity-tested.
                                  ARU_FUSE_PAIRS=1 in the environment turns it on as well. */
 
+#define ARU_OPT_U8_CHANNELS 6 /* k > 0: the uint8 outputs (out_u8) of the host-buffer calls hold only the k leading channels,
+                                 [n,h,w,k] - every consumer reads channel 0 alone (separator_net_post_processor.py:33,
+                                 heading_net_post_processor.py:209), and the device->host copy shrinks with it; 0 = all */
+
 int aru_abi_version(void);
 int aru_device_count(void);
 

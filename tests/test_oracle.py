@@ -78,7 +78,12 @@ def test_upsample_simple_sums_channels():
     np.testing.assert_allclose(out[..., 0], np.repeat(np.repeat(pooled, 2, 0), 2, 1)[:7, :5], rtol=1e-5)
 
 
-@pytest.mark.parametrize("net,h,w", [("tiny", 40, 32), ("tiny", 45, 39), ("ru", 48, 33), ("tiny_sigmoid", 21, 30)])
+@pytest.mark.parametrize("net,h,w", [
+    ("tiny", 40, 32), ("tiny", 45, 39), ("ru", 48, 33), ("tiny_sigmoid", 21, 30),
+    # the graphs the engine is benchmarked and parity-tested on, at BASELINE sizes: configs[0] / [1] (1024x768, separator
+    # and heading nets), the CLI default size (odd at every pyramid level) and the upstream S = 6 / A = 5 topology
+    ("separator", 1024, 768), ("heading", 1024, 768), ("separator", 1500, 1125), ("aru_s6a5", 257, 193),
+])
 def test_oracle_matches_opencv_importer(net, h, w):
     pb = synth_pb(net)
     x = page_to_net_input(synth_page(h, w, 11))
