@@ -1,0 +1,73 @@
+"""GPU half of the polygon / heading-flag equivalence check (north_star: identical separator polylines / heading flags
+on >= 99 % of pages): the ENGINE's uint8 maps and text-line sums for 100 synthetic pages, written to
+gpurun_out/equiv_engine_r02.npz and committed as tests/golden/equiv_engine_r02.npz.  The CPU half
+(tests/test_polygon_equivalence.py) recomputes the same quantities with the fp32 oracle and drives the reference's real
+to_polygons / rescale_polygons over both.
+
+Nets: the calibrated synthetic separator / heading nets, and "sharp" variants whose classifier margin is 4x larger (a
+trained net's maps are close to 0 / 1; the calibrated random-weight nets put ~1 % of all pixels within one uint8 step of
+the 13/255 cut, which is what decides whether two implementations give the same mask)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import __graft_entry__ as entry
+
+entry.build()
+from aru_b200.engine import Engine  # noqa: E402
+from aru_b200.synth import synth_page, synth_pb  # noqa: E402
+
+H, W, N, SEED0 = 256, 192, 100, 1000
+SHARP = {"separator_sharp": ("separator", dict(logit_gain=3.09268, logit_bias=(-52.508, 0.0))),
+         "heading_sharp": ("heading", dict(logit_gain=4.450784, logit_bias=(18.098, 0.0)))}
+
+
+def net_pb(name):
+    if name in SHARP:
+        base, kw = SHARP[name]
+        return synth_pb(base, **kw)
+    return synth_pb(name)
+
+
+def line_boxes(seed, h=H, w=W):
+    """~24 text-line boxes (page, y0, y1, x0, x1) per page in two columns, like the TextLines of a PAGE-XML."""
+    rng = np.random.default_rng(seed)
+    boxes = []
+    for c in range(2):
+        x0 = 8 + c * (w // 2)
+        y = 6 + int(rng.integers(0, 6))
+        while y + 8 < h - 6:
+            lh = int(rng.integers(5, 12))
+            lw = int(rng.integers(w // 5, w // 2 - 12))
+            boxes.append((0, y, y + lh, x0, x0 + lw))
+            y += lh + int(rng.integers(2, 9))
+    return boxes
+
+
+if __name__ == "__main__":
+    pages = np.stack([synth_page(H, W, SEED0 + i) for i in range(N)])
+    out = {"pages_seed0": SEED0, "shape": np.array([H, W]), "n": N}
+    for net in ("separator", "separator_sharp"):
+        eng = Engine(net_pb(net), device=0)
+        r = eng.separator_pages(pages, want_u8=True, u8_channels=1, want_separators=True)
+        out[net + "_u8"] = r["u8"][..., 0].copy()
+        out[net + "_hor"] = np.packbits(r["horizontal"] > 0)
+        out[net + "_ver"] = np.packbits(r["vertical"] > 0)
+        eng.close()
+    boxes, owner = [], []
+    for i in range(N):
+        b = line_boxes(SEED0 + i)
+        boxes += [(i,) + bb[1:] for bb in b]
+    boxes = np.asarray(boxes, np.int32)
+    out["boxes"] = boxes
+    for net in ("heading", "heading_sharp"):
+        eng = Engine(net_pb(net), device=0)
+        sums, bx = eng.heading_pages(pages, boxes)
+        assert np.array_equal(bx, boxes)
+        out[net + "_sums"] = sums.astype(np.uint64)
+        eng.close()
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.savez_compressed("gpurun_out/equiv_engine_r02.npz", **out)
+    print("wrote gpurun_out/equiv_engine_r02.npz", os.path.getsize("gpurun_out/equiv_engine_r02.npz") / 1e6, "MB")
