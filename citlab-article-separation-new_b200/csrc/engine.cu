@@ -935,12 +935,37 @@ struct ScalePlan {
   int fast = 0, ix = 1, iy = 1;
   int *x_start = nullptr, *x_si = nullptr, *y_start = nullptr, *y_si = nullptr;
   float *x_alpha = nullptr, *y_alpha = nullptr;
+  int cubic = 0;   // enlarging: INTER_CUBIC tables [d][4] (indices, 11-bit fixed-point weights)
+  int *cx_idx = nullptr, *cx_coef = nullptr, *cy_idx = nullptr, *cy_coef = nullptr;
 };
 
 void free_scale_plan(ScalePlan* sp) {
   cudaFree(sp->x_start); cudaFree(sp->x_si); cudaFree(sp->x_alpha);
   cudaFree(sp->y_start); cudaFree(sp->y_si); cudaFree(sp->y_alpha);
+  cudaFree(sp->cx_idx); cudaFree(sp->cx_coef); cudaFree(sp->cy_idx); cudaFree(sp->cy_coef);
   *sp = ScalePlan();
+}
+
+// OpenCV's cubic tables (resize.cpp, INTER_CUBIC, 8-bit): fx = (float)((dx + 0.5) * scale - 0.5), sx = floor(fx),
+// weights of taps sx - 1 .. sx + 2 with A = -0.75 in float32, stored as cvRound(w * 2048); indices clamped to the image
+void cubic_table(int ssize, int dsize, double scale, std::vector<int>* idx, std::vector<int>* coef) {
+  idx->resize((size_t)dsize * 4);
+  coef->resize((size_t)dsize * 4);
+  const float A = -0.75f;
+  for (int d = 0; d < dsize; ++d) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    const int sx = (int)std::floor(fx);
+    fx -= (float)sx;
+    float c[4];
+    c[0] = ((A * (fx + 1) - 5 * A) * (fx + 1) + 8 * A) * (fx + 1) - 4 * A;
+    c[1] = ((A + 2) * fx - (A + 3)) * fx * fx + 1;
+    c[2] = ((A + 2) * (1 - fx) - (A + 3)) * (1 - fx) * (1 - fx) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+    for (int k = 0; k < 4; ++k) {
+      (*idx)[(size_t)d * 4 + k] = std::min(std::max(sx - 1 + k, 0), ssize - 1);
+      (*coef)[(size_t)d * 4 + k] = (int)std::nearbyint(c[k] * 2048.f);
+    }
+  }
 }
 
 int cv_round(double v) { return (int)std::nearbyint(v); }   // cvRound / saturate_cast<int>(double): half to even
@@ -961,13 +986,25 @@ void area_table(int ssize, int dsize, double scale, std::vector<int>* start, std
 }
 
 int make_scale_plan(aru_engine* e, int sh, int sw, double sc, ScalePlan* sp) {
-  if (!(sc > 0.0) || sc >= 1.0)
-    return fail(e, ARU_EUNSUP, "device resize covers shrinking only (INTER_AREA, scale < 1); got scale %.6f: enlarging is "
-                "INTER_CUBIC in the reference and stays on the host", sc);
+  if (!(sc > 0.0) || sc == 1.0) return fail(e, ARU_EINVAL, "bad scale %.6f", sc);
   sp->sh = sh; sp->sw = sw;
   sp->dw = cv_round(sw * sc);
   sp->dh = cv_round(sh * sc);
   if (sp->dw < 1 || sp->dh < 1) return fail(e, ARU_EINVAL, "scaled page would be empty");
+  if (sc > 1.0) {
+    // enlarging: cv2.INTER_CUBIC (helper.py:21-23); scale = 1 / fx as OpenCV computes it for fx-given calls
+    std::vector<int> xi, xc, yi, yc;
+    cubic_table(sw, sp->dw, 1.0 / sc, &xi, &xc);
+    cubic_table(sh, sp->dh, 1.0 / sc, &yi, &yc);
+    sp->cubic = 1;
+    int rc;
+    if ((rc = upload(e, xi, &sp->cx_idx)) || (rc = upload(e, xc, &sp->cx_coef)) || (rc = upload(e, yi, &sp->cy_idx)) ||
+        (rc = upload(e, yc, &sp->cy_coef))) {
+      free_scale_plan(sp);
+      return rc;
+    }
+    return ARU_OK;
+  }
   const double scale = 1.0 / sc;
   const int iscale = cv_round(scale);
   if (std::fabs(scale - iscale) < 2.220446049250313e-16) {   // OpenCV's integer-scale path
@@ -1104,8 +1141,11 @@ int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w) {
     CU(e, cudaStreamWaitEvent(e->s_comp, p->ev_h2d[par], 0));
     if (io.scale) {
       const ScalePlan& sp = *io.scale;
-      cudaError_t err = launch_resize_area(e->s_comp, p->src_dev[par], io.channels, cnt, sp.sh, sp.sw, p->page_dev[par], h, w,
-                                           sp.x_start, sp.x_si, sp.x_alpha, sp.y_start, sp.y_si, sp.y_alpha, sp.fast, sp.ix, sp.iy);
+      cudaError_t err = sp.cubic
+          ? launch_resize_cubic(e->s_comp, p->src_dev[par], io.channels, cnt, sp.sh, sp.sw, p->page_dev[par], h, w, sp.cx_idx,
+                                sp.cx_coef, sp.cy_idx, sp.cy_coef)
+          : launch_resize_area(e->s_comp, p->src_dev[par], io.channels, cnt, sp.sh, sp.sw, p->page_dev[par], h, w,
+                               sp.x_start, sp.x_si, sp.x_alpha, sp.y_start, sp.y_si, sp.y_alpha, sp.fast, sp.ix, sp.iy);
       if (err != cudaSuccess) return fail(e, ARU_ECUDA, "resize_area launch: %s", cudaGetErrorString(err));
     }
     if (io.in_u8) {
@@ -1497,8 +1537,10 @@ int aru_scale_pages(aru_engine* e, const uint8_t* pages, int channels, int n, in
     const int cnt = std::min(mb, n - i0);
     cudaError_t err = cudaMemcpyAsync(d_in, pages + (size_t)i0 * src_b, cnt * src_b, cudaMemcpyHostToDevice, e->s_comp);
     if (err == cudaSuccess)
-      err = launch_resize_area(e->s_comp, d_in, channels, cnt, src_h, src_w, d_out, sp.dh, sp.dw, sp.x_start, sp.x_si,
-                               sp.x_alpha, sp.y_start, sp.y_si, sp.y_alpha, sp.fast, sp.ix, sp.iy);
+      err = sp.cubic ? launch_resize_cubic(e->s_comp, d_in, channels, cnt, src_h, src_w, d_out, sp.dh, sp.dw, sp.cx_idx,
+                                           sp.cx_coef, sp.cy_idx, sp.cy_coef)
+                     : launch_resize_area(e->s_comp, d_in, channels, cnt, src_h, src_w, d_out, sp.dh, sp.dw, sp.x_start,
+                                          sp.x_si, sp.x_alpha, sp.y_start, sp.y_si, sp.y_alpha, sp.fast, sp.ix, sp.iy);
     if (err == cudaSuccess) err = cudaMemcpyAsync(out + (size_t)i0 * dst_b, d_out, cnt * dst_b, cudaMemcpyDeviceToHost, e->s_comp);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
     if (err != cudaSuccess) rc = fail(e, ARU_ECUDA, "aru_scale_pages: %s", cudaGetErrorString(err));
@@ -1739,6 +1781,40 @@ int aru_open_rect(aru_engine* e, const uint8_t* mask, int n, int h, int w, int k
   cleanup();
   if (err != cudaSuccess) return fail(e, ARU_ECUDA, "aru_open_rect: %s", cudaGetErrorString(err));
   return ARU_OK;
+}
+
+int aru_swt_distance(aru_engine* e, const uint8_t* gray, int n, int h, int w, int dark_on_bright, uint8_t* out,
+                     int32_t* thresholds) {
+  if (!e || !gray || !out || n <= 0 || h <= 0 || w <= 0)
+    return e ? fail(e, ARU_EINVAL, "aru_swt_distance: bad argument") : ARU_EINVAL;
+  if (h >= 60000 || w >= 60000) return fail(e, ARU_EUNSUP, "aru_swt_distance: page dimensions must be below 60000");
+  CU(e, cudaSetDevice(e->device));
+  const size_t page_px = (size_t)h * w;
+  const int mb = (int)std::max<long long>(1, std::min<long long>(n, (256LL << 20) / (long long)page_px));
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  void* scratch = nullptr;
+  auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(scratch); };
+  if (cudaMalloc((void**)&d_in, mb * page_px) || cudaMalloc((void**)&d_out, mb * page_px) ||
+      cudaMalloc(&scratch, swt_scratch_bytes(mb, h, w))) {
+    cleanup();
+    cudaGetLastError();
+    return fail(e, ARU_ENOMEM, "aru_swt_distance: device allocation failed");
+  }
+  int rc = ARU_OK;
+  std::vector<int> thr(mb);
+  for (int i0 = 0; i0 < n && rc == ARU_OK; i0 += mb) {
+    const int cnt = std::min(mb, n - i0);
+    cudaError_t err = cudaMemcpyAsync(d_in, gray + (size_t)i0 * page_px, cnt * page_px, cudaMemcpyHostToDevice, e->s_comp);
+    if (err == cudaSuccess) err = launch_swt_distance(e->s_comp, d_in, cnt, h, w, dark_on_bright, scratch, d_out, thr.data());
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(out + (size_t)i0 * page_px, d_out, cnt * page_px, cudaMemcpyDeviceToHost, e->s_comp);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+    if (err != cudaSuccess) rc = fail(e, ARU_ECUDA, "aru_swt_distance: %s", cudaGetErrorString(err));
+    if (thresholds)
+      for (int i = 0; i < cnt; ++i) thresholds[i0 + i] = thr[i];
+  }
+  cleanup();
+  return rc;
 }
 
 int aru_pages_to_input(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, float* out) {

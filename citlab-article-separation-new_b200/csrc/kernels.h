@@ -65,6 +65,10 @@ cudaError_t launch_pages_to_input(cudaStream_t st, const uint8_t* pages, int cha
 cudaError_t launch_resize_area(cudaStream_t st, const uint8_t* src, int channels, int n, int sh, int sw, uint8_t* dst,
                                int dh, int dw, const int* x_start, const int* x_si, const float* x_alpha,
                                const int* y_start, const int* y_si, const float* y_alpha, int fast, int ix, int iy);
+// cv2.resize(INTER_CUBIC) of n uint8 pages (enlarging): per destination index 4 clamped source indices and 4 fixed-point
+// (11-bit) weights, device arrays [d][4] built by the engine
+cudaError_t launch_resize_cubic(cudaStream_t st, const uint8_t* src, int channels, int n, int sh, int sw, uint8_t* dst,
+                                int dh, int dw, const int* x_idx, const int* x_coef, const int* y_idx, const int* y_coef);
 // SeparatorNetPostProcessor.post_process on n thresholded masks of h x w: component size filter, three rectangular
 // openings and the saturating subtract; scratch >= separator_post_scratch_bytes(n, h, w)
 size_t separator_post_scratch_bytes(int n, int h, int w);
@@ -80,6 +84,12 @@ cudaError_t launch_cc_filter(cudaStream_t st, const uint8_t* mask, int n, int h,
                              uint8_t* out);
 cudaError_t launch_open_rect(cudaStream_t st, const uint8_t* mask, int n, int h, int w, int kw, int kh, void* scratch,
                              uint8_t* out);
+// StrokeWidthDistanceTransform.distance_transform (swt_dist_trafo.py:18-29) of n gray pages (swt.cu): invert, 5x5 Gaussian,
+// Otsu, exact Euclidean distance transform, uint8 truncation.  scratch >= swt_scratch_bytes(n, h, w); synchronises `st`.
+size_t swt_scratch_bytes(int n, int h, int w);
+int swt_otsu_from_hist(const unsigned* hist, long long size);
+cudaError_t launch_swt_distance(cudaStream_t st, const uint8_t* gray, int n, int h, int w, int dark_on_bright, void* scratch,
+                                uint8_t* out, int* thr_host);
 // debug read-back: chunk-planar view -> dense float32 NHWC [N][H][W][C]
 cudaError_t launch_unpack_nhwc(cudaStream_t st, PV in, const Geo& g, float* out);
 

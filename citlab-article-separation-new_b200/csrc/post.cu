@@ -168,6 +168,60 @@ cudaError_t launch_resize_area(cudaStream_t st, const uint8_t* src, int channels
   return cudaGetLastError();
 }
 
+// cv2.resize(INTER_CUBIC) for enlarging (scale_image with sc > 1, net_post_processing_helper.py:21-23): OpenCV's 8-bit
+// path in its scalar form - per destination column / row four source indices (clamped to the image) and four bicubic
+// weights (A = -0.75, computed in float32 from fx = (dx + 0.5) / sc - 0.5) as 11-bit fixed point, horizontal pass first,
+// result (sum + 2^21) >> 22 saturated.  OpenCV's SIMD builds evaluate the vertical pass in float and differ from this
+// scalar form by at most one grey level on a few percent of the pixels (tests: |device - cv2| <= 1), which is the
+// stated tolerance of this path; against the restatement (oracle/resize_oracle.py) it is bit-exact.
+template <int CH>
+__global__ void __launch_bounds__(256) k_resize_cubic(const uint8_t* __restrict__ src, int n, int sh, int sw,
+                                                      uint8_t* __restrict__ dst, int dh, int dw,
+                                                      const int* __restrict__ x_idx, const int* __restrict__ x_coef,
+                                                      const int* __restrict__ y_idx, const int* __restrict__ y_coef) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * dh * dw) return;
+  const int dx = (int)(i % dw);
+  const long long r = i / dw;
+  const int dy = (int)(r % dh), pg = (int)(r / dh);
+  const uint8_t* S = src + (long long)pg * sh * sw * CH;
+  long long acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = 0;
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    const uint8_t* row = S + (long long)y_idx[dy * 4 + ky] * sw * CH;
+    int hor[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) hor[c] = 0;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      const uint8_t* px = row + (long long)x_idx[dx * 4 + kx] * CH;
+      const int a = x_coef[dx * 4 + kx];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) hor[c] += a * px[c];
+    }
+    const int b = y_coef[dy * 4 + ky];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] += (long long)b * hor[c];
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const long long v = (acc[c] + (1LL << 21)) >> 22;
+    dst[i * CH + c] = (uint8_t)min(max(v, 0LL), 255LL);
+  }
+}
+
+cudaError_t launch_resize_cubic(cudaStream_t st, const uint8_t* src, int channels, int n, int sh, int sw, uint8_t* dst,
+                                int dh, int dw, const int* x_idx, const int* x_coef, const int* y_idx, const int* y_coef) {
+  if (channels != 1 && channels != 3) return cudaErrorInvalidValue;
+  const long long total = (long long)n * dh * dw;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (channels == 1) k_resize_cubic<1><<<blocks, 256, 0, st>>>(src, n, sh, sw, dst, dh, dw, x_idx, x_coef, y_idx, y_coef);
+  else k_resize_cubic<3><<<blocks, 256, 0, st>>>(src, n, sh, sw, dst, dh, dw, x_idx, x_coef, y_idx, y_coef);
+  return cudaGetLastError();
+}
+
 // ---- f2a: connected-component size filter ---------------------------------------------------------------------------
 // Works on the 1-bit image (bit b of word i of a row = pixel 32 i + b, pad bits 0), one thread per 32-pixel word.  The
 // union-find nodes are the in-word runs of ones: a label is the page-local pixel index of a run's first pixel, and the

@@ -31,7 +31,7 @@ EXPORTS = [
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
     "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
     "aru_box_sums", "aru_cc_filter", "aru_scaled_size", "aru_scale_pages", "aru_separator_images", "aru_heading_images",
-    "aru_bind_host_to_device",
+    "aru_bind_host_to_device", "aru_swt_distance",
 ]
 
 _lib = None
@@ -92,6 +92,7 @@ def load_library() -> ctypes.CDLL:
         lib.aru_host_free.argtypes = [vp]
         lib.aru_host_free.restype = None
         lib.aru_bind_host_to_device.argtypes = [i32, ctypes.POINTER(i32)]
+        lib.aru_swt_distance.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
         del u8p
         _lib = lib
         return lib
@@ -319,8 +320,9 @@ class Engine:
         return hh.value, ww.value
 
     def scale_pages(self, pages: np.ndarray, sc: float) -> np.ndarray:
-        """``scale_image`` for sc < 1 (helper.py:14-25): ``cv2.resize(image, None, fx=sc, fy=sc, INTER_AREA)`` of uint8
-        pages [N,H,W] / [N,H,W,3] (or one page) on the device, bit-exact against OpenCV."""
+        """``scale_image`` (helper.py:14-25) of uint8 pages [N,H,W] / [N,H,W,3] (or one page) on the device: sc < 1 is
+        ``cv2.resize(..., INTER_AREA)`` bit-exact against OpenCV; sc > 1 is ``INTER_CUBIC`` within one grey level of
+        OpenCV (its scalar fixed-point form)."""
         x, n, h, w, ch = self._as_pages(pages)
         x = np.ascontiguousarray(x)
         dh, dw = self.scaled_size(h, w, sc)
@@ -333,7 +335,7 @@ class Engine:
                          want_u8: bool = False, want_mask: bool = False, want_separators: bool = True) -> dict:
         """``load_and_scale_image`` after the decode + ``SeparatorNetPostProcessor.run`` up to the polygon step: the
         unscaled uint8 images (as ``cv2.imread`` returns them, all of one size) go up, are shrunk by ``sc`` on the device
-        (INTER_AREA; ``sc == 1`` is a no-op as in the reference, ``sc > 1`` raises: enlarge on the host), and the
+        (INTER_AREA; ``sc == 1`` is a no-op as in the reference; ``sc > 1`` is INTER_CUBIC within one grey level), and the
         results come back at the scaled size.  Same dict as ``separator_pages``."""
         self._u8_channels(0)
         x, n, h, w, ch = self._as_pages(images)
@@ -399,7 +401,7 @@ class Engine:
         return (sums, bx, u8) if want_u8 else (sums, bx)
 
     def heading_images(self, images: np.ndarray, sc: float, boxes, want_u8: bool = False):
-        """``heading_pages`` with ``scale_image`` (sc < 1, INTER_AREA) in front, on the device: unscaled uint8 images in;
+        """``heading_pages`` with ``scale_image`` in front, on the device: unscaled uint8 images in;
         ``boxes`` are in the coordinates of the scaled page (the reference rescales the text-line polygons by the same
         factor, heading_net_post_processor.py:262-263)."""
         self._u8_channels(0)
@@ -414,6 +416,23 @@ class Engine:
                                                 ctypes.c_void_p(sums.ctypes.data),
                                                 ctypes.c_void_p(u8.ctypes.data) if u8 is not None else None))
         return (sums, bx, u8) if want_u8 else (sums, bx)
+
+    def swt_distance(self, gray: np.ndarray, dark_on_bright: bool = True, return_thresholds: bool = False):
+        """``StrokeWidthDistanceTransform.distance_transform`` (swt_dist_trafo.py:18-29) of uint8 gray pages ``[H,W]`` /
+        ``[N,H,W]`` on the device: invert, 5x5 Gaussian, Otsu, exact Euclidean distance transform, uint8 truncation -
+        bit-exact against the reference (which decodes the file itself: pass ``cv2.imread(path, cv2.IMREAD_GRAYSCALE)``)."""
+        x = np.asarray(gray)
+        if x.dtype != np.uint8 or x.ndim not in (2, 3):
+            raise ValueError(f"expected uint8 [H,W] or [N,H,W] gray pages, got {x.dtype} {x.shape}")
+        single = x.ndim == 2
+        x = np.ascontiguousarray(x[None] if single else x)
+        n, h, w = x.shape
+        out = np.empty((n, h, w), np.uint8)
+        thr = np.zeros(n, np.int32)
+        self._check(self.lib.aru_swt_distance(self.handle, ctypes.c_void_p(x.ctypes.data), n, h, w, int(bool(dark_on_bright)),
+                                              ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(thr.ctypes.data)))
+        res = out[0] if single else out
+        return (res, thr) if return_thresholds else res
 
     def box_sums(self, u8: np.ndarray, boxes) -> np.ndarray:
         """Sum of channel 0 of a host uint8 map [N,H,W,C] (or [H,W,C] / [H,W]) over numpy-slice boxes."""

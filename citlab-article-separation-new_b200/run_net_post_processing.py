@@ -48,6 +48,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--mode", type=str, required=True, choices=["heading", "separator"])
     p.add_argument("--threshold", type=float, default=0.05, help="Threshold for binarization of net output.")
     p.add_argument("--gpus", type=int, default=0, help="Spawn this many single-GPU ranks (0: use the torchrun env / 1 rank).")
+    p.add_argument("--device_cubic", action="store_true",
+                   help="Enlarge small scans (scale > 1, cv2.INTER_CUBIC in the reference) on the device too: within one grey "
+                        "level of OpenCV. Default: OpenCV on the host, as the reference does.")
     p.add_argument("--dump_dir", type=str, default=None,
                    help="Write uint8 probability maps / masks + a manifest here instead of running the PAGE-XML writers.")
     return p
@@ -89,7 +92,7 @@ def _run_page(eng, image, args, fixed_height):
     sc = net_boundary._scaling_factor(image.shape[0], image.shape[1], args.scaling_factor, fixed_height=fixed_height)
     want_sep = args.mode == "separator"
     kw = dict(threshold=args.threshold, want_u8=True, want_mask=True)
-    if sc < 1.0:
+    if sc < 1.0 or (sc > 1.0 and args.device_cubic):
         h, w = eng.scaled_size(image.shape[0], image.shape[1], sc)
         try:
             return eng.separator_images(image, sc, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
@@ -112,7 +115,7 @@ def _run_heading_page(eng, image, image_path, args, fixed_height):
     boxed = [(lid, T.textline_box(pts, sc)) for lid, pts in lines if pts]
     boxes = [(0, y, y + h, x, x + w) for _, (x, y, w, h) in boxed]
     res = None
-    if sc < 1.0:
+    if sc < 1.0 or (sc > 1.0 and args.device_cubic):
         try:
             res = eng.heading_images(image, sc, boxes, want_u8=True)
         except EngineError as err:

@@ -6,7 +6,7 @@
  *     :36-53  load_graph(path_to_pb)            -> aru_create()  (+ the Python GraphDef loader)
  *     :56-72  get_net_output(image, graph, dev) -> aru_forward() (replaces tf.Session.run)
  * and, one level up, for the integer steps either side of it:
- *     :14-25  scale_image (sc < 1, cv2.resize INTER_AREA)          -> aru_scale_pages(), aru_separator_images(), aru_heading_images()
+ *     :14-25  scale_image (INTER_AREA / INTER_CUBIC)                -> aru_scale_pages(), aru_separator_images(), aru_heading_images()
  *     :31     cv2.cvtColor(BGR2GRAY) / 255.0                        -> aru_pages_to_input(), aru_separator_pages(), aru_heading_pages()
  *     :75-78  apply_threshold; separator_net_post_processor.py:147  -> the uint8 / mask outputs of aru_forward() / aru_separator_pages()
  *   region_net_post_processor_base.py:230-251  apply_cc_analysis   -> aru_cc_filter()
@@ -191,7 +191,7 @@ int aru_separator_pages(aru_engine* e, const uint8_t* pages, int channels, int n
 int aru_heading_pages(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, const int32_t* boxes,
                       int n_boxes, uint64_t* sums, uint8_t* out_u8);
 
-/* scale_image (sc < 1, INTER_AREA) + aru_heading_pages in one call; boxes are in the coordinates of the scaled page. */
+/* scale_image + aru_heading_pages in one call; boxes are in the coordinates of the scaled page. */
 int aru_heading_images(aru_engine* e, const uint8_t* images, int channels, int n, int src_h, int src_w, double sc,
                        const int32_t* boxes, int n_boxes, uint64_t* sums, uint8_t* out_u8);
 
@@ -200,10 +200,13 @@ int aru_box_sums(aru_engine* e, const uint8_t* u8, int n, int h, int w, int c, c
                  uint64_t* sums);
 
 /*
- * scale_image on the device (net_post_processing_helper.py:14-25) for the shrinking case sc < 1:
- * cv2.resize(image, None, fx=sc, fy=sc, interpolation=cv2.INTER_AREA), bit-exact against OpenCV (general and integer
- * scales).  sc > 1 (INTER_CUBIC in the reference) is ARU_EUNSUP: enlarge on the host.  The destination size is
- * (cvRound(src_h*sc), cvRound(src_w*sc)) = aru_scaled_size().
+ * scale_image on the device (net_post_processing_helper.py:14-25):
+ *   sc < 1  cv2.resize(image, None, fx=sc, fy=sc, interpolation=cv2.INTER_AREA), bit-exact against OpenCV (general and
+ *           integer scales);
+ *   sc > 1  cv2.resize(..., interpolation=cv2.INTER_CUBIC) in OpenCV's scalar fixed-point form: the destination size is
+ *           OpenCV's, the values are within ONE grey level of cv2.resize (its SIMD builds evaluate the vertical pass in
+ *           float; ~6 % of the pixels differ by 1) - the stated tolerance of the enlarging path.
+ * The destination size is (cvRound(src_h*sc), cvRound(src_w*sc)) = aru_scaled_size().
  *   aru_scale_pages       uint8 [n,src_h,src_w,channels] -> uint8 [n,h,w,channels], host memory in and out
  *   aru_separator_images  = scale_image + aru_separator_pages in one call: the unscaled uint8 images go up, the
  *                           outputs have the scaled size (sc == 1: no resize, as in the reference)
@@ -225,6 +228,17 @@ int aru_cc_filter(aru_engine* e, const uint8_t* mask, int n, int h, int w, int m
 /* cv2.morphologyEx(mask, MORPH_OPEN, getStructuringElement(MORPH_RECT, (kw, kh))) for kw == 1 or kh == 1 on binary
  * masks (non-zero = 255), host memory in and out; exposed for the parity tests of the morphology kernels. */
 int aru_open_rect(aru_engine* e, const uint8_t* mask, int n, int h, int w, int kw, int kh, uint8_t* out);
+
+/*
+ * StrokeWidthDistanceTransform.distance_transform (python_util/image_processing/swt_dist_trafo.py:18-29) - the SWT feature
+ * image HeadingNetPostProcessor computes twice per page at full image resolution (heading_net_post_processor.py:86,297):
+ * 255 - gray (dark_on_bright), cv2.GaussianBlur 5x5 sigma 0, cv2.threshold OTSU, cv2.distanceTransform(DIST_L2,
+ * DIST_MASK_PRECISE), astype(uint8).  Bit-exact against the reference's function (the decode, cv2.imread(GRAYSCALE),
+ * stays with the caller).
+ *   gray        uint8 [n,h,w] host memory;   out  uint8 [n,h,w];   thresholds  int32 [n] Otsu thresholds, or NULL
+ */
+int aru_swt_distance(aru_engine* e, const uint8_t* gray, int n, int h, int w, int dark_on_bright, uint8_t* out,
+                     int32_t* thresholds);
 
 /* The colour step alone: uint8 pages [n,h,w,channels] -> float32 [n,h,w] = gray / 255.0 (helper.py:31). */
 int aru_pages_to_input(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, float* out);

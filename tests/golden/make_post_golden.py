@@ -135,3 +135,33 @@ if __name__ == "__main__":
         cases[name + "_sc"] = np.float64(sc)
     np.savez_compressed(os.path.join(HERE, "post_resize.npz"), **cases)
     print("post_resize:", len(cases) // 3, "cases")
+
+    # SWT feature image (python_util/image_processing/swt_dist_trafo.py:18-29) by the reference's own class: it reads the
+    # file itself, so every page goes through a temporary PNG
+    import tempfile
+    from python_util.image_processing.swt_dist_trafo import StrokeWidthDistanceTransform
+    from aru_b200.synth import synth_page
+    from oracle import swt_oracle as S
+    swt = StrokeWidthDistanceTransform(dark_on_bright=True)
+    rng = np.random.default_rng(31)
+    pages = {"page": synth_page(300, 220, 1), "odd": synth_page(257, 131, 2),
+             "noise": rng.integers(0, 256, size=(90, 140), dtype=np.uint8)}
+    blob = synth_page(400, 300, 3)
+    blob[50:350, 40:260] = 20                         # a photograph-sized dark block: distances up to 110
+    pages["blob"] = blob
+    wrap = np.full((700, 600), 230, np.uint8)
+    wrap[20:680, 10:590] = 10                         # distances beyond 255: the uint8 cast wraps
+    pages["wrap"] = wrap
+    pages["flat"] = np.full((40, 50), 17, np.uint8)   # no pixel at or below the Otsu threshold: all zeros
+    out = {}
+    for name, gray in pages.items():
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "page.png")
+            cv2.imwrite(path, gray)
+            with np.errstate(invalid="ignore"):
+                ref = swt.distance_transform(path)
+        mine, thr, _ = S.swt_distance_transform(gray)
+        assert ref.dtype == np.uint8 and np.array_equal(mine, ref), name
+        out[name + "_gray"], out[name + "_dt"], out[name + "_thr"] = gray, ref, np.int32(thr)
+        print(f"post_swt {name}: {gray.shape} otsu {thr} max distance {int(ref.max())}")
+    np.savez_compressed(os.path.join(HERE, "post_swt.npz"), **out)

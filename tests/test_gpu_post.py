@@ -434,3 +434,56 @@ def test_page_level_calls_with_a_one_class_sigmoid_net(built_lib):
             assert int(s) == O.box_sum_u8(r["u8"][pg], ya, yb, xa, xb)
     finally:
         e.close()
+
+
+def test_swt_distance_matches_reference_golden(eng):
+    """aru_swt_distance against tests/golden/post_swt.npz, which the reference's own
+    StrokeWidthDistanceTransform.distance_transform (swt_dist_trafo.py:18-29) produced: blob-sized distances, the uint8
+    wrap beyond 255, a page without any pixel below the Otsu threshold."""
+    z = np.load(os.path.join(GOLDEN, "post_swt.npz"))
+    for name in sorted(k[:-5] for k in z.files if k.endswith("_gray")):
+        dt, thr = eng.swt_distance(z[name + "_gray"], return_thresholds=True)
+        assert int(thr[0]) == int(z[name + "_thr"]), name
+        assert np.array_equal(dt, z[name + "_dt"]), name
+
+
+@pytest.mark.parametrize("h,w,n", [(1, 1, 1), (7, 300, 2), (257, 131, 3), (1500, 1125, 2), (3000, 2250, 1)])
+def test_swt_distance_against_opencv_on_pages(eng, h, w, n):
+    from aru_b200.synth import synth_page
+    from test_post_oracle import _swt_cv2
+    pages = np.stack([synth_page(h, w, seed=900 + 13 * i + h) for i in range(n)])
+    if h > 100:
+        pages[0, h // 4:h // 2, w // 5:w // 2] = 25          # a dark block: large distances in one page of the batch
+    got = eng.swt_distance(pages)
+    for i in range(n):
+        assert np.array_equal(got[i], _swt_cv2(pages[i])), (h, w, i)
+
+
+@pytest.mark.parametrize("shape,sc", [((120, 90, 3), 1.125), ((97, 131), 1.5), ((64, 80, 3), 2.0), ((333, 250, 3), 900 / 800),
+                                      ((800, 600), 1.125)])
+def test_scale_pages_enlarging_cubic(eng, shape, sc):
+    """scale_image for sc > 1 (cv2.INTER_CUBIC, helper.py:21-23) on the device: bit-exact against the fixed-point
+    restatement, within one grey level of cv2.resize itself (the stated tolerance of this path)."""
+    import cv2
+    from oracle import resize_oracle as R
+    rng = np.random.default_rng(17)
+    imgs = rng.integers(0, 256, size=(2,) + shape, dtype=np.uint8)
+    got = eng.scale_pages(imgs, sc)
+    for i in range(2):
+        ref = cv2.resize(imgs[i], None, fx=sc, fy=sc, interpolation=cv2.INTER_CUBIC)
+        assert got[i].shape == ref.shape
+        assert np.array_equal(got[i], R.resize_cubic(imgs[i], sc))
+        assert np.abs(got[i].astype(int) - ref.astype(int)).max() <= 1
+
+
+def test_separator_images_enlarging(eng):
+    """A scan smaller than the net input (fixed height above the image height): device cubic + net == device cubic, then
+    the page call on the enlarged page."""
+    from aru_b200.synth import synth_page
+    page = synth_page(160, 120, 5)
+    sc = 1.25
+    big = eng.scale_pages(page, sc)
+    a = eng.separator_images(page, sc, want_u8=True, want_mask=True)
+    b = eng.separator_pages(big, want_u8=True, want_mask=True)
+    for k in ("u8", "mask", "horizontal", "vertical"):
+        assert np.array_equal(a[k], b[k]), k

@@ -1,5 +1,5 @@
 """Output equivalence one level above the masks (BASELINE north_star: identical separator polylines / heading flags):
-the ENGINE's uint8 maps for 100 synthetic pages (tests/golden/equiv_engine_r02.npz, written on a B200 by
+the ENGINE's uint8 maps for 100 synthetic pages (tests/golden/equiv/engine_r02.npz, written on a B200 by
 tools/equivalence_gpu.py) against the fp32 oracle's maps of the same pages, both pushed through the reference's own code
 where polygon extraction starts:
 
@@ -36,7 +36,7 @@ from aru_b200.synth import page_to_net_input, synth_page  # noqa: E402
 from oracle import separator_post_oracle as post_oracle  # noqa: E402
 from oracle.aru_oracle import Oracle  # noqa: E402
 
-FIXTURE = os.path.join(HERE, "golden", "equiv_engine_r02.npz")
+FIXTURE = os.path.join(HERE, "golden", "equiv", "engine_r02.npz")
 HAVE_REFERENCE = os.path.isdir("/root/reference/article_separation")
 SC = 0.5      # the page was shrunk by 0.5 for the net; polygons go back to image coordinates with 1 / sc
 

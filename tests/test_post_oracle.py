@@ -136,3 +136,49 @@ def test_resize_oracle_against_opencv():
     for sh, sw, sc in ((97, 131, 0.73), (200, 150, 0.375), (120, 90, 0.5), (150, 93, 1 / 3), (64, 64, 0.25), (333, 77, 0.9017)):
         img = rng.integers(0, 256, size=(sh, sw, 3), dtype=np.uint8)
         assert np.array_equal(R.resize_area(img, sc), cv2.resize(img, None, fx=sc, fy=sc, interpolation=cv2.INTER_AREA)), (sh, sw, sc)
+
+
+def _swt_cv2(gray):
+    """The reference's distance_transform after its cv2.imread (swt_dist_trafo.py:19-24), same OpenCV calls."""
+    import cv2
+    image = -gray + 255
+    blur = cv2.GaussianBlur(image, (5, 5), 0)
+    _, image_t = cv2.threshold(blur, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+    with np.errstate(invalid="ignore"):
+        return cv2.distanceTransform(image_t, cv2.DIST_L2, cv2.DIST_MASK_PRECISE).astype(np.uint8)
+
+
+def test_swt_oracle_reproduces_reference_fixture():
+    """tests/golden/post_swt.npz was written by the reference's own StrokeWidthDistanceTransform.distance_transform."""
+    from oracle import swt_oracle as S
+    z = np.load(os.path.join(GOLDEN, "post_swt.npz"))
+    names = sorted(k[:-5] for k in z.files if k.endswith("_gray"))
+    assert len(names) >= 6
+    for name in names:
+        dt, thr, _ = S.swt_distance_transform(z[name + "_gray"])
+        assert thr == int(z[name + "_thr"]) and np.array_equal(dt, z[name + "_dt"]), name
+
+
+def test_swt_oracle_against_opencv():
+    from aru_b200.synth import synth_page
+    from oracle import swt_oracle as S
+    rng = np.random.default_rng(5)
+    for gray in (synth_page(120, 97, 8), rng.integers(0, 256, size=(33, 61), dtype=np.uint8),
+                 np.where(rng.random((70, 90)) < 0.5, 200, 30).astype(np.uint8), synth_page(64, 5, 2)):
+        assert np.array_equal(S.swt_distance_transform(gray)[0], _swt_cv2(gray))
+
+
+def test_cubic_restatement_is_within_one_grey_level_of_opencv():
+    """scale_image for sc > 1 (helper.py:21-23) calls cv2.resize(INTER_CUBIC).  The fixed-point restatement the device
+    kernel follows reproduces OpenCV's destination size exactly and its values to one grey level (OpenCV's SIMD vertical
+    pass works in float) - the stated tolerance of the enlarging path."""
+    import cv2
+    from oracle import resize_oracle as R
+    rng = np.random.default_rng(3)
+    for shape, sc in (((120, 90, 3), 1.125), ((97, 131), 1.5), ((64, 80, 3), 2.0), ((50, 60), 3.3), ((31, 17, 3), 900 / 800)):
+        img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        ref = cv2.resize(img, None, fx=sc, fy=sc, interpolation=cv2.INTER_CUBIC)
+        mine = R.resize_cubic(img, sc)
+        assert mine.shape == ref.shape
+        d = np.abs(mine.astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.15, (shape, sc, int(d.max()), float((d > 0).mean()))

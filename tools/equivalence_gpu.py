@@ -1,6 +1,6 @@
 """GPU half of the polygon / heading-flag equivalence check (north_star: identical separator polylines / heading flags
 on >= 99 % of pages): the ENGINE's uint8 maps and text-line sums for 100 synthetic pages, written to
-gpurun_out/equiv_engine_r02.npz and committed as tests/golden/equiv_engine_r02.npz.  The CPU half
+gpurun_out/equiv_engine_r02.npz and committed as tests/golden/equiv/engine_r02.npz.  The CPU half
 (tests/test_polygon_equivalence.py) recomputes the same quantities with the fp32 oracle and drives the reference's real
 to_polygons / rescale_polygons over both.
 
