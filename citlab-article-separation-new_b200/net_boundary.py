@@ -152,6 +152,18 @@ def apply_cc_analysis(self, net_output, threshold):
     return eng.cc_size_filter(np.ascontiguousarray(net_output), min_size).astype(net_output.dtype, copy=False)
 
 
+def heading_swt_features_image(self, image_path):
+    """Drop-in for ``HeadingNetPostProcessor.get_swt_features_image`` (heading_net_post_processor.py:215-220), i.e.
+    ``StrokeWidthDistanceTransform.distance_transform`` (swt_dist_trafo.py:18-24), which the heading post-processor runs
+    twice per page on the full-resolution scan (head:86,297): the decode stays ``cv2.imread(path, IMREAD_GRAYSCALE)`` as in
+    the reference; inversion, 5x5 Gaussian, Otsu threshold and the exact Euclidean distance transform run on the GPU
+    (csrc/swt.cu, bit-exact against the reference's function)."""
+    import cv2
+    image = cv2.imread(image_path, cv2.IMREAD_GRAYSCALE)
+    eng = self.pb_graph.engine(resolve_device(getattr(self, "gpu_devices", "")))
+    return eng.swt_distance(image, dark_on_bright=getattr(self.SWT, "_dark_on_bright", True))
+
+
 def separator_pages(images_bgr, pb_graph: GraphHandle, threshold=0.05, gpu_device="0", **kw):
     """One call for ``SeparatorNetPostProcessor.run`` up to the polygon step (sep:141-151) on uint8 pages as
     ``cv2.imread`` / ``scale_image`` return them ([N,H,W,3] BGR, or [N,H,W] gray): see ``Engine.separator_pages``."""
@@ -194,13 +206,18 @@ def install(patch_post_process: bool = True):
 
 
 def patch_separator_post_processor() -> bool:
-    """Rebind ``SeparatorNetPostProcessor.post_process`` to the GPU version; returns False when the reference class has
-    not been imported (call again after importing it)."""
+    """Rebind ``SeparatorNetPostProcessor.post_process``, ``RegionNetPostProcessor.apply_cc_analysis`` and
+    ``HeadingNetPostProcessor.get_swt_features_image`` to the GPU versions; returns False when the reference classes have
+    not been imported (call again after importing them)."""
     pkg = REFERENCE_MODULE.rsplit(".", 1)[0]
     base = sys.modules.get(pkg + ".region_net_post_processor_base")
     base_cls = getattr(base, "RegionNetPostProcessor", None) if base is not None else None
     if base_cls is not None:
         base_cls.apply_cc_analysis = apply_cc_analysis      # separator, text-block and any other region post-processor
+    head = sys.modules.get(pkg + ".heading_net_post_processor")
+    head_cls = getattr(head, "HeadingNetPostProcessor", None) if head is not None else None
+    if head_cls is not None:
+        head_cls.get_swt_features_image = heading_swt_features_image
     mod = sys.modules.get(pkg + ".separator_net_post_processor")
     cls = getattr(mod, "SeparatorNetPostProcessor", None) if mod is not None else None
     if cls is None:

@@ -42,6 +42,7 @@ assert sep.SeparatorNetPostProcessor.post_process is nb.separator_post_process
 # subclasses resolve the rebound methods; the heading / text-block classes keep their own post_process
 assert tb.TextBlockNetPostProcessor.apply_cc_analysis is nb.apply_cc_analysis
 assert head.HeadingNetPostProcessor.apply_cc_analysis is nb.apply_cc_analysis
+assert head.HeadingNetPostProcessor.get_swt_features_image is nb.heading_swt_features_image
 assert importlib.import_module(nb.REFERENCE_MODULE) is nb
 # the constructor of the real class goes through our load_graph and keeps our handle
 import tempfile, os
@@ -74,5 +75,6 @@ def test_install_before_the_classes_are_imported():
 assert nb.install() is nb
 import importlib
 importlib.import_module(PKG + 'separator_net_post_processor')
+importlib.import_module(PKG + 'heading_net_post_processor')
 assert nb.patch_separator_post_processor() is True
 """)

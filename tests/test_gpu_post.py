@@ -330,7 +330,7 @@ def test_scale_pages_against_oracle_batches_and_sizes(eng):
         for i in range(3):
             assert np.array_equal(got[i], R.resize_area(imgs[i], sc)), (sh, sw, ch, sc, i)
     with pytest.raises(EngineError):
-        eng.scale_pages(np.zeros((64, 64), np.uint8), 1.5)       # enlarging is INTER_CUBIC: host
+        eng.scale_pages(np.zeros((64, 64), np.uint8), 1.0)       # the reference does not resize at sc == 1 (helper.py:19-23)
 
 
 def test_separator_images_is_scale_image_plus_separator_pages(eng):

@@ -142,7 +142,14 @@ def _swt_cv2(gray):
     """The reference's distance_transform after its cv2.imread (swt_dist_trafo.py:19-24), same OpenCV calls."""
     import cv2
     image = -gray + 255
-    blur = cv2.GaussianBlur(image, (5, 5), 0)
+    # OpenCV 4.13's multi-threaded GaussianBlur is not deterministic on images of a few rows (8 x 40 with 8 threads gives
+    # two different results run to run); single-threaded it is, and that is what the restatement reproduces
+    threads = cv2.getNumThreads()
+    cv2.setNumThreads(1)
+    try:
+        blur = cv2.GaussianBlur(image, (5, 5), 0)
+    finally:
+        cv2.setNumThreads(threads)
     _, image_t = cv2.threshold(blur, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
     with np.errstate(invalid="ignore"):
         return cv2.distanceTransform(image_t, cv2.DIST_L2, cv2.DIST_MASK_PRECISE).astype(np.uint8)
