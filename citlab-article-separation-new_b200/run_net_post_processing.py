@@ -48,6 +48,13 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--mode", type=str, required=True, choices=["heading", "separator"])
     p.add_argument("--threshold", type=float, default=0.05, help="Threshold for binarization of net output.")
     p.add_argument("--gpus", type=int, default=0, help="Spawn this many single-GPU ranks (0: use the torchrun env / 1 rank).")
+    p.add_argument("--decode_threads", type=int, default=0,
+                   help="--dump_dir: threads that decode images ahead of the GPU and encode the results behind it "
+                        "(0 = the CPUs this rank may use, at most 16).")
+    p.add_argument("--batch_pages", type=int, default=16,
+                   help="--dump_dir: pages of one size that go to the GPU in one call.")
+    p.add_argument("--dump_format", type=str, default="png", choices=["png", "none"],
+                   help="--dump_dir: png = probability / mask images per page; none = manifest only (throughput runs).")
     p.add_argument("--device_cubic", action="store_true",
                    help="Enlarge small scans (scale > 1, cv2.INTER_CUBIC in the reference) on the device too: within one grey "
                         "level of OpenCV. Default: OpenCV on the host, as the reference does.")
@@ -84,55 +91,6 @@ def _reference_available() -> bool:
         return False
 
 
-def _run_page(eng, image, args, fixed_height):
-    """One decoded page (uint8 BGR as ``cv2.imread`` returns it) through ``load_and_scale_image``'s remaining steps, the net
-    and the integer post-processing.  Shrinking (INTER_AREA, the usual case: scans are larger than the net input), the
-    colour step, the net, uint8 / threshold and ``post_process`` run on the device; enlarging (INTER_CUBIC) is done by
-    cv2 on the host as in the reference.  Returns (result dict, scale, (H, W) of the net input)."""
-    sc = net_boundary._scaling_factor(image.shape[0], image.shape[1], args.scaling_factor, fixed_height=fixed_height)
-    want_sep = args.mode == "separator"
-    kw = dict(threshold=args.threshold, want_u8=True, want_mask=True)
-    if sc < 1.0 or (sc > 1.0 and args.device_cubic):
-        h, w = eng.scaled_size(image.shape[0], image.shape[1], sc)
-        try:
-            return eng.separator_images(image, sc, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
-        except EngineError as err:
-            if err.code != ARU_EUNSUP:      # an integer scale with a partial last cell: resize on the host
-                raise
-    image, sc = net_boundary.scale_image(image, fixed_height, args.scaling_factor)
-    h, w = image.shape[:2]
-    return eng.separator_pages(image, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
-
-
-def _run_heading_page(eng, image, image_path, args, fixed_height):
-    """Heading mode for one decoded page: the net's uint8 map and, when ``<dir>/page/<stem>.xml`` exists, the network
-    feature of every TextLine - ``get_net_prob_for_text_line`` (heading_net_post_processor.py:247-270), box sums on the
-    device.  Returns (uint8 map [H,W,C], {text line id: probability} or None, scale, (H, W))."""
-    from . import page_textlines as T
-    sc = net_boundary._scaling_factor(image.shape[0], image.shape[1], args.scaling_factor, fixed_height=fixed_height)
-    page_xml = T.page_path_for_image(image_path)
-    lines = T.read_textlines(page_xml) if os.path.exists(page_xml) else []
-    boxed = [(lid, T.textline_box(pts, sc)) for lid, pts in lines if pts]
-    boxes = [(0, y, y + h, x, x + w) for _, (x, y, w, h) in boxed]
-    res = None
-    if sc < 1.0 or (sc > 1.0 and args.device_cubic):
-        try:
-            res = eng.heading_images(image, sc, boxes, want_u8=True)
-        except EngineError as err:
-            if err.code != ARU_EUNSUP:
-                raise
-    if res is None:
-        scaled = net_boundary.scale_image(image, fixed_height, args.scaling_factor)[0]
-        res = eng.heading_pages(scaled, boxes, want_u8=True)
-    sums, _, u8 = res
-    probs = None
-    if lines:
-        probs = {lid: 0 for lid, pts in lines if not pts}          # no surrounding polygon: 0 (head:259-260)
-        for (lid, (x, y, w, h)), s_ in zip(boxed, sums):
-            probs[lid] = T.net_prob(int(s_), w, h)
-    return u8[0], probs, sc, u8.shape[1:3]
-
-
 def run_rank(args, rank: int, world: int, local_rank: int) -> int:
     paths = net_boundary.load_image_paths(args.path_to_image_list)
     shard = sharding.shard_for_rank(paths, world, rank, _pixel_counts(paths))
@@ -161,39 +119,161 @@ def run_rank(args, rank: int, world: int, local_rank: int) -> int:
                                      "sw_th_thresh": 0.9}, 0.8).run(gpu_device="")
         return len(shard)
 
+    return _run_rank_dump(args, shard, rank, world, fixed_height)
+
+
+def _run_pages(eng, images, args, fixed_height):
+    """A batch of decoded pages of ONE size (uint8 [n,H,W,3] as ``cv2.imread`` returns them) through
+    ``load_and_scale_image``'s remaining steps, the net and the integer post-processing.  Shrinking (INTER_AREA, the usual
+    case: scans are larger than the net input), the colour step, the net, uint8 / threshold and ``post_process`` run on the
+    device; enlarging (INTER_CUBIC) is done by cv2 on the host as in the reference unless ``--device_cubic``.
+    Returns (result dict of [n,...] arrays, scale, (H, W) of the net input)."""
+    sc = net_boundary._scaling_factor(images.shape[1], images.shape[2], args.scaling_factor, fixed_height=fixed_height)
+    want_sep = args.mode == "separator"
+    kw = dict(threshold=args.threshold, want_u8=True, want_mask=True, u8_channels=1)
+    if sc < 1.0 or (sc > 1.0 and args.device_cubic):
+        h, w = eng.scaled_size(images.shape[1], images.shape[2], sc)
+        try:
+            return eng.separator_images(images, sc, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
+        except EngineError as err:
+            if err.code != ARU_EUNSUP:
+                raise
+    scaled = np.stack([net_boundary.scale_image(im, fixed_height, args.scaling_factor)[0] for im in images])
+    h, w = scaled.shape[1:3]
+    return eng.separator_pages(scaled, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
+
+
+def _run_heading_pages(eng, images, paths, args, fixed_height):
+    """Heading mode for a batch of decoded pages of one size: the net's uint8 map and, for the pages that have a
+    ``<dir>/page/<stem>.xml``, the network feature of every TextLine - ``get_net_prob_for_text_line``
+    (heading_net_post_processor.py:247-270), box sums on the device.
+    Returns ([(uint8 map [H,W,C], {text line id: probability} or None)], scale, (H, W))."""
+    from . import page_textlines as T
+    sc = net_boundary._scaling_factor(images.shape[1], images.shape[2], args.scaling_factor, fixed_height=fixed_height)
+    per_page, boxes = [], []
+    for i, path in enumerate(paths):
+        page_xml = T.page_path_for_image(path)
+        lines = T.read_textlines(page_xml) if os.path.exists(page_xml) else []
+        boxed = [(lid, T.textline_box(pts, sc)) for lid, pts in lines if pts]
+        per_page.append((lines, boxed, len(boxes)))
+        boxes += [(i, y, y + h, x, x + w) for _, (x, y, w, h) in boxed]
+    res = None
+    if sc < 1.0 or (sc > 1.0 and args.device_cubic):
+        try:
+            res = eng.heading_images(images, sc, boxes, want_u8=True)
+        except EngineError as err:
+            if err.code != ARU_EUNSUP:
+                raise
+    if res is None:
+        scaled = np.stack([net_boundary.scale_image(im, fixed_height, args.scaling_factor)[0] for im in images])
+        res = eng.heading_pages(scaled, boxes, want_u8=True)
+    sums, _, u8 = res
+    out = []
+    for i, (lines, boxed, b0) in enumerate(per_page):
+        probs = None
+        if lines:
+            probs = {lid: 0 for lid, pts in lines if not pts}          # no surrounding polygon: 0 (head:259-260)
+            for k, (lid, (x, y, w, h)) in enumerate(boxed):
+                probs[lid] = T.net_prob(int(sums[b0 + k]), w, h)
+        out.append((u8[i], probs))
+    return out, sc, u8.shape[1:3]
+
+
+def _run_rank_dump(args, shard, rank, world, fixed_height) -> int:
+    """--dump_dir: decode -> GPU -> encode as a pipeline.  The reference reads, runs and writes one page at a time per worker
+    process (run_net_post_processing.py:59-82, separator_net_post_processor.py:141); here a thread pool decodes ahead of
+    the GPU (``cv2.imread`` releases the GIL), decoded pages of one size are batched into one device call (the engine
+    micro-batches and overlaps copies with compute inside it), and the same pool encodes / writes the results behind."""
+    import collections
+    import itertools
     import cv2
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(args.dump_dir, exist_ok=True)
     manifest_path = os.path.join(args.dump_dir, f"manifest_rank{rank}.json")
     done = {}
     if os.path.exists(manifest_path):
         with open(manifest_path) as f:
             done = json.load(f).get("pages", {})
+    todo = [p for p in shard if p not in done]
     graph = net_boundary.load_graph(args.path_to_pb)
-    eng = graph.engine(net_boundary.resolve_device(""))
-    for path in shard:
-        if path in done:
-            continue
-        stem = os.path.splitext(os.path.basename(path))[0]
-        if args.mode == "heading":
-            u8, probs, sc, shape = _run_heading_page(eng, cv2.imread(path), path, args, fixed_height)
-            cv2.imwrite(os.path.join(args.dump_dir, stem + "_prob.png"), np.ascontiguousarray(u8[:, :, 0]))
-            if probs is not None:
-                with open(os.path.join(args.dump_dir, stem + "_textlines.json"), "w") as f:
-                    json.dump(probs, f)
-            done[path] = {"scale": sc, "shape": list(shape)}
-            with open(manifest_path, "w") as f:
-                json.dump({"rank": rank, "world": world, "pages": done}, f)
-            continue
-        r, sc, shape = _run_page(eng, cv2.imread(path), args, fixed_height)
-        cv2.imwrite(os.path.join(args.dump_dir, stem + "_prob.png"), np.ascontiguousarray(r["u8"][0, :, :, 0]))
-        if args.mode == "separator":
-            cv2.imwrite(os.path.join(args.dump_dir, stem + "_mask.png"), np.ascontiguousarray(r["mask"][0]))
-        if "horizontal" in r:
-            cv2.imwrite(os.path.join(args.dump_dir, stem + "_horizontal.png"), np.ascontiguousarray(r["horizontal"][0]))
-            cv2.imwrite(os.path.join(args.dump_dir, stem + "_vertical.png"), np.ascontiguousarray(r["vertical"][0]))
-        done[path] = {"scale": sc, "shape": list(shape)}
+    eng = graph.engine(net_boundary.resolve_device(""))          # binds this rank's threads to the GPU's NUMA node
+    n_threads = args.decode_threads or max(1, min(16, len(os.sched_getaffinity(0))))
+    batch = max(1, args.batch_pages)
+    def write_png(name, arr):
+        if args.dump_format == "png":
+            cv2.imwrite(os.path.join(args.dump_dir, name), np.ascontiguousarray(arr))
+
+    def save_manifest():
         with open(manifest_path, "w") as f:
             json.dump({"rank": rank, "world": world, "pages": done}, f)
+
+    def flush(group, pool):
+        """One device call for a group of same-size pages; returns (manifest entries, futures of their file writes)."""
+        paths = [p for p, _ in group]
+        images = np.stack([im for _, im in group])
+        entries, futs = {}, []
+        if args.mode == "heading":
+            pages, sc, shape = _run_heading_pages(eng, images, paths, args, fixed_height)
+            for path, (u8, probs) in zip(paths, pages):
+                stem = os.path.splitext(os.path.basename(path))[0]
+                futs.append(pool.submit(write_png, stem + "_prob.png", u8[:, :, 0].copy()))
+                if probs is not None:
+                    with open(os.path.join(args.dump_dir, stem + "_textlines.json"), "w") as f:
+                        json.dump(probs, f)
+                entries[path] = {"scale": sc, "shape": list(shape)}
+        else:
+            r, sc, shape = _run_pages(eng, images, args, fixed_height)
+            for i, path in enumerate(paths):
+                stem = os.path.splitext(os.path.basename(path))[0]
+                futs.append(pool.submit(write_png, stem + "_prob.png", r["u8"][i, :, :, 0].copy()))
+                futs.append(pool.submit(write_png, stem + "_mask.png", r["mask"][i].copy()))
+                if "horizontal" in r:
+                    futs.append(pool.submit(write_png, stem + "_horizontal.png", r["horizontal"][i].copy()))
+                    futs.append(pool.submit(write_png, stem + "_vertical.png", r["vertical"][i].copy()))
+                entries[path] = {"scale": sc, "shape": list(shape)}
+        return entries, futs
+
+    in_flight = collections.deque()          # (manifest entries, write futures) of flushed groups, oldest first
+
+    def retire(keep):
+        """A page enters the manifest once its files are on disk (a re-run skips exactly the pages listed there)."""
+        while len(in_flight) > keep:
+            entries, futs = in_flight.popleft()
+            for f in futs:
+                f.result()
+            done.update(entries)
+            save_manifest()
+
+    import time
+    t_start = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as pool:
+        it = iter(todo)
+        window = collections.deque((p, pool.submit(cv2.imread, p)) for p in itertools.islice(it, 2 * n_threads + batch))
+        pending = collections.OrderedDict()                      # decoded pages waiting for a full batch, per image size
+        while window:
+            path, fut = window.popleft()
+            nxt = next(it, None)
+            if nxt is not None:
+                window.append((nxt, pool.submit(cv2.imread, nxt)))
+            image = fut.result()
+            if image is None:
+                raise SystemExit(f"cannot read image {path}")
+            group = pending.setdefault(image.shape, [])
+            group.append((path, image))
+            if len(group) >= batch:
+                in_flight.append(flush(pending.pop(image.shape), pool))
+            elif sum(len(g) for g in pending.values()) > 4 * batch:   # many sizes in flight: run the oldest group
+                in_flight.append(flush(pending.pop(next(iter(pending))), pool))
+            retire(keep=2)
+        for shape in list(pending):
+            in_flight.append(flush(pending.pop(shape), pool))
+        retire(keep=0)
+    save_manifest()
+    dt = time.perf_counter() - t_start
+    # one line per rank: pages from disk to results on disk, engine start-up excluded (tools/file_throughput.py adds them up)
+    print(json.dumps({"rank": rank, "world": world, "mode": args.mode, "pages": len(todo), "seconds": round(dt, 4),
+                      "pages_per_s": round(len(todo) / dt, 1) if dt > 0 else None, "decode_threads": n_threads,
+                      "batch_pages": batch, "dump_format": args.dump_format}), file=sys.stderr, flush=True)
     return len(shard)
 
 
