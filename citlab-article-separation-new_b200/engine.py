@@ -332,12 +332,13 @@ class Engine:
         return out
 
     def separator_images(self, images: np.ndarray, sc: float, threshold: float = 0.05, want_prob: bool = False,
-                         want_u8: bool = False, want_mask: bool = False, want_separators: bool = True) -> dict:
+                         want_u8: bool = False, want_mask: bool = False, want_separators: bool = True,
+                         u8_channels: int = 0) -> dict:
         """``load_and_scale_image`` after the decode + ``SeparatorNetPostProcessor.run`` up to the polygon step: the
         unscaled uint8 images (as ``cv2.imread`` returns them, all of one size) go up, are shrunk by ``sc`` on the device
         (INTER_AREA; ``sc == 1`` is a no-op as in the reference; ``sc > 1`` is INTER_CUBIC within one grey level), and the
         results come back at the scaled size.  Same dict as ``separator_pages``."""
-        self._u8_channels(0)
+        cu = self._u8_channels(u8_channels)
         x, n, h, w, ch = self._as_pages(images)
         x = np.ascontiguousarray(x)
         dh, dw = (h, w) if sc == 1.0 else self.scaled_size(h, w, sc)
@@ -346,7 +347,7 @@ class Engine:
         if want_prob:
             res["prob"] = pinned_empty((n, dh, dw, c), np.float32)
         if want_u8:
-            res["u8"] = pinned_empty((n, dh, dw, c), np.uint8)
+            res["u8"] = pinned_empty((n, dh, dw, cu), np.uint8)
         if want_mask:
             res["mask"] = pinned_empty((n, dh, dw), np.uint8)
         if want_separators:

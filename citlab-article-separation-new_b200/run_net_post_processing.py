@@ -143,7 +143,13 @@ def _run_pages(eng, images, args, fixed_height):
     return eng.separator_pages(scaled, want_separators=want_sep and h >= 50 and w >= 100, **kw), sc, (h, w)
 
 
-def _run_heading_pages(eng, images, paths, args, fixed_height):
+def _read_page_textlines(image_path):
+    from . import page_textlines as T
+    page_xml = T.page_path_for_image(image_path)
+    return T.read_textlines(page_xml) if os.path.exists(page_xml) else []
+
+
+def _run_heading_pages(eng, images, paths, args, fixed_height, textlines=None):
     """Heading mode for a batch of decoded pages of one size: the net's uint8 map and, for the pages that have a
     ``<dir>/page/<stem>.xml``, the network feature of every TextLine - ``get_net_prob_for_text_line``
     (heading_net_post_processor.py:247-270), box sums on the device.
@@ -152,8 +158,7 @@ def _run_heading_pages(eng, images, paths, args, fixed_height):
     sc = net_boundary._scaling_factor(images.shape[1], images.shape[2], args.scaling_factor, fixed_height=fixed_height)
     per_page, boxes = [], []
     for i, path in enumerate(paths):
-        page_xml = T.page_path_for_image(path)
-        lines = T.read_textlines(page_xml) if os.path.exists(page_xml) else []
+        lines = textlines[i] if textlines is not None else _read_page_textlines(path)
         boxed = [(lid, T.textline_box(pts, sc)) for lid, pts in lines if pts]
         per_page.append((lines, boxed, len(boxes)))
         boxes += [(i, y, y + h, x, x + w) for _, (x, y, w, h) in boxed]
@@ -209,11 +214,11 @@ def _run_rank_dump(args, shard, rank, world, fixed_height) -> int:
 
     def flush(group, pool):
         """One device call for a group of same-size pages; returns (manifest entries, futures of their file writes)."""
-        paths = [p for p, _ in group]
-        images = np.stack([im for _, im in group])
+        paths = [g[0] for g in group]
+        images = np.stack([g[1] for g in group])
         entries, futs = {}, []
         if args.mode == "heading":
-            pages, sc, shape = _run_heading_pages(eng, images, paths, args, fixed_height)
+            pages, sc, shape = _run_heading_pages(eng, images, paths, args, fixed_height, [g[2] for g in group])
             for path, (u8, probs) in zip(paths, pages):
                 stem = os.path.splitext(os.path.basename(path))[0]
                 futs.append(pool.submit(write_png, stem + "_prob.png", u8[:, :, 0].copy()))
@@ -244,29 +249,46 @@ def _run_rank_dump(args, shard, rank, world, fixed_height) -> int:
             done.update(entries)
             save_manifest()
 
+    def decode(path):
+        """``cv2.imread(path)`` as the reference calls it (helper.py:29) - except that a file which holds ONE 8-bit channel
+        is kept as one channel: its B = G = R copy would go through the same resize per channel and BGR2GRAY
+        ((3735 + 19235 + 9798) g + 2^14) >> 15 = g, i.e. identical results for a third of the bytes."""
+        img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if img is None or img.dtype != np.uint8 or img.ndim != 2:
+            img = cv2.imread(path)
+        # heading mode: the page's TextLines are read here too, off the thread that feeds the GPU
+        return img, (_read_page_textlines(path) if args.mode == "heading" and img is not None else None)
+
     import time
     t_start = time.perf_counter()
-    with ThreadPoolExecutor(n_threads) as pool:
+    # three stages: the pool decodes ahead, this thread groups decoded pages by size, one worker thread owns the GPU
+    # (stacking a batch, the device call and handing the results to the pool for encoding)
+    with ThreadPoolExecutor(n_threads) as pool, ThreadPoolExecutor(1) as gpu:
         it = iter(todo)
-        window = collections.deque((p, pool.submit(cv2.imread, p)) for p in itertools.islice(it, 2 * n_threads + batch))
+        window = collections.deque((p, pool.submit(decode, p)) for p in itertools.islice(it, 2 * n_threads + batch))
         pending = collections.OrderedDict()                      # decoded pages waiting for a full batch, per image size
+        flushing = collections.deque()
         while window:
             path, fut = window.popleft()
             nxt = next(it, None)
             if nxt is not None:
-                window.append((nxt, pool.submit(cv2.imread, nxt)))
-            image = fut.result()
+                window.append((nxt, pool.submit(decode, nxt)))
+            image, lines = fut.result()
             if image is None:
                 raise SystemExit(f"cannot read image {path}")
             group = pending.setdefault(image.shape, [])
-            group.append((path, image))
+            group.append((path, image, lines))
             if len(group) >= batch:
-                in_flight.append(flush(pending.pop(image.shape), pool))
+                flushing.append(gpu.submit(flush, pending.pop(image.shape), pool))
             elif sum(len(g) for g in pending.values()) > 4 * batch:   # many sizes in flight: run the oldest group
-                in_flight.append(flush(pending.pop(next(iter(pending))), pool))
+                flushing.append(gpu.submit(flush, pending.pop(next(iter(pending))), pool))
+            while len(flushing) > 2:                                  # at most two batches queued behind the GPU
+                in_flight.append(flushing.popleft().result())
             retire(keep=2)
         for shape in list(pending):
-            in_flight.append(flush(pending.pop(shape), pool))
+            flushing.append(gpu.submit(flush, pending.pop(shape), pool))
+        while flushing:
+            in_flight.append(flushing.popleft().result())
         retire(keep=0)
     save_manifest()
     dt = time.perf_counter() - t_start
