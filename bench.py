@@ -318,45 +318,51 @@ def run_b200(args):
     eng.sync()
 
     # ---- end to end through the public call (e2e) ----
-    for _ in range(max(1, min(args.warmup, 2))):
-        y_host = eng.forward(x_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        y_host = eng.forward(x_host)          # host float32 in -> host float32 [n,H,W,C] out, copies included
-        checksum = float(y_host[0, 0, 0, 0])  # touch the result on the host
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    def pipelined(call, *a, **kw):
+        """args.steps calls through the public API, two in flight (Engine.submit / wait): every step's inputs are copied
+        from pinned host memory and every step's result is read on the host inside the timed region; the next step's
+        copy-in overlaps the previous step's tail.  Returns (seconds, last result, checksum)."""
+        warm = [eng.submit(call, *a, **kw) for _ in range(max(2, min(args.warmup, 3)))]   # also fills the pinned-block pool
+        for t, _ in warm:
+            eng.wait(t)
+        del warm
+        barrier()
+        acc, pending = 0.0, None
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ticket, res = eng.submit(call, *a, **kw)
+            if pending is not None:
+                eng.wait(pending[0])
+                acc += touch(pending[1])
+            pending = (ticket, res)
+        eng.wait(pending[0])
+        acc += touch(pending[1])
+        last = pending[1]
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        return dt, last, acc
+
+    def touch(res):
+        arr = next(iter(res.values())) if isinstance(res, dict) else (res[0] if isinstance(res, tuple) else res)
+        return float(arr.reshape(-1)[0]) + float(arr.reshape(-1)[-1])
+
+    # host float32 in -> host float32 [n,H,W,C] out, copies included
+    e2e_s, y_host, checksum = pipelined(eng.forward, x_host)
 
     # ---- the contract-minimal call: uint8 pages in (as cv2.imread / scale_image give them), channel 0 of
     # np.array(net_output * 255, dtype=np.uint8) out - all any caller of get_net_output keeps of the float map
     # (separator_net_post_processor.py:33,147, heading_net_post_processor.py:209,287): 1 B/px up, 1 B/px down ----
     p_host = pinned_empty((n, H, W), np.uint8)
     p_host[...] = np.rint(pages * 255.0).astype(np.uint8)
-    for _ in range(max(1, min(args.warmup, 2))):
-        u8_host = eng.separator_pages(p_host, want_u8=True, want_separators=False, u8_channels=1)["u8"]
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        u8_host = eng.separator_pages(p_host, want_u8=True, want_separators=False, u8_channels=1)["u8"]
-        checksum += float(u8_host[0, 0, 0, 0])
-    torch.cuda.synchronize()
-    u8_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    u8_s, r_u8, c2 = pipelined(eng.separator_pages, p_host, want_u8=True, want_separators=False, u8_channels=1)
+    u8_host = r_u8["u8"]
+    checksum += c2
 
     # ---- end to end one level up: uint8 pages in, the two separator masks out (SURVEY.md 8 f1+f2) ----
     # = SeparatorNetPostProcessor.run up to the polygon step; only 1 B/px goes up and 2 B/px come down
-    for _ in range(max(1, min(args.warmup, 2))):
-        r_pages = eng.separator_pages(p_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r_pages = eng.separator_pages(p_host)
-        checksum += float(r_pages["vertical"][0, 0, 0])
-    torch.cuda.synchronize()
-    pages_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    pages_s, r_pages, c3 = pipelined(eng.separator_pages, p_host)
+    checksum += c3
 
     # ---- what the unmodified caller does: one pageable float64 page per get_net_output call (helper.py:31,56-72) ----
     n_single = min(n, 8)
@@ -395,7 +401,8 @@ def run_b200(args):
                        "sharding": "page-wise, one process per GPU, no collective"},
             "e2e": {"value": total_pages / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
                     "d2h_bytes_per_step": int(y_host.nbytes), "ms_per_step": e2e_s / args.steps * 1e3,
-                    "call": "Engine.forward == get_net_output for a batch: float32 pages in, float32 probability maps out"},
+                    "call": "Engine.forward == get_net_output for a batch: float32 pages in, float32 probability maps out; two steps in "
+                            "flight (Engine.submit / wait), every step's copies and host read inside the timed region"},
             "e2e_uint8": {"value": total_pages / u8_s, "unit": UNIT, "h2d_bytes_per_step": int(p_host.nbytes),
                           "d2h_bytes_per_step": int(u8_host.nbytes), "ms_per_step": u8_s / args.steps * 1e3,
                           "call": "Engine.separator_pages(want_u8=True, u8_channels=1): uint8 pages in; colour step, net and "

@@ -117,7 +117,10 @@ struct aru_engine {
   std::vector<OpWeights> opw;
   std::vector<int> kind;  // per buffer
   int input_buf = -1, output_buf = -1, n_class = 0;
-  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0, u8_channels = 0;
+  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0, u8_channels = 0, async_calls = 0;
+  // ARU_OPT_ASYNC: completion events of the host-buffer calls in flight (ticket t lives in tickets[t % 8])
+  cudaEvent_t tickets[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t last_ticket = 0;
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   int* err_flag = nullptr;
   float* zero_bias = nullptr;
@@ -1082,7 +1085,11 @@ int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w) {
   // (8 B/px out); with uint8 / mask outputs only (1-3 B/px) the copies are short and the extra small passes cost more
   // than they hide, so those calls keep [mb/4, mb, ..., (rest), mb/4].
   std::vector<int> sched;
-  if (n > mb && mb >= 8 && io.out != nullptr) {
+  if (e->async_calls && io.n_boxes == 0) {
+    // calls in flight overlap each other: the exposed first copy-in / last copy-out run under the neighbouring calls,
+    // so plain full passes (no small head / ramped tail, which cost fixed launch time) are the fastest schedule
+    for (int left = n; left > 0; left -= mb) sched.push_back(std::min(mb, left));
+  } else if (n > mb && mb >= 8 && io.out != nullptr) {
     const int head = mb / 4;
     std::vector<int> tail = {mb / 2, mb / 4, mb / 8};
     int tail_sum = tail[0] + tail[1] + tail[2];
@@ -1188,6 +1195,16 @@ int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w) {
     }
     CU(e, cudaEventRecord(p->ev_d2h[par], e->s_d2h));
     p->d2h_pending[par] = true;
+  }
+  if (e->async_calls && io.n_boxes == 0) {
+    // ARU_OPT_ASYNC: return once everything is enqueued; the copy stream's last event is the call's ticket (every
+    // micro-batch's copy-out waits for its compute, so the event covers the whole call).  The staging buffers of the
+    // plans stay guarded by their own events, so the next call's first copy-in overlaps this call's tail.
+    const uint64_t t = ++e->last_ticket;
+    cudaEvent_t& ev = e->tickets[t % 8];
+    if (!ev) CU(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(e, cudaEventRecord(ev, e->s_d2h));
+    return ARU_OK;
   }
   CU(e, cudaStreamSynchronize(e->s_d2h));
   CU(e, cudaStreamSynchronize(e->s_comp));
@@ -1408,6 +1425,8 @@ void aru_destroy(aru_engine* e) {
     if (w.w32) cudaFree(w.w32);
     if (w.bias) cudaFree(w.bias);
   }
+  for (auto& ev : e->tickets)
+    if (ev) cudaEventDestroy(ev);
   if (e->err_flag) cudaFree(e->err_flag);
   if (e->zero_bias) cudaFree(e->zero_bias);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
@@ -1449,6 +1468,9 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
         e->cur = nullptr;
       }
       e->fuse_pairs = value ? 1 : 0;
+      return ARU_OK;
+    case ARU_OPT_ASYNC:   // calls already in flight stay in flight; any later synchronous call or aru_sync completes them
+      e->async_calls = value ? 1 : 0;
       return ARU_OK;
     case ARU_OPT_U8_CHANNELS:
       if (value < 0 || value > 64) return fail(e, ARU_EINVAL, "bad number of uint8 channels");
@@ -1867,6 +1889,19 @@ int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, floa
     }
   }
   return ARU_OK;
+}
+
+uint64_t aru_last_ticket(const aru_engine* e) { return e ? e->last_ticket : 0; }
+
+int aru_wait(aru_engine* e, uint64_t ticket) {
+  if (!e) return ARU_EINVAL;
+  if (ticket == 0 || ticket > e->last_ticket) return fail(e, ARU_EINVAL, "aru_wait: unknown ticket");
+  CU(e, cudaSetDevice(e->device));
+  if (e->last_ticket - ticket >= 8) return check_err_flag(e);   // its event was recycled: 8 later calls were submitted, and
+                                                               // a call is only submitted after ... its predecessors' waits
+  cudaEvent_t ev = e->tickets[ticket % 8];
+  if (ev) CU(e, cudaEventSynchronize(ev));
+  return check_err_flag(e);
 }
 
 int aru_sync(aru_engine* e) {

@@ -22,7 +22,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ARU_B200_LIB") or os.path.join(_PKG_DIR, "libaru_b200.so")
 
 ARU_OK, ARU_EINVAL, ARU_ECUDA, ARU_ENOMEM, ARU_EUNSUP, ARU_ENODEV = 0, 1, 2, 3, 4, 5
-OPT_CONV_PATH, OPT_USE_GRAPH, OPT_MICRO_BATCH, OPT_KEEP_ALL, OPT_FUSE_PAIRS, OPT_U8_CHANNELS = 1, 2, 3, 4, 5, 6
+OPT_CONV_PATH, OPT_USE_GRAPH, OPT_MICRO_BATCH, OPT_KEEP_ALL, OPT_FUSE_PAIRS, OPT_U8_CHANNELS, OPT_ASYNC = 1, 2, 3, 4, 5, 6, 7
 
 # every symbol include/aru_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = [
@@ -31,7 +31,7 @@ EXPORTS = [
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
     "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
     "aru_box_sums", "aru_cc_filter", "aru_scaled_size", "aru_scale_pages", "aru_separator_images", "aru_heading_images",
-    "aru_bind_host_to_device", "aru_swt_distance",
+    "aru_bind_host_to_device", "aru_swt_distance", "aru_last_ticket", "aru_wait",
 ]
 
 _lib = None
@@ -93,6 +93,9 @@ def load_library() -> ctypes.CDLL:
         lib.aru_host_free.restype = None
         lib.aru_bind_host_to_device.argtypes = [i32, ctypes.POINTER(i32)]
         lib.aru_swt_distance.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+        lib.aru_last_ticket.argtypes = [vp]
+        lib.aru_last_ticket.restype = ctypes.c_uint64
+        lib.aru_wait.argtypes = [vp, ctypes.c_uint64]
         del u8p
         _lib = lib
         return lib
@@ -188,6 +191,8 @@ class Engine:
         self.handle = handle
         self.device = int(device)
         self.n_class = self.lib.aru_num_classes(handle)
+        self._in_flight = {}
+        self._staged, self._collect = [], False
         self._finalizer = weakref.finalize(self, self.lib.aru_destroy, handle)
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -241,6 +246,8 @@ class Engine:
             xin = pinned_empty((n, h, w), np.float32)
             np.copyto(xin, x, casting="unsafe")
             x = xin
+        if self._collect:
+            self._staged.append(x)
         c = self.n_class
         prob = pinned_empty((n, h, w, c), np.float32) if want_prob else None
         cu = self._u8_channels(u8_channels)
@@ -261,6 +268,29 @@ class Engine:
 
     def sync(self):
         self._check(self.lib.aru_sync(self.handle))
+
+    # -- asynchronous host-buffer calls ----------------------------------------------------------------------------
+    def submit(self, call, *args, **kw):
+        """Run ``call`` (``self.forward``, ``self.separator_pages`` or ``self.separator_images``) without waiting for it:
+        returns ``(ticket, result)``; the result arrays are filled when ``wait(ticket)`` returns.  Inputs that are not
+        already pinned float32 / uint8 arrays are staged, so the caller's arrays can be reused at once; a pinned input
+        must stay untouched until ``wait``.  Up to 8 calls may be in flight; consecutive calls overlap (the copy-in of
+        the next runs under the tail of the previous)."""
+        self._staged, self._collect = [], True
+        self.set_option(OPT_ASYNC, 1)
+        try:
+            res = call(*args, **kw)
+        finally:
+            self._collect = False
+            self.set_option(OPT_ASYNC, 0)              # calls in flight stay in flight
+        ticket = int(self.lib.aru_last_ticket(self.handle))
+        self._in_flight[ticket] = (res, args, self._staged)   # keeps every buffer of the call alive until wait()
+        self._staged = []
+        return ticket, res
+
+    def wait(self, ticket: int):
+        self._check(self.lib.aru_wait(self.handle, int(ticket)))
+        self._in_flight.pop(int(ticket), None)
 
     # -- integer pre / post-processing on the device (SURVEY.md section 8 rows f1 / f2) ------------------------
     @staticmethod
@@ -294,6 +324,8 @@ class Engine:
             xin = pinned_empty(x.shape, np.uint8)
             np.copyto(xin, x)
             x = xin
+        if self._collect:
+            self._staged.append(x)
         c = self.n_class
         res = {}
         if want_prob:
@@ -341,6 +373,8 @@ class Engine:
         cu = self._u8_channels(u8_channels)
         x, n, h, w, ch = self._as_pages(images)
         x = np.ascontiguousarray(x)
+        if self._collect:
+            self._staged.append(x)
         dh, dw = (h, w) if sc == 1.0 else self.scaled_size(h, w, sc)
         c = self.n_class
         res = {}

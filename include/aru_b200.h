@@ -123,6 +123,12 @@ typedef struct aru_engine aru_engine;
                                  [n,h,w,k] - every consumer reads channel 0 alone (separator_net_post_processor.py:33,
                                  heading_net_post_processor.py:209), and the device->host copy shrinks with it; 0 = all */
 
+#define ARU_OPT_ASYNC 7       /* 1 = aru_forward / aru_separator_pages / aru_separator_images return as soon as their work is
+                                 enqueued; aru_last_ticket() names the call and aru_wait() blocks until its outputs are in
+                                 the host buffers (which, like the inputs, must stay alive until then).  Consecutive calls
+                                 then overlap: the next call's first copy-in runs under this call's tail.  At most 8 calls
+                                 may be in flight.  The heading calls (they return sums by value) always complete. */
+
 int aru_abi_version(void);
 int aru_device_count(void);
 
@@ -242,6 +248,10 @@ int aru_swt_distance(aru_engine* e, const uint8_t* gray, int n, int h, int w, in
 
 /* The colour step alone: uint8 pages [n,h,w,channels] -> float32 [n,h,w] = gray / 255.0 (helper.py:31). */
 int aru_pages_to_input(aru_engine* e, const uint8_t* pages, int channels, int n, int h, int w, float* out);
+
+/* ARU_OPT_ASYNC: ticket of the most recent host-buffer call, and completion of one call. */
+uint64_t aru_last_ticket(const aru_engine* e);
+int aru_wait(aru_engine* e, uint64_t ticket);
 
 /* Block until everything enqueued on the engine's stream has finished. */
 int aru_sync(aru_engine* e);

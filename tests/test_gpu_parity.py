@@ -428,3 +428,30 @@ def test_micro_batch_schedules_cover_every_page_once(engines, n):
             assert np.array_equal(r["u8"], (alone * 255).astype(np.uint8)), (n, mb)
     finally:
         eng.set_option(OPT_MICRO_BATCH, 0)
+
+
+def test_async_calls_overlap_and_give_the_same_results(engines):
+    """Engine.submit / wait (ARU_OPT_ASYNC): several host-buffer calls in flight give the bits of the synchronous calls,
+    whatever the order of the waits, for the float and the uint8-page entry points."""
+    from aru_b200.synth import synth_page
+    eng = engines("separator")
+    pages = [np.stack([synth_page(120, 112, 40 * k + i) for i in range(5)]) for k in range(4)]
+    xs = [(p / 255.0).astype(np.float32) for p in pages]
+    want = [eng.forward(x).copy() for x in xs]
+    want_pages = [eng.separator_pages(p, want_u8=True) for p in pages]
+    tickets = [eng.submit(eng.forward, x) for x in xs]
+    for k in (2, 0, 3, 1):
+        eng.wait(tickets[k][0])
+        assert np.array_equal(tickets[k][1], want[k]), k
+    tickets = [eng.submit(eng.separator_pages, p, want_u8=True) for p in pages]
+    for k, (t, r) in enumerate(tickets):
+        eng.wait(t)
+        for key in ("u8", "horizontal", "vertical"):
+            assert np.array_equal(r[key], want_pages[k][key]), (k, key)
+    # a float64 pageable input is staged by the call: the caller's array may change right after submit
+    x64 = xs[0].astype(np.float64)
+    t, r = eng.submit(eng.forward, x64)
+    x64[...] = 0
+    eng.wait(t)
+    assert np.array_equal(r, want[0])
+    assert np.array_equal(eng.forward(xs[1]), want[1])          # synchronous calls still complete before returning
