@@ -131,6 +131,10 @@ struct aru_engine {
   Plan* cur = nullptr;
   uint64_t tick = 0;
   std::string error;
+  // dynamic-range check of the first real pass (fp16 stores saturate at 65504: real weights could exceed what the
+  // synthetic nets do); ARU_RANGE_CHECK=0 skips it
+  int range_checked = 0;
+  std::string warning;
 };
 
 namespace {
@@ -1030,6 +1034,47 @@ int make_scale_plan(aru_engine* e, int sh, int sw, double sc, ScalePlan* sp) {
   return ARU_OK;
 }
 
+// After the first pass on real data: count the stored activations that sit on the storage limit or are not finite.
+int range_check(aru_engine* e, Plan* p) {
+  unsigned long long* cnt = nullptr;
+  const int nb = (int)p->bufs.size();
+  CU(e, cudaMalloc((void**)&cnt, (size_t)nb * sizeof(unsigned long long)));
+  CU(e, cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(unsigned long long), e->s_comp));
+  for (int b = 0; b < nb; ++b) {
+    const BufPlan& bp = p->bufs[b];
+    if (!bp.sized || bp.kind != KIND_PLANAR || b == e->input_buf || b == e->output_buf) continue;
+    cudaError_t err = launch_range_scan(e->s_comp, reinterpret_cast<const act_t*>(p->arena + bp.offset),
+                                        (long long)bp.chunks * bp.geo.plane * 8, cnt + b);
+    if (err != cudaSuccess) { cudaFree(cnt); return fail(e, ARU_ECUDA, "range scan: %s", cudaGetErrorString(err)); }
+  }
+  std::vector<unsigned long long> h(nb);
+  cudaError_t err = cudaMemcpyAsync(h.data(), cnt, (size_t)nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->s_comp);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->s_comp);
+  cudaFree(cnt);
+  if (err != cudaSuccess) return fail(e, ARU_ECUDA, "range scan: %s", cudaGetErrorString(err));
+  unsigned long long total = 0;
+  int first = -1, n_bufs = 0;
+  for (int b = 0; b < nb; ++b)
+    if (h[b]) { total += h[b]; ++n_bufs; if (first < 0) first = b; }
+  if (total) {
+    int writer = -1;
+    for (int i = 0; i < (int)e->ops.size() && writer < 0; ++i)
+      if (e->ops[i].out.buf == first || e->ops[i].out_pre.buf == first) writer = i;
+    char msg[512];
+    snprintf(msg, sizeof msg, "%llu stored activations in %d tensor(s) reached the " ARU_ACT_NAME " storage limit or are not "
+             "finite (first: buffer %d written by op %d): the probability maps of this graph are not trustworthy in this "
+             "build%s", total, n_bufs, first, writer,
+#ifdef ARU_USE_BF16
+             "");
+#else
+             "; fp16 stores saturate at +-65504 - use the bf16 library (ARU_B200_LIB=.../libaru_b200_bf16.so)");
+#endif
+    e->warning = msg;
+    fprintf(stderr, "aru_b200 warning: %s\n", msg);
+  }
+  return ARU_OK;
+}
+
 struct HostIO {
   const ScalePlan* scale = nullptr;   // in_u8 holds unscaled pages sh x sw; they are resized on the device first
   const float* in_f32 = nullptr;   // float32 [n,h,w] pages (gray / 255) ...
@@ -1162,6 +1207,11 @@ int forward_host_impl(aru_engine* e, const HostIO& io, int n, int h, int w) {
     }
     rc = enqueue_forward(e, p, par, e->s_comp);
     if (rc) return rc;
+    if (!e->range_checked) {
+      e->range_checked = 1;
+      const char* rcv = getenv("ARU_RANGE_CHECK");
+      if (!(rcv && rcv[0] == '0') && (rc = range_check(e, p))) return rc;
+    }
     if (want_u8 || want_mask) {
       cudaError_t err = launch_quantize(e->s_comp, p->out_dev[par], want_u8 ? p->u8_dev[par] : nullptr,
                                         want_mask ? p->mask_dev[par] : nullptr, (long long)cnt * page_px, C, io.thr, io.cut, Cu);
@@ -1229,6 +1279,8 @@ int aru_device_count(void) {
 }
 
 const char* aru_last_error(const aru_engine* e) { return e ? e->error.c_str() : g_error.c_str(); }
+
+const char* aru_last_warning(const aru_engine* e) { return e ? e->warning.c_str() : ""; }
 
 // One process per GPU: the host buffers a rank page-locks must live on the NUMA node its GPU hangs off, or the
 // host<->device copies of the ranks on the other socket cross the inter-socket link and the 8-GPU end-to-end rate

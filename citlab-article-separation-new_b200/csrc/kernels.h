@@ -90,6 +90,8 @@ size_t swt_scratch_bytes(int n, int h, int w);
 int swt_otsu_from_hist(const unsigned* hist, long long size);
 cudaError_t launch_swt_distance(cudaStream_t st, const uint8_t* gray, int n, int h, int w, int dark_on_bright, void* scratch,
                                 uint8_t* out, int* thr_host);
+// *count += number of stored 16-bit values at the storage limit (fp16: |v| = 65504) or not finite
+cudaError_t launch_range_scan(cudaStream_t st, const act_t* p, long long elements, unsigned long long* count);
 // debug read-back: chunk-planar view -> dense float32 NHWC [N][H][W][C]
 cudaError_t launch_unpack_nhwc(cudaStream_t st, PV in, const Geo& g, float* out);
 

@@ -980,6 +980,39 @@ cudaError_t launch_quantize(cudaStream_t st, const float* prob, uint8_t* u8, uin
   return cudaGetLastError();
 }
 
+// Range check of stored 16-bit activations: values at the storage limit (fp16: |v| = 65504, where stores saturate) or
+// not finite.  One counter per call; 8 values per thread.
+__global__ void __launch_bounds__(256) k_range_scan(const uint4* __restrict__ v, long long n_vec,
+                                                    unsigned long long* __restrict__ count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned bad = 0;
+  if (i < n_vec) {
+    const uint4 q = __ldg(v + i);
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const unsigned e = (w[k] >> (16 * h)) & 0x7fffu;
+#ifdef ARU_USE_BF16
+        bad += e >= 0x7f80u;                 // inf / nan
+#else
+        bad += e >= 0x7bffu;                 // 65504 (saturated store), inf, nan
+#endif
+      }
+    }
+  }
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, (unsigned long long)bad);
+}
+
+cudaError_t launch_range_scan(cudaStream_t st, const act_t* p, long long elements, unsigned long long* count) {
+  const long long n_vec = elements / 8;
+  if (n_vec <= 0) return cudaSuccess;
+  k_range_scan<<<blocks_for(n_vec, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(p), n_vec, count);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_unpack_nhwc(cudaStream_t st, PV in, const Geo& g, float* out) {
   k_unpack_nhwc<<<blocks_for(npix(g), 256), 256, 0, st>>>(in.p, in.plane, in.C, g, out);
   return cudaGetLastError();

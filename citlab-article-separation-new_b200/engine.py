@@ -31,7 +31,7 @@ EXPORTS = [
     "aru_buffer_dims", "aru_profile_ops", "aru_op_kernel_name", "aru_last_error", "aru_host_alloc", "aru_host_free",
     "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
     "aru_box_sums", "aru_cc_filter", "aru_scaled_size", "aru_scale_pages", "aru_separator_images", "aru_heading_images",
-    "aru_bind_host_to_device", "aru_swt_distance", "aru_last_ticket", "aru_wait",
+    "aru_bind_host_to_device", "aru_swt_distance", "aru_last_ticket", "aru_wait", "aru_last_warning",
 ]
 
 _lib = None
@@ -96,6 +96,8 @@ def load_library() -> ctypes.CDLL:
         lib.aru_last_ticket.argtypes = [vp]
         lib.aru_last_ticket.restype = ctypes.c_uint64
         lib.aru_wait.argtypes = [vp, ctypes.c_uint64]
+        lib.aru_last_warning.argtypes = [vp]
+        lib.aru_last_warning.restype = ctypes.c_char_p
         del u8p
         _lib = lib
         return lib
@@ -202,6 +204,11 @@ class Engine:
 
     def close(self):
         self._finalizer()
+
+    @property
+    def last_warning(self) -> str:
+        """Result of the dynamic-range check of the engine's first pass ('' = every stored activation was in range)."""
+        return (self.lib.aru_last_warning(self.handle) or b"").decode()
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.aru_set_option(self.handle, option, int(value)))

@@ -270,6 +270,13 @@ const char* aru_op_kernel_name(const aru_engine* e, int op);
 
 const char* aru_last_error(const aru_engine* e);
 
+/* Dynamic-range check: the first host-buffer pass of an engine on real data is followed by one scan of every stored
+ * tensor for 16-bit values at the storage limit (fp16 stores saturate at +-65504) or not finite.  A non-empty string
+ * says how many were found and where; it is also printed to stderr once.  The synthetic nets stay below 40; a trained
+ * ReLU net without normalisation could exceed the limit - then the bf16 build is the one to use.  ARU_RANGE_CHECK=0
+ * in the environment skips the scan. */
+const char* aru_last_warning(const aru_engine* e);
+
 /* Page-locked host memory for the in / out arrays of aru_forward(): with pinned buffers the
  * host<->device copies of consecutive micro-batches overlap the kernels (pageable memory works too,
  * but serialises). */

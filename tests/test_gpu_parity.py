@@ -455,3 +455,33 @@ def test_async_calls_overlap_and_give_the_same_results(engines):
     eng.wait(t)
     assert np.array_equal(r, want[0])
     assert np.array_equal(eng.forward(xs[1]), want[1])          # synchronous calls still complete before returning
+
+
+def test_range_check_reports_saturating_activations(built_lib):
+    """fp16 stores saturate at 65504 (bf16 build: only inf / nan count).  A graph whose second layer exceeds that must
+    raise the engine's warning on its first pass; the calibrated nets must not."""
+    from aru_b200.engine import Engine
+    from aru_b200.graphdef import GraphBuilder
+    from aru_b200.synth import synth_pb, synth_page, page_to_net_input
+    x = page_to_net_input(synth_page(40, 48, 1)).astype(np.float32)
+    eng = Engine(synth_pb("tiny"), device=0)
+    eng.forward(x)
+    assert eng.last_warning == ""
+    eng.close()
+    b = GraphBuilder()
+    inp = b.placeholder("inImg", [None, None, None, 1])
+    rng = np.random.default_rng(0)
+    h = inp
+    for i, (cin, cout, scale) in enumerate(((1, 8, 300.0), (8, 8, 300.0), (8, 8, 1e-6))):
+        w = b.variable(f"w{i}", (np.abs(rng.normal(0, 1, size=(3, 3, cin, cout))) * scale).astype(np.float32))
+        bi = b.variable(f"b{i}", np.zeros((cout,), np.float32))
+        h = b.relu(f"a{i}", b.bias_add(f"p{i}", b.conv2d(f"c{i}", h, w), bi))
+    w = b.variable("wl", rng.normal(0, 1e-3, size=(4, 4, 8, 2)).astype(np.float32))
+    bi = b.variable("bl", np.zeros((2,), np.float32))
+    b.softmax("output", b.bias_add("logits", b.conv2d("cl", h, w), bi), unique=False)
+    eng = Engine(b.serialize(), device=0)
+    out = eng.forward(x)
+    assert np.isfinite(out).all()                         # stores saturate instead of producing inf
+    if os.path.basename(os.environ.get("ARU_B200_LIB", "")) != "libaru_b200_bf16.so":
+        assert "storage limit" in eng.last_warning and "bf16" in eng.last_warning, eng.last_warning
+    eng.close()
