@@ -44,6 +44,9 @@ struct OpWeights {
   std::vector<TcImage> tc_images;
   act_t* band_w = nullptr;  // banded masters of conv_band.cu (depend on the filter only)
   size_t band_bytes = 0;
+  uint32_t* blk_w = nullptr;   // block_mma.cu: B fragments of the residual block this op ends (with / without conv1)
+  float* blk_bias = nullptr;   // [4][16]
+  int blk_cin = -1;            // conv1 input channels the fragments were packed for (0: block starts from x0)
   float* w32 = nullptr;     // stem [tap][cpad] / small [tap][cin_pad][cout]
   float* bias = nullptr;    // zero-padded to a multiple of 16
   int cin = 0, cout = 0;
@@ -77,6 +80,11 @@ struct Plan {
   std::vector<int> pair_first;          // per conv op k: the conv op i whose launch it absorbs (conv_band2.cu), -1: none
   std::vector<ConvBand2Plan> pair;      // per conv op k with pair_first[k] >= 0
   std::vector<char> pair_store0;        // per conv op k: the stage-0 (op i) activated output must also be stored
+  // whole residual blocks as one launch (block_mma.cu): per conv op c = convR_2 of a block, its conv1 / convR_0 / convR_1
+  std::vector<int> blk_conv1, blk_r0, blk_r1;   // -1: op c does not end a fused block
+  std::vector<BlockMmaPlan> blk;
+  std::vector<char> blk_from_x0;        // per op c: conv1 runs as its own launch and the block starts from its pre-activation
+  std::vector<char> pre_only;           // per conv1 op of such a block: only the pre-activation is stored
   act_t* scratch = nullptr;             // partial sums of split-K launches
   size_t scratch_bytes = 0;
   std::vector<const char*> kernel;   // per op label
@@ -117,7 +125,7 @@ struct aru_engine {
   std::vector<OpWeights> opw;
   std::vector<int> kind;  // per buffer
   int input_buf = -1, output_buf = -1, n_class = 0;
-  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0, u8_channels = 0, async_calls = 0;
+  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0, fuse_blocks = 1, u8_channels = 0, async_calls = 0;
   // ARU_OPT_ASYNC: completion events of the host-buffer calls in flight (ticket t lives in tickets[t % 8])
   cudaEvent_t tickets[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t last_ticket = 0;
@@ -301,7 +309,9 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
       if (bi.kind == KIND_F32) {
         const int pj = p->fused_pool[oi];
         label = pj >= 0 ? (p->pool_only[oi] ? "conv_stem_pool" : "conv_stem_fpool") : "conv_stem";
-        err = launch_conv_stem(st, op.ksize, f32_ptr(e, p, op.in.buf, parity), make_pv(e, p, op.out),
+        PV stem_out = make_pv(e, p, op.out);
+        if (p->pre_only[oi]) { stem_out.p = nullptr; label = "conv_stem_pre"; }   // the fused block reads the pre-activation only
+        err = launch_conv_stem(st, op.ksize, f32_ptr(e, p, op.in.buf, parity), stem_out,
                                make_pv(e, p, op.out_pre), e->weights.data() + op.w_off, e->weights.data() + op.b_off,
                                bo.geo, op.act, pj >= 0 ? make_pv(e, p, e->ops[pj].out) : PV(),
                                pj >= 0 ? &p->bufs[e->ops[pj].out.buf].geo : nullptr, !p->pool_only[oi], ow.w32, ow.bias);
@@ -318,7 +328,15 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
         err = launch_conv_small(st, op.ksize, op.out.ch, make_pv(e, p, op.in), f32_ptr(e, p, op.out.buf, parity), ow.w32,
                                 ow.bias, bi.geo, op.act);
       } else if (p->skip[oi]) {
-        label = "pair_fused";   // performed by the launch of the convolution that consumes it (conv_band2.cu)
+        label = "pair_fused";   // performed by the launch of the convolution that consumes it (conv_band2.cu, block_mma.cu)
+      } else if (p->blk_conv1[oi] >= 0) {
+        // the whole residual block in one launch, at the position of its last convolution
+        const aru_op& o1 = e->ops[p->blk_conv1[oi]];
+        const int pj = p->fused_pool[oi];
+        label = pj >= 0 ? "block_mma_pool" : "block_mma";
+        err = launch_block_mma(st, p->blk[oi], p->blk_from_x0[oi] ? make_pv(e, p, o1.out_pre) : make_pv(e, p, o1.in),
+                               make_pv(e, p, op.out), pj >= 0 ? make_pv(e, p, e->ops[pj].out) : PV(),
+                               pj >= 0 ? &p->bufs[e->ops[pj].out.buf].geo : nullptr, ow.blk_w, ow.blk_bias, bo.geo, e->err_flag);
       } else if (p->pair_first[oi] >= 0) {
         // two chained convolutions in one launch: op `fi` (stage 0) feeds this op through a shared-memory row FIFO
         const int fi = p->pair_first[oi];
@@ -478,6 +496,12 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   p->pair_first.assign(no, -1);
   p->pair.resize(no);
   p->pair_store0.assign(no, 0);
+  p->blk_conv1.assign(no, -1);
+  p->blk_r0.assign(no, -1);
+  p->blk_r1.assign(no, -1);
+  p->blk.resize(no);
+  p->blk_from_x0.assign(no, 0);
+  p->pre_only.assign(no, 0);
   p->kernel.assign(no, "?");
   for (int i = 0; i < nb; ++i) {
     p->bufs[i].kind = e->kind[i];
@@ -699,6 +723,79 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
     if ((rc = check_err_flag(e))) { free_plan(p.get()); return rc; }
   }
+  // Whole residual blocks of the 8-channel levels (conv1 -> convR_0 -> convR_1 -> convR_2 + conv1's pre-activation,
+  // ARU_v1.py:212-227, 266-281) run as ONE launch on the warp-level tensor path (block_mma.cu); the intermediates are
+  // never stored.  The launch sits at convR_2's position.  conv1 joins the launch when its input is an 8 / 16 channel
+  // tensor; a conv1 that reads the float32 page (the stem) stays its own launch and stores its pre-activation only.
+  {
+    const char* env = getenv("ARU_FUSE_BLOCKS");
+    const bool fuse = e->conv_path == 0 && !e->keep_all && (env ? env[0] == '1' : e->fuse_blocks != 0);
+    auto reads = [&](const aru_op& ro, int buf) {
+      if (ro.in.buf == buf || ro.res.buf == buf) return true;
+      if (ro.kind == ARU_OP_COMBINE)
+        for (int a = 0; a < ro.n_scales; ++a)
+          if (ro.att[a].buf == buf || ro.det[a].buf == buf) return true;
+      return false;
+    };
+    auto conv3 = [&](const aru_op& o) {
+      return o.kind == ARU_OP_CONV && o.ksize == 3 && p->bufs[o.out.buf].kind == KIND_PLANAR && o.act == ARU_ACT_RELU;
+    };
+    // the only reader of view v after op i, or -1
+    auto sole_reader = [&](int i, const aru_view& v) {
+      int k = -1, cnt = 0;
+      for (int j = i + 1; j < no; ++j)
+        if (reads(e->ops[j], v.buf)) { if (k < 0) k = j; ++cnt; }
+      return cnt == 1 ? k : -1;
+    };
+    auto same_view = [](const aru_view& a, const aru_view& b) { return a.buf == b.buf && a.ch_off == b.ch_off && a.ch == b.ch; };
+    for (int i = 0; i < no && fuse; ++i) {
+      const aru_op& o1 = e->ops[i];
+      if (!conv3(o1) || o1.out_pre.buf < 0 || o1.res.buf >= 0 || o1.out.ch != 8) continue;
+      if (o1.out.buf == e->output_buf || o1.out_pre.buf == e->output_buf) continue;
+      const int ia = sole_reader(i, o1.out);
+      if (ia < 0) continue;
+      const aru_op& oa = e->ops[ia];
+      if (!conv3(oa) || !same_view(oa.in, o1.out) || oa.res.buf >= 0 || oa.out_pre.buf >= 0 || oa.out.ch != 8) continue;
+      const int ib = sole_reader(ia, oa.out);
+      if (ib < 0) continue;
+      const aru_op& ob = e->ops[ib];
+      if (!conv3(ob) || !same_view(ob.in, oa.out) || ob.res.buf >= 0 || ob.out_pre.buf >= 0 || ob.out.ch != 8) continue;
+      const int ic = sole_reader(ib, ob.out);
+      if (ic < 0) continue;
+      const aru_op& oc = e->ops[ic];
+      if (!conv3(oc) || !same_view(oc.in, ob.out) || !same_view(oc.res, o1.out_pre) || oc.out_pre.buf >= 0 || oc.out.ch != 8)
+        continue;
+      if (sole_reader(i, o1.out_pre) != ic) continue;
+      if (oa.out.buf == e->output_buf || ob.out.buf == e->output_buf) continue;
+      const bool planar_in = p->bufs[o1.in.buf].kind == KIND_PLANAR && (o1.in.ch == 8 || o1.in.ch == 16) && o1.in.ch_off % 8 == 0;
+      const int cin = planar_in ? o1.in.ch : 0;
+      BlockMmaPlan bp = block_mma_plan(cin, 8, p->bufs[oc.out.buf].geo, e->num_sms, e->max_smem);
+      if (!bp.ok) continue;
+      OpWeights& ow = e->opw[ic];
+      if (!ow.blk_w || ow.blk_cin != cin) {
+        if (ow.blk_w) { cudaFree(ow.blk_w); ow.blk_w = nullptr; }
+        if (ow.blk_bias) { cudaFree(ow.blk_bias); ow.blk_bias = nullptr; }
+        std::vector<uint32_t> img(bp.wfrag_bytes / 4, 0u);
+        const float* wt[4] = {e->weights.data() + o1.w_off, e->weights.data() + oa.w_off, e->weights.data() + ob.w_off,
+                              e->weights.data() + oc.w_off};
+        block_mma_pack(bp, wt, cin, img.data());
+        std::vector<float> b4(64, 0.f);
+        const int offs[4] = {o1.b_off, oa.b_off, ob.b_off, oc.b_off};
+        for (int s2 = 0; s2 < 4; ++s2)
+          for (int c2 = 0; c2 < 8; ++c2) b4[s2 * 16 + c2] = e->weights[(size_t)offs[s2] + c2];
+        if ((rc = upload(e, img, &ow.blk_w)) || (rc = upload(e, b4, &ow.blk_bias))) { free_plan(p.get()); return rc; }
+        ow.blk_cin = cin;
+      }
+      p->blk[ic] = bp;
+      p->blk_conv1[ic] = i;
+      p->blk_r0[ic] = ia;
+      p->blk_r1[ic] = ib;
+      p->blk_from_x0[ic] = cin == 0;
+      p->skip[ia] = p->skip[ib] = 1;
+      if (cin > 0) p->skip[i] = 1;
+      else if (p->bufs[o1.in.buf].kind == KIND_F32) p->pre_only[i] = 1;
+    }
+  }
   // Pairs of chained 3x3 convolutions with C_out = 8 / 16 run as one launch (conv_band2.cu): greedy in program order,
   // op i -> its only consumer k.  The launch happens at k's position, so nothing between i and k may read i's outputs.
   const char* fuse_env = getenv("ARU_FUSE_PAIRS");
@@ -717,13 +814,14 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     };
     for (int i = 0; i < no && fuse; ++i) {
       const aru_op& o0 = e->ops[i];
-      if (!planar_conv3(o0) || o0.res.buf >= 0 || p->skip[i] || p->pair_first[i] >= 0) continue;
+      if (!planar_conv3(o0) || o0.res.buf >= 0 || p->skip[i] || p->pair_first[i] >= 0 || p->blk_conv1[i] >= 0) continue;
       // consumers of o0.out
       int k = -1, n_readers = 0;
       for (int j = i + 1; j < no; ++j)
         if (reads(e->ops[j], o0.out.buf)) { if (k < 0) k = j; ++n_readers; }
       if (k < 0) continue;
       const aru_op& o1 = e->ops[k];
+      if (p->blk_conv1[k] >= 0 || p->skip[k]) continue;
       if (!planar_conv3(o1) || o1.out_pre.buf >= 0 || o1.in.buf != o0.out.buf || o1.in.ch_off != o0.out.ch_off ||
           o1.in.ch != o0.out.ch || o1.out.ch != o0.out.ch || o1.res.buf == o0.out.buf)
         continue;
@@ -750,8 +848,8 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       for (int i = j - 1; i >= 0; --i) {
         const aru_op& co = e->ops[i];
         if (co.out.buf != po.in.buf) continue;
-        if (co.kind == ARU_OP_CONV && co.out.ch_off == po.in.ch_off && co.out.ch == po.in.ch && p->pair_first[i] >= 0 &&
-            p->fused_pool[i] < 0 && co.act == ARU_ACT_RELU) {
+        if (co.kind == ARU_OP_CONV && co.out.ch_off == po.in.ch_off && co.out.ch == po.in.ch &&
+            (p->pair_first[i] >= 0 || p->blk_conv1[i] >= 0) && p->fused_pool[i] < 0 && co.act == ARU_ACT_RELU) {
           p->fused_pool[i] = j;
           p->skip[j] = 1;
         } else if (co.kind == ARU_OP_CONV && co.out.ch_off == po.in.ch_off && co.out.ch == po.in.ch && p->band[i].ok &&
@@ -1474,6 +1572,8 @@ void aru_destroy(aru_engine* e) {
     if (w.w16) cudaFree(w.w16);
     for (auto& im : w.tc_images) cudaFree(im.w);
     if (w.band_w) cudaFree(w.band_w);
+    if (w.blk_w) cudaFree(w.blk_w);
+    if (w.blk_bias) cudaFree(w.blk_bias);
     if (w.w32) cudaFree(w.w32);
     if (w.bias) cudaFree(w.bias);
   }
@@ -1520,6 +1620,15 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
         e->cur = nullptr;
       }
       e->fuse_pairs = value ? 1 : 0;
+      return ARU_OK;
+    case ARU_OPT_FUSE_BLOCKS:
+      if (e->fuse_blocks != (value ? 1 : 0)) {
+        cudaSetDevice(e->device);
+        cudaDeviceSynchronize();
+        e->plans.clear();
+        e->cur = nullptr;
+      }
+      e->fuse_blocks = value ? 1 : 0;
       return ARU_OK;
     case ARU_OPT_ASYNC:   // calls already in flight stay in flight; any later synchronous call or aru_sync completes them
       e->async_calls = value ? 1 : 0;

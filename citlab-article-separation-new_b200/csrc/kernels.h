@@ -189,6 +189,27 @@ cudaError_t launch_conv_band2(cudaStream_t st, const ConvBand2Plan& plan, PV in,
                               const act_t* wpack0, const float* bias0, int act0, const act_t* wpack1, const float* bias1,
                               int act1, const Geo& g, int* err_flag, PV pool = PV(), const Geo* pool_geo = nullptr);
 
+// ---- a whole residual block per launch on the warp-level tensor path (block_mma.cu) --------------
+// [conv1 (cin -> c) ->] x0 -> ReLU -> convR_0 -> ReLU -> convR_1 -> ReLU -> convR_2 + x0 -> ReLU [-> 2x2 max-pool], c = 8;
+// cin == 0: the launch starts from x0 (conv1's pre-activation, written by another kernel).
+struct BlockMmaPlan {
+  bool ok = false;
+  int c = 0, nt = 0, cin_ch = 0;
+  int WC = 0, WS = 0, n_strips = 0;          // compute columns per CTA, output columns per strip
+  int rows_per_unit = 0, units_per_page = 0, n_units = 0;
+  int grid = 0, threads = 0;
+  int wbase[4] = {0, 0, 0, 0};               // first B-fragment register of every stage
+  size_t smem_bytes = 0;
+  size_t wfrag_bytes = 0;
+  const char* why = "";
+};
+BlockMmaPlan block_mma_plan(int cin, int c, const Geo& g, int num_sms, size_t max_smem);
+// w_tf[s]: TF filter [3][3][ci][c] (float32) of stage s (w_tf[0] unused when cin == 0) -> per-lane B fragments
+void block_mma_pack(const BlockMmaPlan& plan, const float* const w_tf[4], int cin, uint32_t* dst);
+// bias4: device [4][16] float32 (stage s at bias4 + 16 s)
+cudaError_t launch_block_mma(cudaStream_t st, const BlockMmaPlan& plan, PV in, PV out, PV pool, const Geo* pool_geo,
+                             const uint32_t* wfrag, const float* bias4, const Geo& g, int* err_flag);
+
 // host-side 16-bit conversion matching act_t
 uint16_t host_f_to_act(float v);
 

@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(128) k_conv_stem(const float* __restrict__ in,
         for (int j = 0; j < 8; ++j)
           if (c * 8 + j < COUT) acc[j] = fmaf(v[t / KS][t % KS], sw.w[t * 16 + c * 8 + j], acc[j]);
       if (out_pre) *reinterpret_cast<uint4*>(out_pre + (c * pre_plane + p) * 8) = pack8_fin<false>(acc, true);
-      *reinterpret_cast<uint4*>(out + (c * out_plane + p) * 8) =
-          act == 1 ? pack8_fin<true>(acc, true) : pack8_fin<false>(acc, true);
+      if (out)   // null: only the pre-activation is wanted (the fused residual block starts from it, block_mma.cu)
+        *reinterpret_cast<uint4*>(out + (c * out_plane + p) * 8) =
+            act == 1 ? pack8_fin<true>(acc, true) : pack8_fin<false>(acc, true);
     }
   }
 }
@@ -565,13 +566,50 @@ __global__ void __launch_bounds__(256) k_pool_f32(const float* __restrict__ in, 
     if (hy) a = fmaxf(a, src[Wi]);
     if (hx && hy) a = fmaxf(a, src[Wi + 1]);
   } else {
-    int cnt = 1;
-    if (hx) { a += src[1]; ++cnt; }
-    if (hy) { a += src[Wi]; ++cnt; }
-    if (hx && hy) { a += src[Wi + 1]; ++cnt; }
-    a = a / cnt;
+    // the divisor counts the valid cells only: 1, 2 or 4 - a multiplication by its reciprocal is exact
+    float inv = 1.f;
+    if (hx) { a += src[1]; inv = 0.5f; }
+    if (hy) { a += src[Wi]; inv *= 0.5f; }
+    if (hx && hy) a += src[Wi + 1];
+    a *= inv;
   }
   out[p] = a;
+}
+
+// widths that are multiples of 4: two outputs per thread from one 16-byte load per input row (same sums in the same
+// order as k_pool_f32: (a + b) + c + d with a, b of the upper row)
+__global__ void __launch_bounds__(256) k_pool_f32_x2(const float4* __restrict__ in, float2* __restrict__ out, int N, int Hi,
+                                                     int Wi4, int Ho, int Wo2, int is_max) {
+  const long long total = (long long)N * Ho * Wo2;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int x = (int)(p % Wo2);
+  const int y = (int)((p / Wo2) % Ho);
+  const int n = (int)(p / ((long long)Wo2 * Ho));
+  const float4* src = in + ((long long)n * Hi + 2 * y) * Wi4 + x;
+  const bool hy = 2 * y + 1 < Hi;
+  const float4 u = __ldg(src);
+  float2 r;
+  if (is_max) {
+    r = make_float2(fmaxf(u.x, u.y), fmaxf(u.z, u.w));
+    if (hy) {
+      const float4 d = __ldg(src + Wi4);
+      r.x = fmaxf(fmaxf(r.x, d.x), d.y);
+      r.y = fmaxf(fmaxf(r.y, d.z), d.w);
+    }
+  } else {
+    r = make_float2(u.x + u.y, u.z + u.w);
+    float inv = 0.5f;
+    if (hy) {
+      const float4 d = __ldg(src + Wi4);
+      r.x = (r.x + d.x) + d.y;
+      r.y = (r.y + d.z) + d.w;
+      inv = 0.25f;
+    }
+    r.x *= inv;
+    r.y *= inv;
+  }
+  out[p] = r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -909,7 +947,12 @@ cudaError_t launch_pool(cudaStream_t st, bool is_max, PV in, const Geo& gi, PV o
 cudaError_t launch_pool_f32(cudaStream_t st, bool is_max, const float* in, float* out, int N, int Hi, int Wi, int Ho,
                             int Wo) {
   const long long total = (long long)N * Ho * Wo;
-  k_pool_f32<<<blocks_for(total, 256), 256, 0, st>>>(in, out, N, Hi, Wi, Ho, Wo, is_max ? 1 : 0);
+  if (Wi % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0)
+    k_pool_f32_x2<<<blocks_for(total / 2, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(in),
+                                                               reinterpret_cast<float2*>(out), N, Hi, Wi / 4, Ho, Wo / 2,
+                                                               is_max ? 1 : 0);
+  else
+    k_pool_f32<<<blocks_for(total, 256), 256, 0, st>>>(in, out, N, Hi, Wi, Ho, Wo, is_max ? 1 : 0);
   return cudaGetLastError();
 }
 

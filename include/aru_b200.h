@@ -129,6 +129,12 @@ typedef struct aru_engine aru_engine;
                                  then overlap: the next call's first copy-in runs under this call's tail.  At most 8 calls
                                  may be in flight.  The heading calls (they return sums by value) always complete. */
 
+#define ARU_OPT_FUSE_BLOCKS 8  /* 1 (default) = with ARU_OPT_CONV_PATH 0 and ARU_OPT_KEEP_ALL 0, a residual block of the
+                                 8-channel levels (conv1 -> convR_0 -> convR_1 -> convR_2 + conv1's pre-activation -> ReLU
+                                 [-> max-pool], ARU_v1.py:212-227, 266-281) runs as ONE launch on the warp-level tensor
+                                 path with its intermediates in shared memory (block_mma.cu); 0 = one launch per layer.
+                                 ARU_FUSE_BLOCKS=0 / 1 in the environment overrides the option. */
+
 int aru_abi_version(void);
 int aru_device_count(void);
 

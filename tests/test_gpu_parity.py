@@ -175,6 +175,48 @@ def test_fused_conv_pairs_against_one_launch_per_layer(engines, oracles, net, n,
         eng.set_option(OPT_FUSE_PAIRS, 0)
 
 
+@pytest.mark.parametrize("net,n,h,w", [
+    ("separator", 1, 257, 130),     # odd sizes, one strip at every level
+    ("separator", 2, 150, 613),     # several strips (W > 168) and a batch: strip halo columns, page boundaries
+    ("separator", 3, 420, 300),     # several row segments per page and strip
+    ("separator", 1, 37, 1250),     # wide and flat: more pipeline fill than rows
+    ("heading", 1, 90, 68),
+    ("aru_s6a5", 1, 129, 97),
+    ("ru", 1, 333, 101),
+    ("tiny", 1, 9, 200), ("tiny", 1, 1, 1), ("tiny", 2, 3, 5),
+])
+def test_fused_residual_blocks_against_one_launch_per_layer(engines, oracles, net, n, h, w):
+    """block_mma.cu (a whole residual block of the 8-channel levels per launch, intermediates in shared memory, warp-level
+    tensor cores) against the same layers run one launch each (ARU_OPT_FUSE_BLOCKS 0): same 16-bit operands and rounding
+    points (every intermediate is rounded to 16 bits where the per-layer path stores it), fp32 accumulation in another
+    order and the residual added before the one rounding instead of after it - and each path is within BASELINE's
+    tolerance of the oracle."""
+    from aru_b200.engine import OPT_CONV_PATH, OPT_FUSE_BLOCKS
+    from aru_b200.synth import synth_page, page_to_net_input
+    eng = engines(net)
+    eng.set_option(OPT_CONV_PATH, 0)
+    x = np.stack([page_to_net_input(synth_page(h, w, seed=11 * h + w + i)) for i in range(n)]).astype(np.float32)
+    try:
+        eng.set_option(OPT_FUSE_BLOCKS, 1)
+        fused = eng.forward(x).copy()
+        names = [k for _, k, _ in eng.profile_ops(1)]
+        assert any(k.startswith("block_mma") for k in names), names
+        again = eng.forward(x).copy()
+        alone = eng.forward(x[n - 1])[0].copy()
+        eng.set_option(OPT_FUSE_BLOCKS, 0)
+        plain = eng.forward(x).copy()
+        assert not any(k.startswith("block_mma") for _, k, _ in eng.profile_ops(1))
+    finally:
+        eng.set_option(OPT_FUSE_BLOCKS, 1)
+    assert np.abs(fused - plain).max() <= 5e-3, float(np.abs(fused - plain).max())
+    ref = oracles(net).run(x)
+    for i in range(n):
+        _check(fused[i], ref[i], f"{net} {h}x{w} page {i} [fused blocks]")
+    # run to run, and a page alone against the same page inside a batch (row segments are cut differently)
+    assert np.array_equal(again, fused)
+    assert np.array_equal(alone, fused[n - 1])
+
+
 @pytest.mark.parametrize("fuse", [0, 1])
 def test_two_fresh_engines_give_identical_bits(built_lib, fuse):
     """Kernel selection is a fixed rule (no plan-time timing): two engines, two plans, same pages -> same bits, at the
