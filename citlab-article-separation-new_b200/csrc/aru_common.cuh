@@ -113,18 +113,16 @@ __device__ __forceinline__ uint4 pack8(const float f[8]) {
 // become inf and poison later 0*x products), optionally ReLU'd.  max(.,0) commutes with the rounding.
 template <bool RELU>
 __device__ __forceinline__ uint32_t pack2_fin(float x, float y) {
+  // one F2FP: round to nearest even, clamp to the largest finite value, optional ReLU (x -> low half, y -> high half)
+  uint32_t d;
 #ifdef ARU_USE_BF16
-  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-  if (RELU) h = __hmax2(h, __floats2bfloat162_rn(0.f, 0.f));
-  return *reinterpret_cast<uint32_t*>(&h);
+  if (RELU) asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
+  else asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
 #else
-  __half2 h = __floats2half2_rn(x, y);
-  const __half2 hi = __half2half2(__ushort_as_half((unsigned short)0x7bff));   // 65504
-  h = __hmin2(h, hi);
-  if (RELU) h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0)));
-  else h = __hmax2(h, __half2half2(__ushort_as_half((unsigned short)0xfbff)));  // -65504
-  return *reinterpret_cast<uint32_t*>(&h);
+  if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
 #endif
+  return d;
 }
 template <bool RELU>
 __device__ __forceinline__ uint4 pack8_fin(const float f[8], bool valid) {

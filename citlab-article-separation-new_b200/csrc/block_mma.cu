@@ -43,10 +43,13 @@ namespace {
 
 constexpr int RB = 4;             // rows per band
 constexpr int LAG = RB + 1;       // rows a stage runs behind its predecessor
-constexpr int IN_ROWS = 2 * RB + 2;
-constexpr int X0_ROWS = 3 * LAG + RB + 1;
-constexpr int R_ROWS = 2 * RB + 2;
-constexpr int ROW_BIAS = 64 * IN_ROWS * X0_ROWS;   // multiple of every ring size, makes row + ROW_BIAS non-negative
+// Rings are made of BANDS of RB rows aligned with the bands their producer writes (a stage's output band, or the RB rows
+// the loader brings in per iteration).  The window a consumer reads - rows a-1 .. a+RB of its own band [a, a+RB) - is
+// then always "rows 2, 3 of one producer band and all four rows of the next", whatever the iteration: no per-row ring
+// arithmetic, a row address is (band address, uniform) + (row offset, a per-lane constant).
+constexpr int NB_IN = 3;          // input ring: the band being loaded + the two being read
+constexpr int NB_X0 = 5;          // x0 ring: written by conv1 (or the loader), read by convR_0 and, 3 (RB+1) rows later, by convR_2
+constexpr int NB_R = 3;
 
 struct BlockArgs {
   const act_t* in;       // CIN_CH > 0: conv1's input planes; CIN_CH == 0: the block's x0 (pre-activation of conv1)
@@ -86,9 +89,6 @@ __device__ __forceinline__ void ldsm4(uint32_t (&a)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr) : "memory");
 }
-__device__ __forceinline__ void ldsm2(uint32_t (&a)[2], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(a[0]), "=r"(a[1]) : "r"(addr) : "memory");
-}
 __device__ __forceinline__ uint32_t relu2(uint32_t v) {
   act2_t h = *reinterpret_cast<act2_t*>(&v);
 #ifdef ARU_USE_BF16
@@ -110,7 +110,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ int ring_slot(int row, int ring) { return (row + ROW_BIAS) % ring; }
 
 // number of B-fragment registers of a stage with ICH input planes and NT output planes
 __host__ __device__ constexpr int stage_regs(int ich, int nt) { return ich == 1 ? 9 * nt : 9 * ich * nt; }
@@ -121,46 +120,65 @@ __device__ __forceinline__ void load_wfrag(uint32_t (&w)[N], const uint32_t* __r
   for (int r = 0; r < N; ++r) w[r] = __ldg(img + (size_t)(base + r) * 32 + lane);
 }
 
-// One stage of one band: acc[i][nt] += conv over the RB + 2 input rows starting at page row `row_first`.
-//   ring: shared-memory address of the input ring (ring_rows rows of ICH planes of `pitch` positions)
-//   lane4 / lane2: per-lane ldmatrix row offsets (bytes) inside a ring row
+// Per-lane byte offsets inside a band of a ring whose rows are `rb` bytes apart.
+struct LaneOff {
+  uint32_t a[4];    // ldmatrix.x4 of row k: (kx = -1 | kx = 0) for one input plane, (plane 2cp | plane 2cp+1) at kx = -1 otherwise
+  uint32_t p[3];    // one input plane: ldmatrix.x4 of the kx = +1 halves of rows k (matrices 0, 1) and k + 1 (matrices 2, 3)
+  uint32_t p_lo;    // the kx = +1 lane offset alone (row offset added by the caller)
+};
+
+// One stage of one band: acc[i][nt] += the 3x3 convolution.  The RB + 2 input rows are rows 0, 1 at bx (+ k rb) and rows
+// 2 .. RB+1 at by (+ k rb).
 template <int ICH, int NT, bool RELU_IN>
-__device__ __forceinline__ void stage_mma(float (&acc)[RB][NT][4], uint32_t ring, int ring_rows, int row_first, int pitch,
-                                          uint32_t lane4, uint32_t lane2, const uint32_t (&w)[stage_regs(ICH, NT)]) {
-  int slot = ring_slot(row_first, ring_rows);
-  const uint32_t row_bytes = (uint32_t)(ICH * pitch) * 16u;
+__device__ __forceinline__ void stage_mma(float (&acc)[RB][NT][4], uint32_t bx, uint32_t by, uint32_t rb, int pitch,
+                                          const LaneOff& lo, bool upper, const uint32_t (&w)[stage_regs(ICH, NT)]) {
+  static_assert(RB == 4, "window layout");
+  if constexpr (ICH == 1) {
+    // weights: w[(ky * NT + nt) * 3 + kx]
+    uint32_t a[RB + 2][4], c[RB + 1][4];
 #pragma unroll
-  for (int j = 0; j < RB + 2; ++j) {
-    const uint32_t base = ring + (uint32_t)slot * row_bytes;
-    slot = slot + 1 == ring_rows ? 0 : slot + 1;
-    if (ICH == 1) {
-      uint32_t a[4], c[2];
-      ldsm4(a, base + lane4);   // kx = -1 (k 0..7) | kx = 0 (k 8..15)
-      ldsm2(c, base + lane2);   // kx = +1
-      if (RELU_IN) {
+    for (int j = 0; j < RB + 2; ++j) ldsm4(a[j], (j < 2 ? bx + lo.a[j] : by + lo.a[j - 2]));
+    ldsm4(c[0], bx + lo.p[0]);
+    ldsm4(c[1], (upper ? by : bx + rb) + lo.p_lo);     // row 1 (old band) | row 2 (new band)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = relu2(a[q]);
-        c[0] = relu2(c[0]);
-        c[1] = relu2(c[1]);
+    for (int j = 2; j < RB + 1; ++j) ldsm4(c[j], by + lo.p[j - 2]);
+    if (RELU_IN) {
+#pragma unroll
+      for (int j = 0; j < RB + 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[j][q] = relu2(a[j][q]);
+#pragma unroll
+      for (int j = 0; j < RB + 1; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[j][q] = relu2(c[j][q]);
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int i = 0; i < RB; ++i)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          mma16(acc[i][nt], a[i + ky][0], a[i + ky][1], a[i + ky][2], a[i + ky][3], w[(ky * NT + nt) * 3], w[(ky * NT + nt) * 3 + 1]);
+    // kx = +1: rows i, i+1 (ky = 0, 1) as one K = 16 step, row i+2 (ky = 2) as a K = 8 step
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mma16(acc[i][nt], c[i][0], c[i][1], c[i][2], c[i][3], w[(0 * NT + nt) * 3 + 2], w[(1 * NT + nt) * 3 + 2]);
+        if (i + 2 < RB + 1) mma8(acc[i][nt], c[i + 2][0], c[i + 2][1], w[(2 * NT + nt) * 3 + 2]);
+        else mma8(acc[i][nt], c[i + 1][2], c[i + 1][3], w[(2 * NT + nt) * 3 + 2]);
       }
+  } else {
+    // weights: w[(((ky * 3 + kx) * (ICH / 2) + cp) * NT + nt) * 2 + {0, 1}]
 #pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        const int ky = j - i;   // input row j = output row i + ky - 1 + 1
-        if (ky < 0 || ky > 2) continue;
+    for (int j = 0; j < RB + 2; ++j) {
+      const uint32_t row = j < 2 ? bx + lo.a[j] : by + lo.a[j - 2];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const int r = (ky * NT + nt) * 3;
-          mma16(acc[i][nt], a[0], a[1], a[2], a[3], w[r], w[r + 1]);
-          mma8(acc[i][nt], c[0], c[1], w[r + 2]);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
+      for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
         for (int cp = 0; cp < ICH / 2; ++cp) {
           uint32_t a[4];
-          ldsm4(a, base + lane4 + (uint32_t)(cp * 2 * pitch + kx) * 16u);   // plane 2cp (k 0..7) | plane 2cp+1 (k 8..15)
+          ldsm4(a, row + (uint32_t)(cp * 2 * pitch + kx) * 16u);
           if (RELU_IN) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) a[q] = relu2(a[q]);
@@ -176,39 +194,46 @@ __device__ __forceinline__ void stage_mma(float (&acc)[RB][NT][4], uint32_t ring
             }
           }
         }
-      }
     }
   }
 }
 
 template <int NT>
-__device__ __forceinline__ void zero_acc(float (&acc)[RB][NT][4]) {
+__device__ __forceinline__ void init_acc(float (&acc)[RB][NT][4], const float (&b)[NT][2]) {
 #pragma unroll
   for (int i = 0; i < RB; ++i)
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) acc[i][nt][0] = acc[i][nt][1] = acc[i][nt][2] = acc[i][nt][3] = 0.f;
+    for (int nt = 0; nt < NT; ++nt) {
+      acc[i][nt][0] = acc[i][nt][2] = b[nt][0];
+      acc[i][nt][1] = acc[i][nt][3] = b[nt][1];
+    }
 }
 
-// bias + (ReLU) + 16-bit store of a band into a ring; out-of-image positions become zeros
-template <int NT, bool RELU>
-__device__ __forceinline__ void store_ring(const float (&acc)[RB][NT][4], uint32_t ring, int ring_rows, int row0, int H,
-                                           int pitch, uint32_t lane_st, bool cv0, bool cv1, const float (&b)[NT][2]) {
-  int slot = ring_slot(row0, ring_rows);
+// (ReLU) + 16-bit store of a band into its ring band at `band`; MASK: out-of-image positions become zeros
+template <int NT, bool RELU, bool MASK>
+__device__ __forceinline__ void store_band(const float (&acc)[RB][NT][4], uint32_t band, const uint32_t (&st)[RB], int pitch,
+                                           int row0, int H, bool cv0, bool cv1) {
 #pragma unroll
   for (int i = 0; i < RB; ++i) {
     const bool rv = (unsigned)(row0 + i) < (unsigned)H;
-    const uint32_t base = ring + (uint32_t)(slot * NT * pitch) * 16u + lane_st;
-    slot = slot + 1 == ring_rows ? 0 : slot + 1;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      uint32_t h0 = pack2_fin<RELU>(acc[i][nt][0] + b[nt][0], acc[i][nt][1] + b[nt][1]);
-      uint32_t h1 = pack2_fin<RELU>(acc[i][nt][2] + b[nt][0], acc[i][nt][3] + b[nt][1]);
-      if (!(rv && cv0)) h0 = 0u;
-      if (!(rv && cv1)) h1 = 0u;
-      sts32(base + (uint32_t)(nt * pitch) * 16u, h0);
-      sts32(base + (uint32_t)(nt * pitch + 8) * 16u, h1);
+      uint32_t h0 = pack2_fin<RELU>(acc[i][nt][0], acc[i][nt][1]);
+      uint32_t h1 = pack2_fin<RELU>(acc[i][nt][2], acc[i][nt][3]);
+      if (MASK) {
+        if (!(rv && cv0)) h0 = 0u;
+        if (!(rv && cv1)) h1 = 0u;
+      }
+      sts32(band + st[i] + (uint32_t)(nt * pitch) * 16u, h0);
+      sts32(band + st[i] + (uint32_t)(nt * pitch + 8) * 16u, h1);
     }
   }
+}
+
+__device__ __forceinline__ uint32_t band_addr(uint32_t base, int cur, int back, int nb, uint32_t band_bytes) {
+  int q = cur - back;
+  q += q < 0 ? nb : 0;
+  return base + (uint32_t)q * band_bytes;
 }
 
 // CIN_CH: input planes of conv1 (0: the launch starts from x0), NT: planes of the block (C / 8)
@@ -223,17 +248,20 @@ __global__ void __launch_bounds__(384, 1) k_block_mma(const __grid_constant__ Bl
   constexpr int FIRST = CONV1 ? 0 : 1;
   constexpr int T3 = CONV1 ? (3 * LAG + 3 + RB - 1) / RB : (2 * LAG + 2 + RB - 1) / RB;
   constexpr int LD_CH = CONV1 ? CIN_CH : NT;       // planes the loader streams
-  constexpr int LD_ROWS = CONV1 ? IN_ROWS : X0_ROWS;
+  constexpr int NB_LD = CONV1 ? NB_IN : NB_X0;
+  constexpr int ICH0 = CONV1 ? CIN_CH : 1;
 
-  // shared-memory carve-up: [mbarriers 64 B][input ring (CONV1)][x0 ring][r0 ring][r1 ring]
+  // shared-memory carve-up: [mbarriers 128 B][input ring (CONV1)][x0 ring][r0 ring][r1 ring]
+  const uint32_t rb_in = (uint32_t)(ICH0 * pitch) * 16u, rb = (uint32_t)(NT * pitch) * 16u;   // bytes per ring row
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_bar = s_base;
   const uint32_t s_in = s_base + 128;
-  const uint32_t s_x0 = s_in + (CONV1 ? (uint32_t)(IN_ROWS * CIN_CH * pitch) * 16u : 0u);
-  const uint32_t s_r0 = s_x0 + (uint32_t)(X0_ROWS * NT * pitch) * 16u;
-  const uint32_t s_r1 = s_r0 + (uint32_t)(R_ROWS * NT * pitch) * 16u;
-  const uint32_t s_end = s_r1 + (uint32_t)(R_ROWS * NT * pitch) * 16u;
+  const uint32_t s_x0 = s_in + (CONV1 ? (uint32_t)(NB_IN * RB) * rb_in : 0u);
+  const uint32_t s_r0 = s_x0 + (uint32_t)(NB_X0 * RB) * rb;
+  const uint32_t s_r1 = s_r0 + (uint32_t)(NB_R * RB) * rb;
+  const uint32_t s_end = s_r1 + (uint32_t)(NB_R * RB) * rb;
   const uint32_t s_ld = CONV1 ? s_in : s_x0;
+  const uint32_t rb_ld = CONV1 ? rb_in : rb;
 
   for (uint32_t o = 128 + threadIdx.x * 16; o < s_end - s_base; o += blockDim.x * 16)
     *reinterpret_cast<uint4*>(smem + o) = make_uint4(0u, 0u, 0u, 0u);
@@ -249,14 +277,32 @@ __global__ void __launch_bounds__(384, 1) k_block_mma(const __grid_constant__ Bl
   const int g8 = lane >> 2, t4 = lane & 3;
   const int u0 = warp << 4;
   const int m = lane >> 3, r8 = lane & 7;
-  // ldmatrix row offsets inside a ring row (position u lives at (1 + u) * 16 bytes of its plane)
-  const uint32_t lane4_1 = (uint32_t)(1 + u0 + (m < 2 ? -1 : 0) + (m & 1) * 8 + r8) * 16u;              // ICH == 1
-  const uint32_t lane2_1 = (uint32_t)(1 + u0 + 1 + (m & 1) * 8 + r8) * 16u;
-  const uint32_t lane4_c = (uint32_t)((m >> 1) * pitch + 1 + u0 - 1 + (m & 1) * 8 + r8) * 16u;          // ICH >= 2, kx = 0
-  const uint32_t lane_st = (uint32_t)(1 + u0 + g8) * 16u + (uint32_t)t4 * 4u;
+  const bool upper = m >= 2;
+  // position u of a ring row lives at byte (1 + u) * 16 of its plane
+  LaneOff lo_in, lo_x;
+  {
+    const uint32_t a1 = (uint32_t)(1 + u0 + (m < 2 ? -1 : 0) + (m & 1) * 8 + r8) * 16u;            // one plane: kx -1 | kx 0
+    const uint32_t ac = (uint32_t)((m >> 1) * pitch + u0 + (m & 1) * 8 + r8) * 16u;                // plane pairs, kx = -1
+    const uint32_t p1 = (uint32_t)(1 + u0 + 1 + (m & 1) * 8 + r8) * 16u;                           // kx = +1
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      lo_in.a[k] = (ICH0 == 1 ? a1 : ac) + (uint32_t)k * rb_in;
+      lo_x.a[k] = (NT == 1 ? a1 : ac) + (uint32_t)k * rb;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo_in.p[k] = p1 + (uint32_t)(k + (upper ? 1 : 0)) * rb_in;
+      lo_x.p[k] = p1 + (uint32_t)(k + (upper ? 1 : 0)) * rb;
+    }
+    lo_in.p_lo = p1;
+    lo_x.p_lo = p1;
+  }
+  uint32_t st[RB];   // store offsets of this lane's first position in rows 0..3 of a band
+#pragma unroll
+  for (int k = 0; k < RB; ++k) st[k] = (uint32_t)(1 + u0 + g8) * 16u + (uint32_t)t4 * 4u + (uint32_t)k * rb;
 
   // filters and biases: registers for the whole launch
-  uint32_t w0[stage_regs(CONV1 ? CIN_CH : 1, NT)];
+  uint32_t w0[stage_regs(ICH0, NT)];
   uint32_t w1[stage_regs(NT, NT)], w2[stage_regs(NT, NT)], w3[stage_regs(NT, NT)];
   float bs[4][NT][2];
   if (warp < n_cw) {
@@ -286,88 +332,110 @@ __global__ void __launch_bounds__(384, 1) k_block_mma(const __grid_constant__ Bl
     // image columns of this lane's two positions
     const int xc0 = xs - 4 + u0 + g8, xc1 = xc0 + 8;
     const bool cv0 = (unsigned)xc0 < (unsigned)W, cv1 = (unsigned)xc1 < (unsigned)W;
+    const bool cols_in = xs - 4 + u0 >= 0 && xs - 4 + u0 + 16 <= W;     // warp-uniform: no column of this warp needs a mask
     const int x_own_end = min(xs + a.WS, W);
     const bool own0 = xc0 >= xs && xc0 < x_own_end, own1 = xc1 >= xs && xc1 < x_own_end;
     const long long page_row0 = a.g.lead + ((long long)n * a.g.Hp + 1) * a.g.Wp + 1;   // position of (y = 0, x = 0)
+    act_t* const out0 = a.out + (page_row0 + xc0) * 8 + 2 * t4;
+    act_t* const pool0 = POOL ? a.pool + (a.pg.lead + ((long long)n * a.pg.Hp + 1) * a.pg.Wp + 1 + (xc0 >> 1)) * 8 + 2 * t4 : nullptr;
 
     auto stage_active = [&](int s, int t) {
       const int as = a3_0 + t * RB + (3 - s) * LAG;
       return as < y1 + (3 - s) && as + RB > y0 - (3 - s);
     };
-    // loader: the rows the first stage reads in iteration t that no earlier iteration brought in
-    auto issue_loads = [&](int t, uint32_t it_t) {
+    // loader: the rows the first stage reads in iteration t that no earlier iteration brought in = band `cur` of the
+    // loader's ring (rows af + 1 .. af + RB); iteration 0 also needs rows af - 1, af = rows 2, 3 of band cur - 1
+    auto issue_loads = [&](int t, uint32_t it_t, int cur) {
       const uint32_t bar = s_bar + (it_t & 1) * 8;
       const int af = a3_0 + t * RB + (3 - FIRST) * LAG;
       int r_lo = t == 0 ? af - 1 : af + 1, r_hi = af + RB;   // inclusive
       if (!stage_active(FIRST, t)) r_hi = r_lo - 1;
-      r_lo = max(r_lo, -1);
-      r_hi = min(r_hi, H);
-      const int rows = max(r_hi - r_lo + 1, 0);
-      const uint32_t row_bytes = (uint32_t)pitch * 16u;
-      mbar_expect_tx(bar, (uint32_t)(rows * LD_CH) * row_bytes);
-      for (int r = r_lo; r <= r_hi; ++r) {
-        const int slot = ring_slot(r, LD_ROWS);
+      const int c_lo = max(r_lo, -1), c_hi = min(r_hi, H);
+      const int rows = max(c_hi - c_lo + 1, 0);
+      const uint32_t plane_bytes = (uint32_t)pitch * 16u;
+      mbar_expect_tx(bar, (uint32_t)(rows * LD_CH) * plane_bytes);
+      for (int r = c_lo; r <= c_hi; ++r) {
+        const int k = r - (af + 1);    // row inside band cur (negative: band cur - 1)
+        const uint32_t dst = k >= 0 ? band_addr(s_ld, cur, 0, NB_LD, RB * rb_ld) + (uint32_t)k * rb_ld
+                                    : band_addr(s_ld, cur, 1, NB_LD, RB * rb_ld) + (uint32_t)(k + RB) * rb_ld;
         const long long p = page_row0 + (long long)r * a.g.Wp + (xs - 5);
 #pragma unroll
         for (int c = 0; c < LD_CH; ++c)
-          bulk_g2s(s_ld + (uint32_t)((slot * LD_CH + c) * pitch) * 16u, a.in + ((long long)c * a.in_plane + p) * 8, row_bytes, bar);
+          bulk_g2s(dst + (uint32_t)c * plane_bytes, a.in + ((long long)c * a.in_plane + p) * 8, plane_bytes, bar);
       }
     };
 
-    if (warp == n_cw && lane == 0) issue_loads(0, it);
+    // band counters of the rings (the band their producer fills / filled for this iteration)
+    int c_ld = 1, c_x0 = 0, c_r0 = 0, c_r1 = 0;
+    if (warp == n_cw && lane == 0) issue_loads(0, it, c_ld);
     for (int t = 0; t < n_iter; ++t, ++it) {
       if (warp == n_cw) {
-        if (lane == 0 && t + 1 < n_iter) issue_loads(t + 1, it + 1);
+        if (lane == 0 && t + 1 < n_iter) issue_loads(t + 1, it + 1, c_ld + 1 == NB_LD ? 0 : c_ld + 1);
       } else {
         mbar_wait(s_bar + (it & 1) * 8, (it >> 1) & 1, a.err_flag, 41);
         const int a3 = a3_0 + t * RB;
         float acc[RB][NT][4];
         if constexpr (CONV1) if (stage_active(0, t)) {
           const int as = a3 + 3 * LAG;
-          zero_acc<NT>(acc);
-          stage_mma<CONV1 ? CIN_CH : 1, NT, false>(acc, s_in, IN_ROWS, as - 1, pitch, CIN_CH == 1 ? lane4_1 : lane4_c, lane2_1, w0);
-          store_ring<NT, false>(acc, s_x0, X0_ROWS, as, H, pitch, lane_st, cv0, cv1, bs[0]);
+          init_acc<NT>(acc, bs[0]);
+          stage_mma<ICH0, NT, false>(acc, band_addr(s_in, c_ld, 1, NB_IN, RB * rb_in) + 2 * rb_in,
+                                     band_addr(s_in, c_ld, 0, NB_IN, RB * rb_in), rb_in, pitch, lo_in, upper, w0);
+          const uint32_t dst = band_addr(s_x0, c_x0, 0, NB_X0, RB * rb);
+          if (cols_in && as >= 0 && as + RB <= H) store_band<NT, false, false>(acc, dst, st, pitch, as, H, cv0, cv1);
+          else store_band<NT, false, true>(acc, dst, st, pitch, as, H, cv0, cv1);
         }
         if (stage_active(1, t)) {
           const int as = a3 + 2 * LAG;
-          zero_acc<NT>(acc);
-          stage_mma<NT, NT, true>(acc, s_x0, X0_ROWS, as - 1, pitch, NT == 1 ? lane4_1 : lane4_c, lane2_1, w1);
-          store_ring<NT, true>(acc, s_r0, R_ROWS, as, H, pitch, lane_st, cv0, cv1, bs[1]);
+          init_acc<NT>(acc, bs[1]);
+          // conv1 fused: x0 bands 2 and 1 back; loader-fed: bands 1 and 0 back (the loader's band counter)
+          const int cx = CONV1 ? c_x0 : c_ld, back = CONV1 ? 1 : 0;
+          stage_mma<NT, NT, true>(acc, band_addr(s_x0, cx, back + 1, NB_X0, RB * rb) + 2 * rb,
+                                  band_addr(s_x0, cx, back, NB_X0, RB * rb), rb, pitch, lo_x, upper, w1);
+          const uint32_t dst = band_addr(s_r0, c_r0, 0, NB_R, RB * rb);
+          if (cols_in && as >= 0 && as + RB <= H) store_band<NT, true, false>(acc, dst, st, pitch, as, H, cv0, cv1);
+          else store_band<NT, true, true>(acc, dst, st, pitch, as, H, cv0, cv1);
         }
         if (stage_active(2, t)) {
           const int as = a3 + LAG;
-          zero_acc<NT>(acc);
-          stage_mma<NT, NT, false>(acc, s_r0, R_ROWS, as - 1, pitch, NT == 1 ? lane4_1 : lane4_c, lane2_1, w2);
-          store_ring<NT, true>(acc, s_r1, R_ROWS, as, H, pitch, lane_st, cv0, cv1, bs[2]);
+          init_acc<NT>(acc, bs[2]);
+          stage_mma<NT, NT, false>(acc, band_addr(s_r0, c_r0, 2, NB_R, RB * rb) + 2 * rb, band_addr(s_r0, c_r0, 1, NB_R, RB * rb),
+                                   rb, pitch, lo_x, upper, w2);
+          const uint32_t dst = band_addr(s_r1, c_r1, 0, NB_R, RB * rb);
+          if (cols_in && as >= 0 && as + RB <= H) store_band<NT, true, false>(acc, dst, st, pitch, as, H, cv0, cv1);
+          else store_band<NT, true, true>(acc, dst, st, pitch, as, H, cv0, cv1);
         }
         if (stage_active(3, t)) {
-          zero_acc<NT>(acc);
-          stage_mma<NT, NT, false>(acc, s_r1, R_ROWS, a3 - 1, pitch, NT == 1 ? lane4_1 : lane4_c, lane2_1, w3);
-          // + bias + x0 (pre-activation of conv1) -> ReLU -> global (+ pooled copy)
+          init_acc<NT>(acc, bs[3]);
+          stage_mma<NT, NT, false>(acc, band_addr(s_r1, c_r1, 2, NB_R, RB * rb) + 2 * rb, band_addr(s_r1, c_r1, 1, NB_R, RB * rb),
+                                   rb, pitch, lo_x, upper, w3);
+          // + x0 (pre-activation of conv1) -> ReLU -> global (+ pooled copy).  Rows a3 .. a3+3 of x0 are rows 1, 2, 3 of
+          // one band and row 0 of the next: 4 / 3 bands back (conv1 fused), 3 / 2 bands back (loader-fed)
+          const int cx = CONV1 ? c_x0 : c_ld, back = CONV1 ? 4 : 3;
+          const uint32_t xa = band_addr(s_x0, cx, back, NB_X0, RB * rb), xb = band_addr(s_x0, cx, back - 1, NB_X0, RB * rb);
+          const bool edge = !(cols_in && a3 >= 0 && a3 + RB <= H);
           uint32_t hp[RB][NT][2];
-          int slot = ring_slot(a3, X0_ROWS);
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
             const int y = a3 + i;
             const bool rv = (unsigned)y < (unsigned)H && y >= y0 && y < y1;
-            const uint32_t xb = s_x0 + (uint32_t)(slot * NT * pitch) * 16u + lane_st;
-            slot = slot + 1 == X0_ROWS ? 0 : slot + 1;
-            const long long prow = page_row0 + (long long)y * a.g.Wp;
+            const uint32_t xr = i < 3 ? xa + st[i + 1] : xb + st[0];
+            act_t* const orow = out0 + (long long)y * a.g.Wp * 8;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-              const uint32_t q0 = lds32(xb + (uint32_t)(nt * pitch) * 16u);
-              const uint32_t q1 = lds32(xb + (uint32_t)(nt * pitch + 8) * 16u);
+              const uint32_t q0 = lds32(xr + (uint32_t)(nt * pitch) * 16u);
+              const uint32_t q1 = lds32(xr + (uint32_t)(nt * pitch + 8) * 16u);
               const float2 f0 = act2_to_f2(*reinterpret_cast<const act2_t*>(&q0));
               const float2 f1 = act2_to_f2(*reinterpret_cast<const act2_t*>(&q1));
-              uint32_t h0 = pack2_fin<true>(acc[i][nt][0] + bs[3][nt][0] + f0.x, acc[i][nt][1] + bs[3][nt][1] + f0.y);
-              uint32_t h1 = pack2_fin<true>(acc[i][nt][2] + bs[3][nt][0] + f1.x, acc[i][nt][3] + bs[3][nt][1] + f1.y);
-              if (!(rv && cv0)) h0 = 0u;
-              if (!(rv && cv1)) h1 = 0u;
+              uint32_t h0 = pack2_fin<true>(acc[i][nt][0] + f0.x, acc[i][nt][1] + f0.y);
+              uint32_t h1 = pack2_fin<true>(acc[i][nt][2] + f1.x, acc[i][nt][3] + f1.y);
+              if (POOL && edge) {   // the pooling windows of the last row / column take zeros for what lies outside
+                if (!(rv && cv0)) h0 = 0u;
+                if (!(rv && cv1)) h1 = 0u;
+              }
               hp[i][nt][0] = h0;
               hp[i][nt][1] = h1;
-              act_t* o = a.out + ((long long)nt * a.out_plane + prow) * 8 + 2 * t4;
-              if (rv && own0) *reinterpret_cast<uint32_t*>(o + (long long)xc0 * 8) = h0;
-              if (rv && own1) *reinterpret_cast<uint32_t*>(o + (long long)xc1 * 8) = h1;
+              if (rv && own0) *reinterpret_cast<uint32_t*>(orow + (long long)nt * a.out_plane * 8) = h0;
+              if (rv && own1) *reinterpret_cast<uint32_t*>(orow + (long long)nt * a.out_plane * 8 + 64) = h1;
             }
           }
           if (POOL) {
@@ -376,21 +444,24 @@ __global__ void __launch_bounds__(384, 1) k_block_mma(const __grid_constant__ Bl
             for (int i = 0; i < RB; i += 2) {
               const int y = a3 + i;
               const bool rv = (unsigned)y < (unsigned)H && y >= y0 && y < y1;
-              const long long prow = a.pg.lead + ((long long)n * a.pg.Hp + (y >> 1) + 1) * a.pg.Wp + 1;
+              act_t* const prow = pool0 + (long long)(y >> 1) * a.pg.Wp * 8;
 #pragma unroll
               for (int nt = 0; nt < NT; ++nt) {
                 uint32_t m0 = max2(hp[i][nt][0], hp[i + 1][nt][0]);
                 uint32_t m1 = max2(hp[i][nt][1], hp[i + 1][nt][1]);
                 m0 = max2(m0, __shfl_xor_sync(0xffffffffu, m0, 4));
                 m1 = max2(m1, __shfl_xor_sync(0xffffffffu, m1, 4));
-                act_t* o = a.pool + ((long long)nt * a.pool_plane + prow) * 8 + 2 * t4;
-                if (!(g8 & 1) && rv && own0) *reinterpret_cast<uint32_t*>(o + (long long)(xc0 >> 1) * 8) = m0;
-                if (!(g8 & 1) && rv && own1) *reinterpret_cast<uint32_t*>(o + (long long)(xc1 >> 1) * 8) = m1;
+                if (!(g8 & 1) && rv && own0) *reinterpret_cast<uint32_t*>(prow + (long long)nt * a.pool_plane * 8) = m0;
+                if (!(g8 & 1) && rv && own1) *reinterpret_cast<uint32_t*>(prow + (long long)nt * a.pool_plane * 8 + 32) = m1;
               }
             }
           }
         }
       }
+      c_ld = c_ld + 1 == NB_LD ? 0 : c_ld + 1;
+      c_x0 = c_x0 + 1 == NB_X0 ? 0 : c_x0 + 1;
+      c_r0 = c_r0 + 1 == NB_R ? 0 : c_r0 + 1;
+      c_r1 = c_r1 + 1 == NB_R ? 0 : c_r1 + 1;
       __syncthreads();
     }
   }
@@ -399,7 +470,7 @@ __global__ void __launch_bounds__(384, 1) k_block_mma(const __grid_constant__ Bl
 // ---- host side ---------------------------------------------------------------------------------------------------------
 size_t block_smem_bytes(int cin_ch, int nt, int wc) {
   const size_t pitch = wc + 2;
-  size_t rows = (size_t)(cin_ch > 0 ? IN_ROWS * cin_ch : 0) + (size_t)X0_ROWS * nt + 2 * (size_t)R_ROWS * nt;
+  size_t rows = (size_t)(cin_ch > 0 ? NB_IN * RB * cin_ch : 0) + (size_t)(NB_X0 * RB) * nt + 2 * (size_t)(NB_R * RB) * nt;
   return 128 + rows * pitch * 16;
 }
 

@@ -7,6 +7,7 @@
 //   0  MMAs only: NACC independent accumulators per warp, A / B fragments constant in registers
 //   1  one ldmatrix.x4 (512 B of shared memory per warp) per MMA
 //   2  one ldmatrix.x4 per 3 MMAs (the vertical-tap reuse of a fused 3x3 block)
+//   4  m16n8k8 only (FLOP figures printed assume 4096 per MMA: halve them)      5  alternating m16n8k16 / m16n8k8
 //   3  like 2 plus one 16-byte shared-memory store per lane per 15 MMAs (an intermediate row written back)
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -18,6 +19,10 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
 }
 __device__ __forceinline__ void ldsm4(uint32_t (&a)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -42,7 +47,9 @@ __global__ void __launch_bounds__(NACC > 8 ? 512 : 1024) k_rate(int iters, float
     for (int j = 0; j < NACC; ++j) {
       if (VAR == 1) ldsm4(a, sbase + ((it + j) & 3) * 512);
       if ((VAR == 2 || VAR == 3) && (j % 3) == 0) ldsm4(a, sbase + ((it + j) & 3) * 512);
-      mma16816(acc[j], a, b0, b1);
+      if (VAR == 4) mma1688(acc[j], a[0], a[1], b0);
+      else if (VAR == 5 && (j & 1)) mma1688(acc[j], a[0], a[1], b0);
+      else mma16816(acc[j], a, b0, b1);
     }
     if (VAR == 3 && (it % 2) == 0) {
       uint4 v = make_uint4(__float_as_uint(acc[0][0]), __float_as_uint(acc[1][1]), it, lane);
@@ -98,5 +105,7 @@ int main() {
   for (int w : {4, 8, 16, 32}) run<1, 8>(w, it, sms);
   for (int w : {4, 8, 16}) run<2, 15>(w, it, sms);
   for (int w : {4, 8, 16}) run<3, 15>(w, it, sms);
+  for (int w : {4, 8, 16}) run<4, 8>(w, it, sms);
+  for (int w : {4, 8, 16}) run<5, 8>(w, it, sms);
   return 0;
 }
