@@ -47,6 +47,7 @@ struct OpWeights {
   uint32_t* blk_w = nullptr;   // block_mma.cu: B fragments of the residual block this op ends (with / without conv1)
   float* blk_bias = nullptr;   // [4][16]
   int blk_cin = -1;            // conv1 input channels the fragments were packed for (0: block starts from x0)
+  uint32_t* head_w = nullptr;  // combine_head.cu: B fragments of a classifier that runs in the combine's launch
   float* w32 = nullptr;     // stem [tap][cpad] / small [tap][cin_pad][cout]
   float* bias = nullptr;    // zero-padded to a multiple of 16
   int cin = 0, cout = 0;
@@ -85,6 +86,7 @@ struct Plan {
   std::vector<BlockMmaPlan> blk;
   std::vector<char> blk_from_x0;        // per op c: conv1 runs as its own launch and the block starts from its pre-activation
   std::vector<char> pre_only;           // per conv1 op of such a block: only the pre-activation is stored
+  std::vector<int> head_combine;        // per classifier conv op: the COMBINE op its launch also performs (-1: none)
   act_t* scratch = nullptr;             // partial sums of split-K launches
   size_t scratch_bytes = 0;
   std::vector<const char*> kernel;   // per op label
@@ -296,6 +298,29 @@ float* f32_ptr(const aru_engine* e, const Plan* p, int buf, int parity) {
   return reinterpret_cast<float*>(p->arena + p->bufs[buf].offset);
 }
 
+CombineArgs combine_args(const aru_engine* e, const Plan* p, const aru_op& op, int parity) {
+  CombineArgs a{};
+  const BufPlan& bo = p->bufs[op.out.buf];
+  a.A = op.n_scales;
+  a.geo = bo.geo;
+  PV out = make_pv(e, p, op.out);
+  a.out = out.p; a.out_plane = out.plane; a.out_chunks = out.chunks;
+  for (int k = 0; k < op.n_scales; ++k) {
+    const BufPlan& ba = p->bufs[op.att[k].buf];
+    a.att[k] = f32_ptr(e, p, op.att[k].buf, parity);
+    a.att_h[k] = ba.h; a.att_w[k] = ba.w; a.att_up[k] = op.up_att[k];
+    a.att_oy[k] = (ba.h * op.up_att[k] - bo.h) / 2;
+    a.att_ox[k] = (ba.w * op.up_att[k] - bo.w) / 2;
+    const BufPlan& bd = p->bufs[op.det[k].buf];
+    PV det = make_pv(e, p, op.det[k]);
+    a.det[k] = det.p; a.det_plane[k] = det.plane; a.det_chunks[k] = det.chunks; a.det_geo[k] = bd.geo;
+    a.det_up[k] = op.up_det[k];
+    a.det_oy[k] = (bd.h * op.up_det[k] - bo.h) / 2;
+    a.det_ox[k] = (bd.w * op.up_det[k] - bo.w) / 2;
+  }
+  return a;
+}
+
 // Enqueue op `oi` of plan p on stream st.
 int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
   const aru_op& op = e->ops[oi];
@@ -315,6 +340,10 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
                                make_pv(e, p, op.out_pre), e->weights.data() + op.w_off, e->weights.data() + op.b_off,
                                bo.geo, op.act, pj >= 0 ? make_pv(e, p, e->ops[pj].out) : PV(),
                                pj >= 0 ? &p->bufs[e->ops[pj].out.buf].geo : nullptr, !p->pool_only[oi], ow.w32, ow.bias);
+      } else if (bo.kind != KIND_PLANAR && p->head_combine[oi] >= 0) {
+        label = "combine_head";   // attention combine + classifier, the combined map stays in shared memory
+        err = launch_combine_head(st, combine_args(e, p, e->ops[p->head_combine[oi]], parity), ow.head_w,
+                                  e->weights.data() + op.b_off, op.out.ch, op.act, f32_ptr(e, p, op.out.buf, parity), e->err_flag);
       } else if (bo.kind != KIND_PLANAR && p->band[oi].ok && p->use_band[oi]) {
         label = "conv_band_head";
         err = launch_conv_band(st, p->band[oi], make_pv(e, p, op.in), PV(), PV(), PV(), ow.band_w, ow.bias, bi.geo, op.act,
@@ -406,27 +435,12 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
       break;
     }
     case ARU_OP_COMBINE: {
-      label = "combine";
-      CombineArgs a{};
-      const BufPlan& bo = p->bufs[op.out.buf];
-      a.A = op.n_scales;
-      a.geo = bo.geo;
-      PV out = make_pv(e, p, op.out);
-      a.out = out.p; a.out_plane = out.plane; a.out_chunks = out.chunks;
-      for (int k = 0; k < op.n_scales; ++k) {
-        const BufPlan& ba = p->bufs[op.att[k].buf];
-        a.att[k] = f32_ptr(e, p, op.att[k].buf, parity);
-        a.att_h[k] = ba.h; a.att_w[k] = ba.w; a.att_up[k] = op.up_att[k];
-        a.att_oy[k] = (ba.h * op.up_att[k] - bo.h) / 2;
-        a.att_ox[k] = (ba.w * op.up_att[k] - bo.w) / 2;
-        const BufPlan& bd = p->bufs[op.det[k].buf];
-        PV det = make_pv(e, p, op.det[k]);
-        a.det[k] = det.p; a.det_plane[k] = det.plane; a.det_chunks[k] = det.chunks; a.det_geo[k] = bd.geo;
-        a.det_up[k] = op.up_det[k];
-        a.det_oy[k] = (bd.h * op.up_det[k] - bo.h) / 2;
-        a.det_ox[k] = (bd.w * op.up_det[k] - bo.w) / 2;
+      if (p->skip[oi]) {
+        label = "head_fused";   // performed by the classifier's launch (combine_head.cu)
+        break;
       }
-      err = launch_combine(st, a);
+      label = "combine";
+      err = launch_combine(st, combine_args(e, p, op, parity));
       break;
     }
     case ARU_OP_UPSUM: {
@@ -502,6 +516,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
   p->blk.resize(no);
   p->blk_from_x0.assign(no, 0);
   p->pre_only.assign(no, 0);
+  p->head_combine.assign(no, -1);
   p->kernel.assign(no, "?");
   for (int i = 0; i < nb; ++i) {
     p->bufs[i].kind = e->kind[i];
@@ -780,7 +795,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
                               e->weights.data() + oc.w_off};
         block_mma_pack(bp, wt, cin, img.data());
         std::vector<float> b4(64, 0.f);
-        const int offs[4] = {o1.b_off, oa.b_off, ob.b_off, oc.b_off};
+        const long long offs[4] = {o1.b_off, oa.b_off, ob.b_off, oc.b_off};
         for (int s2 = 0; s2 < 4; ++s2)
           for (int c2 = 0; c2 < 8; ++c2) b4[s2 * 16 + c2] = e->weights[(size_t)offs[s2] + c2];
         if ((rc = upload(e, img, &ow.blk_w)) || (rc = upload(e, b4, &ow.blk_bias))) { free_plan(p.get()); return rc; }
@@ -794,6 +809,37 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       p->skip[ia] = p->skip[ib] = 1;
       if (cin > 0) p->skip[i] = 1;
       else if (p->bufs[o1.in.buf].kind == KIND_F32) p->pre_only[i] = 1;
+    }
+  }
+  // The attention combine runs inside the launch of the classifier that is its only reader (combine_head.cu).
+  {
+    const char* env = getenv("ARU_FUSE_HEAD");
+    const bool fuse = e->conv_path == 0 && !e->keep_all && (env ? env[0] == '1' : e->fuse_blocks != 0);
+    for (int c = 0; c < no && fuse; ++c) {
+      const aru_op& oc = e->ops[c];
+      if (oc.kind != ARU_OP_COMBINE || oc.out.buf == e->output_buf) continue;
+      int h = -1, readers = 0;
+      for (int j = c + 1; j < no; ++j) {
+        const aru_op& ro = e->ops[j];
+        bool rd = ro.in.buf == oc.out.buf || ro.res.buf == oc.out.buf;
+        if (ro.kind == ARU_OP_COMBINE)
+          for (int k = 0; k < ro.n_scales; ++k) rd = rd || ro.att[k].buf == oc.out.buf || ro.det[k].buf == oc.out.buf;
+        if (rd) { if (h < 0) h = j; ++readers; }
+      }
+      if (readers != 1) continue;
+      const aru_op& oh = e->ops[h];
+      if (oh.kind != ARU_OP_CONV || oh.in.buf != oc.out.buf || oh.in.ch_off != oc.out.ch_off || oh.in.ch != oc.out.ch ||
+          oh.res.buf >= 0 || oh.out_pre.buf >= 0 || p->bufs[oh.out.buf].kind == KIND_PLANAR)
+        continue;
+      if (!combine_head_ok(combine_args(e, p.get(), oc, 0), oh.ksize, oh.in.ch, oh.out.ch, oh.act)) continue;
+      OpWeights& ow = e->opw[h];
+      if (!ow.head_w) {
+        std::vector<uint32_t> img(16 * 32, 0u);
+        combine_head_pack(e->weights.data() + oh.w_off, oh.out.ch, img.data());
+        if ((rc = upload(e, img, &ow.head_w))) { free_plan(p.get()); return rc; }
+      }
+      p->head_combine[h] = c;
+      p->skip[c] = 1;
     }
   }
   // Pairs of chained 3x3 convolutions with C_out = 8 / 16 run as one launch (conv_band2.cu): greedy in program order,
@@ -1574,6 +1620,7 @@ void aru_destroy(aru_engine* e) {
     if (w.band_w) cudaFree(w.band_w);
     if (w.blk_w) cudaFree(w.blk_w);
     if (w.blk_bias) cudaFree(w.blk_bias);
+    if (w.head_w) cudaFree(w.head_w);
     if (w.w32) cudaFree(w.w32);
     if (w.bias) cudaFree(w.bias);
   }

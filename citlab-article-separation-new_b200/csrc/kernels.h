@@ -210,6 +210,13 @@ void block_mma_pack(const BlockMmaPlan& plan, const float* const w_tf[4], int ci
 cudaError_t launch_block_mma(cudaStream_t st, const BlockMmaPlan& plan, PV in, PV out, PV pool, const Geo* pool_geo,
                              const uint32_t* wfrag, const float* bias4, const Geo& g, int* err_flag);
 
+// ---- attention combine + 4x4 classifier head in one launch (combine_head.cu) ---------------------
+// out = act(conv4x4(combine(...)) + bias) as dense float32 NHWC; the combined 8-channel map stays in shared memory
+bool combine_head_ok(const CombineArgs& c, int ks, int cin, int cout, int act);
+void combine_head_pack(const float* w_tf, int cout, uint32_t* dst);   // dst: 16 * 32 words
+cudaError_t launch_combine_head(cudaStream_t st, const CombineArgs& c, const uint32_t* wfrag, const float* bias_host,
+                                int cout, int act, float* out, int* err_flag);
+
 // host-side 16-bit conversion matching act_t
 uint16_t host_f_to_act(float v);
 
