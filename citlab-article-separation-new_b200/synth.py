@@ -29,6 +29,8 @@ NETS = {
                  logit_gain=0.5, logit_bias=(-3.0, 0.0)),
     "tiny_sigmoid": dict(graph="RU", scale_space_num=2, n_class=1, seed=5, output="sigmoid",
                          logit_gain=0.5, logit_bias=(-1.0,)),
+    "tiny_aru_sigmoid": dict(graph="ARU", scale_space_num=3, num_scales_att=2, n_class=1, seed=6, output="sigmoid",
+                             logit_gain=0.5, logit_bias=(-1.0,)),
 }
 
 

@@ -217,6 +217,40 @@ def test_fused_residual_blocks_against_one_launch_per_layer(engines, oracles, ne
     assert np.array_equal(alone, fused[n - 1])
 
 
+@pytest.mark.parametrize("net,n,h,w", [
+    ("separator", 1, 257, 130),     # odd sizes: partial tiles in both directions, odd crop offsets of the upsampled maps
+    ("separator", 2, 150, 613),     # several column tiles and a batch
+    ("separator", 1, 29, 131),      # one row tile shorter than a tile, 3 columns into the second column tile
+    ("heading", 2, 90, 68),
+    ("aru_s6a5", 1, 129, 97),       # five attention scales
+    ("tiny", 3, 9, 200),            # two scales, pages shorter than a tile
+    ("tiny_aru_sigmoid", 1, 48, 40),   # one class, sigmoid head
+])
+def test_fused_attention_tail_and_classifier_against_two_launches(built_lib, oracles, monkeypatch, net, n, h, w):
+    """combine_head.cu (attention combine + 4x4 classifier in one launch, the combined map in shared memory) against
+    k_combine followed by the stand-alone head: the intermediate is the same bit for bit (same expression, same rounding),
+    the classifier's fp32 sums are accumulated in another order -> probabilities within 5e-5; and against the oracle."""
+    from aru_b200.engine import Engine
+    from aru_b200.synth import synth_pb, synth_page, page_to_net_input
+    x = np.stack([page_to_net_input(synth_page(h, w, seed=13 * h + w + i)) for i in range(n)]).astype(np.float32)
+    outs = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("ARU_FUSE_HEAD", fuse)
+        eng = Engine(synth_pb(net), device=0)
+        outs[fuse] = eng.forward(x).copy()
+        names = [k for _, k, _ in eng.profile_ops(1)]
+        assert ("combine_head" in names) == (fuse == "1"), names
+        assert ("combine" in names) == (fuse == "0"), names
+        if fuse == "1":
+            assert np.array_equal(eng.forward(x), outs[fuse])
+            assert np.array_equal(eng.forward(x[n - 1])[0], outs[fuse][n - 1])
+        eng.close()
+    assert np.abs(outs["1"] - outs["0"]).max() <= 5e-5, float(np.abs(outs["1"] - outs["0"]).max())
+    ref = oracles(net).run(x)
+    for i in range(n):
+        _check(outs["1"][i], ref[i], f"{net} {h}x{w} page {i} [fused head]")
+
+
 @pytest.mark.parametrize("fuse", [0, 1])
 def test_two_fresh_engines_give_identical_bits(built_lib, fuse):
     """Kernel selection is a fixed rule (no plan-time timing): two engines, two plans, same pages -> same bits, at the

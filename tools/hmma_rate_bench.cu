@@ -8,6 +8,7 @@
 //   1  one ldmatrix.x4 (512 B of shared memory per warp) per MMA
 //   2  one ldmatrix.x4 per 3 MMAs (the vertical-tap reuse of a fused 3x3 block)
 //   4  m16n8k8 only (FLOP figures printed assume 4096 per MMA: halve them)      5  alternating m16n8k16 / m16n8k8
+//   6 / 7 / 8  MMAs only as in 0, plus 2 / 4 / 8 independent FFMAs per MMA (does ALU work issue under a busy tensor pipe?)
 //   3  like 2 plus one 16-byte shared-memory store per lane per 15 MMAs (an intermediate row written back)
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -41,6 +42,9 @@ __global__ void __launch_bounds__(NACC > 8 ? 512 : 1024) k_rate(int iters, float
   uint32_t a[4] = {0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u};
   uint32_t b0 = 0x2c002c00u + lane, b1 = 0x2c002c00u;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem) + (warp & 7) * 2048 + lane * 16;
+  float f[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) f[q] = (float)(lane + q);
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -50,6 +54,11 @@ __global__ void __launch_bounds__(NACC > 8 ? 512 : 1024) k_rate(int iters, float
       if (VAR == 4) mma1688(acc[j], a[0], a[1], b0);
       else if (VAR == 5 && (j & 1)) mma1688(acc[j], a[0], a[1], b0);
       else mma16816(acc[j], a, b0, b1);
+      if (VAR >= 6 && VAR <= 8) {
+        constexpr int NF = VAR == 6 ? 2 : VAR == 7 ? 4 : 8;
+#pragma unroll
+        for (int q = 0; q < NF; ++q) f[q] = fmaf(f[q], 1.0001f, 0.5f);
+      }
     }
     if (VAR == 3 && (it % 2) == 0) {
       uint4 v = make_uint4(__float_as_uint(acc[0][0]), __float_as_uint(acc[1][1]), it, lane);
@@ -60,6 +69,8 @@ __global__ void __launch_bounds__(NACC > 8 ? 512 : 1024) k_rate(int iters, float
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < NACC; ++j) s += acc[j][0] + acc[j][1] + acc[j][2] + acc[j][3];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += f[q];
   if (s == 123.456f) out[0] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -105,6 +116,9 @@ int main() {
   for (int w : {4, 8, 16, 32}) run<1, 8>(w, it, sms);
   for (int w : {4, 8, 16}) run<2, 15>(w, it, sms);
   for (int w : {4, 8, 16}) run<3, 15>(w, it, sms);
+  for (int w : {4, 12}) run<6, 8>(w, it, sms);
+  for (int w : {4, 12}) run<7, 8>(w, it, sms);
+  for (int w : {4, 12}) run<8, 8>(w, it, sms);
   for (int w : {4, 8, 16}) run<4, 8>(w, it, sms);
   for (int w : {4, 8, 16}) run<5, 8>(w, it, sms);
   return 0;
