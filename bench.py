@@ -139,6 +139,21 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # roofline of the kernel classes of one plan
 # ---------------------------------------------------------------------------------------------------
+def kernel_of_chain_is_block(op, prog, prof):
+    """True when the launch that performs `op` is a block_mma launch (its conv1 pre-activation stays in shared memory)."""
+    ops = list(prog.ops)
+    i = ops.index(op)
+    buf = op.out.buf
+    for j in range(i + 1, len(ops)):
+        if ops[j].inp.buf == buf:
+            k = prof[j][1]
+            if k == "pair_fused":
+                buf = ops[j].out.buf
+                continue
+            return k.startswith("block_mma")
+    return False
+
+
 def class_rooflines(eng, n, h, w, peaks, iters=3):
     """Per kernel class: algorithmic FLOPs / bytes (every layer reads its input and writes its
     output once at the storage dtype) and the CUDA-event time of its launches on the engine stream."""
@@ -166,11 +181,22 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
             for ent in writer.get(op.inp.buf, ()):
                 ent["bytes"] += n * oh * ow * op.inp.ch * 2
             continue
-        if kernel == "pair_fused":
+        if kernel == "pair_fused":      # performed by a later op's launch (conv_band2.cu, block_mma.cu): carry its work
             oh, ow = hw(op.out.buf)
             ih, iw = hw(op.inp.buf)
-            pending[op.out.buf] = (2.0 * n * oh * ow * op.ksize * op.ksize * op.inp.ch * op.out.ch,
-                                   n * (ih * iw * op.inp.ch * 2 + (oh * ow * op.out.ch * 2 if op.out_pre.buf >= 0 else 0)))
+            f0, b0 = pending.pop(op.inp.buf, (0.0, None))
+            if b0 is None:              # first op of the chain: its input is what the launch reads
+                b0 = n * ih * iw * op.inp.ch * 2
+            pending[op.out.buf] = (f0 + 2.0 * n * oh * ow * op.ksize * op.ksize * op.inp.ch * op.out.ch,
+                                   b0 + (n * oh * ow * op.out.ch * 2 if op.out_pre.buf >= 0 and not kernel_of_chain_is_block(op, prog, prof) else 0))
+            continue
+        if kernel == "head_fused":      # the attention combine, performed by the classifier's launch (combine_head.cu)
+            b = 0.0
+            for a, d in zip(op.att, op.det):
+                ah, aw = hw(a.buf)
+                dh, dw = hw(d.buf)
+                b += n * (ah * aw * 4 + dh * dw * d.ch * 2)
+            pending[op.out.buf] = (0.0, b)
             continue
         if op.kind in (P.OP_CONV, P.OP_DECONV):
             oh, ow = hw(op.out.buf)
@@ -182,14 +208,18 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
             bytes_ = n * (ih * iw * op.inp.ch * in_b + oh * ow * op.out.ch * out_b)
             if kernel == "conv_stem_pool":     # only the pooled tensor is stored (added by the pool_fused op that follows)
                 bytes_ = n * ih * iw * 4
+            if kernel == "conv_stem_pre":      # only the pre-activation is stored (the block that follows starts from it)
+                bytes_ = n * ih * iw * 4
             if op.res.buf >= 0:
                 bytes_ += n * oh * ow * op.out.ch * 2
             if op.out_pre.buf >= 0:
                 bytes_ += n * oh * ow * op.out.ch * 2
-            if kernel.startswith("conv_band2") and op.inp.buf in pending:
+            if kernel.startswith(("conv_band2", "block_mma", "combine_head")) and op.inp.buf in pending:
                 f0, b0 = pending.pop(op.inp.buf)
                 flops += f0
-                bytes_ += b0 - n * ih * iw * op.inp.ch * in_b     # the intermediate never leaves the SM
+                bytes_ += b0 - n * ih * iw * op.inp.ch * in_b     # the intermediates never leave the SM
+                if kernel.startswith("block_mma") and op.res.buf >= 0:
+                    bytes_ -= n * oh * ow * op.out.ch * 2         # the residual is the block's own x0 (computed or already read)
         elif op.kind in (P.OP_MAXPOOL, P.OP_AVGPOOL):
             oh, ow = hw(op.out.buf)
             ih, iw = hw(op.inp.buf)

@@ -92,8 +92,13 @@ struct Plan {
   std::vector<const char*> kernel;   // per op label
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
-  float* in_dev[2] = {nullptr, nullptr};
-  float* out_dev[2] = {nullptr, nullptr};
+  // [0], [1]: the plan's own double-buffered staging; [2 .. 2 + EXT_SLOTS): caller-owned device buffers bound in place
+  // by aru_forward_device (no staging copy; one captured graph per binding, least recently used slot recycled)
+  static constexpr int EXT_SLOTS = 4;
+  float* in_dev[2 + EXT_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* out_dev[2 + EXT_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long ext_use[2 + EXT_SLOTS] = {0, 0, 0, 0, 0, 0};
+  unsigned long long ext_clock = 0;
   uint8_t* u8_dev[2] = {nullptr, nullptr};
   uint8_t* mask_dev[2] = {nullptr, nullptr};
   uint8_t* page_dev[2] = {nullptr, nullptr};   // uint8 gray / BGR pages (aru_separator_pages)
@@ -103,12 +108,12 @@ struct Plan {
   uint8_t* hor_dev[2] = {nullptr, nullptr};    // separator post-processing results
   uint8_t* ver_dev[2] = {nullptr, nullptr};
   void* post_scratch = nullptr;                // labels, areas, bit planes (used on the compute stream only)
-  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  cudaGraphExec_t graph[2 + EXT_SLOTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   bool d2h_pending[2] = {false, false};
   int launches = 0;
   uint64_t last_use = 0;
-  int eager_passes[2] = {0, 0};   // passes enqueued without a graph, per parity (the graph is captured on the second)
+  int eager_passes[2 + EXT_SLOTS] = {0, 0, 0, 0, 0, 0};   // passes enqueued without a graph, per parity (the graph is captured on the second)
   Plan() = default;
   Plan(const Plan&) = delete;
   Plan& operator=(const Plan&) = delete;
@@ -261,6 +266,10 @@ void free_plan(Plan* p) {
     dev_free(p->in_dev[i]); dev_free(p->out_dev[i]); dev_free(p->u8_dev[i]); dev_free(p->mask_dev[i]);
     dev_free(p->page_dev[i]); dev_free(p->src_dev[i]); dev_free(p->hor_dev[i]); dev_free(p->ver_dev[i]);
     ev_free(p->ev_h2d[i]); ev_free(p->ev_comp[i]); ev_free(p->ev_d2h[i]);
+  }
+  for (int i = 2; i < 2 + Plan::EXT_SLOTS; ++i) {   // bindings of caller-owned buffers: only the graphs are ours
+    if (p->graph[i]) { cudaGraphExecDestroy(p->graph[i]); p->graph[i] = nullptr; }
+    p->in_dev[i] = p->out_dev[i] = nullptr;
   }
   dev_free(p->arena); dev_free(p->scratch); dev_free(p->post_scratch);
   p->src_dev_bytes = 0;
@@ -2083,15 +2092,39 @@ int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, floa
     int rc = get_plan(e, cnt, h, w, &p);
     if (rc) return rc;
     e->cur = p;
-    CU(e, cudaMemcpyAsync(p->in_dev[0], in + (size_t)i0 * page_px, (size_t)cnt * page_px * sizeof(float),
-                          cudaMemcpyDeviceToDevice, st));
-    rc = enqueue_forward(e, p, 0, st);
+    const float* in_i = in + (size_t)i0 * page_px;
+    float* out_i = out ? out + (size_t)i0 * page_px * C : nullptr;
+    int slot = 0;
+    // The caller's buffers are bound in place when they can be (16-byte aligned, a float32 result is wanted): the first
+    // layers read `in`, the classifier writes `out`, no staging copies.  One graph per (in, out) pair.
+    if (out_i && !e->keep_all && ((reinterpret_cast<uintptr_t>(in_i) | reinterpret_cast<uintptr_t>(out_i)) & 15) == 0 &&
+        getenv("ARU_NO_INPLACE") == nullptr) {
+      int lru = 2;
+      for (int s2 = 2; s2 < 2 + Plan::EXT_SLOTS; ++s2) {
+        if (p->in_dev[s2] == in_i && p->out_dev[s2] == out_i) { slot = s2; break; }
+        if (p->ext_use[s2] < p->ext_use[lru]) lru = s2;
+      }
+      if (!slot) {
+        slot = lru;
+        if (p->graph[slot]) {
+          CU(e, cudaStreamSynchronize(st));   // the graph may still be running
+          cudaGraphExecDestroy(p->graph[slot]);
+          p->graph[slot] = nullptr;
+        }
+        p->in_dev[slot] = const_cast<float*>(in_i);
+        p->out_dev[slot] = out_i;
+        p->eager_passes[slot] = 0;
+      }
+      p->ext_use[slot] = ++p->ext_clock;
+    }
+    if (!slot)
+      CU(e, cudaMemcpyAsync(p->in_dev[0], in_i, (size_t)cnt * page_px * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    rc = enqueue_forward(e, p, slot, st);
     if (rc) return rc;
-    if (out)
-      CU(e, cudaMemcpyAsync(out + (size_t)i0 * page_px * C, p->out_dev[0], (size_t)cnt * page_px * C * sizeof(float),
-                            cudaMemcpyDeviceToDevice, st));
+    if (out && !slot)
+      CU(e, cudaMemcpyAsync(out_i, p->out_dev[0], (size_t)cnt * page_px * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (out_u8 || out_mask) {
-      cudaError_t err = launch_quantize(st, p->out_dev[0], out_u8 ? out_u8 + (size_t)i0 * page_px * C : nullptr,
+      cudaError_t err = launch_quantize(st, p->out_dev[slot], out_u8 ? out_u8 + (size_t)i0 * page_px * C : nullptr,
                                         out_mask ? out_mask + (size_t)i0 * page_px : nullptr, (long long)cnt * page_px, C, thr, -1);
       if (err != cudaSuccess) return fail(e, ARU_ECUDA, "quantize launch: %s", cudaGetErrorString(err));
     }

@@ -166,7 +166,10 @@ int aru_forward(aru_engine* e, const float* in, int n, int h, int w, float* out,
                 uint8_t* out_mask, float thr);
 
 /* Same, but `in` / `out*` are DEVICE pointers on the engine's device and the work is only enqueued on
- * `stream` (a cudaStream_t, NULL = the engine's own stream); n must not exceed the planned batch. */
+ * `stream` (a cudaStream_t, NULL = the engine's own stream); n must not exceed the planned batch.
+ * When `out` is given and `in` / `out` are 16-byte aligned the buffers are bound IN PLACE: the first layers read `in`,
+ * the classifier writes `out`, nothing is staged (one captured graph per (in, out) pair, four pairs kept per page
+ * shape); `in` is never written.  Otherwise the pages go through the plan's own staging buffers. */
 int aru_forward_device(aru_engine* e, const float* in, int n, int h, int w, float* out, uint8_t* out_u8,
                        uint8_t* out_mask, float thr, void* stream);
 

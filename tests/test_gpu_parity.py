@@ -269,6 +269,50 @@ def test_two_fresh_engines_give_identical_bits(built_lib, fuse):
         assert np.array_equal(outs[0], o)
 
 
+def test_device_resident_call_binds_caller_buffers_in_place(built_lib):
+    """aru_forward_device on caller-owned device buffers (torch tensors): the first layers read the caller's input and
+    the classifier writes the caller's output, no staging copies, one captured graph per (in, out) binding.  Same bits
+    as the host-buffer call; more bindings than slots (the least recently used one is recycled), repeated calls (eager
+    pass, then the graph), a misaligned buffer (falls back to the staging copies), uint8 / mask outputs, micro-batches."""
+    import torch
+    from aru_b200.engine import Engine, OPT_MICRO_BATCH
+    from aru_b200.synth import synth_pb, synth_page, page_to_net_input
+    n, h, w = 5, 96, 80
+    eng = Engine(synth_pb("separator"), device=0)
+    xs = np.stack([page_to_net_input(synth_page(h, w, s)) for s in range(n)]).astype(np.float32)
+    want, want_u8, want_mask = eng.forward(xs, want_u8=True, want_mask=True, threshold=0.05)
+    want, want_u8, want_mask = want.copy(), want_u8.copy(), want_mask.copy()
+    x_dev = torch.from_numpy(xs).cuda()
+    for mb in (0, 2):
+        eng.set_option(OPT_MICRO_BATCH, mb)
+        outs = [torch.zeros((n, h, w, 2), dtype=torch.float32, device="cuda") for _ in range(6)]   # 6 bindings, 4 slots
+        for rep in range(3):
+            for o in outs:
+                o.zero_()
+                eng.forward_device(x_dev.data_ptr(), n, h, w, out_ptr=o.data_ptr())
+                eng.sync()
+                assert np.array_equal(o.cpu().numpy(), want), (mb, rep)
+        # the input must be untouched, uint8 / mask outputs come from the bound output
+        assert np.array_equal(x_dev.cpu().numpy(), xs)
+        u8 = torch.zeros((n, h, w, 2), dtype=torch.uint8, device="cuda")
+        mask = torch.zeros((n, h, w), dtype=torch.uint8, device="cuda")
+        eng.forward_device(x_dev.data_ptr(), n, h, w, out_ptr=outs[0].data_ptr(), u8_ptr=u8.data_ptr(), mask_ptr=mask.data_ptr())
+        eng.sync()
+        assert np.array_equal(u8.cpu().numpy(), want_u8) and np.array_equal(mask.cpu().numpy(), want_mask)
+        # without a float32 result (staging path) and with a misaligned input (4 bytes off a 16-byte boundary)
+        u8.zero_()
+        eng.forward_device(x_dev.data_ptr(), n, h, w, u8_ptr=u8.data_ptr())
+        eng.sync()
+        assert np.array_equal(u8.cpu().numpy(), want_u8)
+        flat = torch.zeros(n * h * w + 1, dtype=torch.float32, device="cuda")
+        flat[1:] = x_dev.reshape(-1)
+        outs[1].zero_()
+        eng.forward_device(flat.data_ptr() + 4, n, h, w, out_ptr=outs[1].data_ptr())
+        eng.sync()
+        assert np.array_equal(outs[1].cpu().numpy(), want)
+    eng.close()
+
+
 def test_batch_and_micro_batch_consistency(engines):
     """forward([p0..p4]) == forward(pi) per page, bit-exact, for any micro-batch split (pages are independent)."""
     from aru_b200.engine import OPT_CONV_PATH, OPT_MICRO_BATCH
