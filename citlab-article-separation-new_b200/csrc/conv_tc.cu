@@ -602,56 +602,77 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
       } else {
         // transposed convolution: this lane's *input* pixel (j, i) = (rin-1, col-1), including the frame row /
         // column j = H, i = W; it owns the four outputs full[2j+py, 2i+px], cropped by (offy, offx)
-        // (layers.py:342-367).  Deliberately compact (rolled loops).
+        // (layers.py:342-367).  The (tile, channel chunk) steps of a pass are software-pipelined over two register
+        // buffers: the TMEM reads of step i + 1 (four output-parity classes) are in flight while step i is converted and
+        // stored - the read-out was a chain of exposed TMEM latencies (ncu: the first FADD / F2FP after every
+        // tcgen05.wait::ld held 25 % of the kernel's samples).
+        const int n_it = T * a.cls_chunks;
         for (int pi = wg; pi < n_pass; pi += 2) {
           mbar_wait(s_tfull + 8 * stage, stage_par, a.err_flag, 4);
           __syncwarp();
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * T * a.npad);
           int c2 = col, r2 = rin, g2 = pg;
-#pragma unroll 1
-          for (int t = 0; t < T; ++t) {
+          bool v[4];
+          long long po[4];
+          auto tile_coords = [&]() {   // validity and output positions of the four classes of the current tile
             const bool in_dom = ((unsigned)g2 < (unsigned)a.N) && (c2 >= 1) && (c2 <= a.W + 1) && (r2 >= 1) && (r2 <= a.H + 1);
             const int oy0 = 2 * (r2 - 1) - a.offy, ox0 = 2 * (c2 - 1) - a.offx;
             const long long po0 = (long long)a.lead_o + ((long long)g2 * a.Hpo + oy0 + 1) * a.Wpo + ox0 + 1;
-            // the four output-parity classes of one channel chunk are read from TMEM together (one wait per chunk
-            // instead of one per class: the read-out was a chain of exposed TMEM latencies)
-            bool v[4];
-            long long po[4];
 #pragma unroll
             for (int cls = 0; cls < 4; ++cls) {
               const int oy = oy0 + (cls >> 1), ox = ox0 + (cls & 1);
               v[cls] = in_dom && (oy >= 0) && (oy < a.Ho) && (ox >= 0) && (ox < a.Wo);
               po[cls] = po0 + (long long)(cls >> 1) * a.Wpo + (cls & 1);
             }
-#pragma unroll 1
-            for (int c = 0; c < a.cls_chunks; ++c) {
-              uint32_t v8[4][8];
+          };
+          int t_ld = 0, c_ld = 0;   // the step whose TMEM reads are issued next
+          auto issue = [&](uint32_t (&dst)[4][8]) {
 #pragma unroll
-              for (int cls = 0; cls < 4; ++cls)
-                tmem_ld8(taddr + (uint32_t)(t * a.npad + (cls * a.cls_chunks + c) * 8), v8[cls]);
-              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 8 + 4);
-              tmem_ld_wait();
-              if (t == T - 1 && c == a.cls_chunks - 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
-              }
+            for (int cls = 0; cls < 4; ++cls)
+              tmem_ld8(taddr + (uint32_t)(t_ld * a.npad + (cls * a.cls_chunks + c_ld) * 8), dst[cls]);
+            if (++c_ld == a.cls_chunks) { c_ld = 0; ++t_ld; }
+          };
+          int c_cur = 0;
+          auto finish = [&](const uint32_t (&src)[4][8]) {
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c_cur * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c_cur * 8 + 4);
 #pragma unroll
-              for (int cls = 0; cls < 4; ++cls) {
-                if (v[cls]) {
-                  float acc[8];
-                  acc[0] = __uint_as_float(v8[cls][0]) + b0.x; acc[1] = __uint_as_float(v8[cls][1]) + b0.y;
-                  acc[2] = __uint_as_float(v8[cls][2]) + b0.z; acc[3] = __uint_as_float(v8[cls][3]) + b0.w;
-                  acc[4] = __uint_as_float(v8[cls][4]) + b1.x; acc[5] = __uint_as_float(v8[cls][5]) + b1.y;
-                  acc[6] = __uint_as_float(v8[cls][6]) + b1.z; acc[7] = __uint_as_float(v8[cls][7]) + b1.w;
-                  *reinterpret_cast<uint4*>(a.out + ((long long)c * a.out_plane + po[cls]) * 8) =
-                      a.act == 1 ? pack8_fin<true>(acc, true) : pack8_fin<false>(acc, true);
-                }
+            for (int cls = 0; cls < 4; ++cls) {
+              if (v[cls]) {
+                float acc[8];
+                acc[0] = __uint_as_float(src[cls][0]) + b0.x; acc[1] = __uint_as_float(src[cls][1]) + b0.y;
+                acc[2] = __uint_as_float(src[cls][2]) + b0.z; acc[3] = __uint_as_float(src[cls][3]) + b0.w;
+                acc[4] = __uint_as_float(src[cls][4]) + b1.x; acc[5] = __uint_as_float(src[cls][5]) + b1.y;
+                acc[6] = __uint_as_float(src[cls][6]) + b1.z; acc[7] = __uint_as_float(src[cls][7]) + b1.w;
+                *reinterpret_cast<uint4*>(a.out + ((long long)c_cur * a.out_plane + po[cls]) * 8) =
+                    a.act == 1 ? pack8_fin<true>(acc, true) : pack8_fin<false>(acc, true);
               }
             }
-            walk_adv(c2, r2, g2, a.dc128, a.dr128, a.Wp, a.Hp);
+            if (++c_cur == a.cls_chunks) {   // next tile
+              c_cur = 0;
+              walk_adv(c2, r2, g2, a.dc128, a.dr128, a.Wp, a.Hp);
+              tile_coords();
+            }
+          };
+          auto release = [&]() {   // every TMEM read of this stage has completed: hand the accumulators back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_tempty + 8 * stage);
+          };
+          uint32_t va[4][8], vb[4][8];
+          tile_coords();
+          issue(va);
+#pragma unroll 1
+          for (int it = 0; it < n_it; it += 2) {
+            tmem_ld_wait();
+            if (it + 1 < n_it) issue(vb); else release();
+            finish(va);
+            if (it + 1 < n_it) {
+              tmem_ld_wait();
+              if (it + 2 < n_it) issue(va); else release();
+              finish(vb);
+            }
           }
           walk_adv(col, rin, pg, a.dcS, a.drS, a.Wp, a.Hp);
           stage += 2;

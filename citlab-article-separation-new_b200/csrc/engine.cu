@@ -22,6 +22,7 @@
 #include <memory>
 #include <tuple>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/aru_b200.h"
@@ -1434,6 +1435,33 @@ int aru_device_count(void) {
 const char* aru_last_error(const aru_engine* e) { return e ? e->error.c_str() : g_error.c_str(); }
 
 const char* aru_last_warning(const aru_engine* e) { return e ? e->warning.c_str() : ""; }
+
+// float64 page -> float32 staging buffer on a few host threads (numpy's single-threaded astype of a 2.5 Mpx page costs
+// more than the page's whole forward pass)
+int aru_f64_to_f32(const double* src, float* dst, long long count, int threads) {
+  if (count < 0 || (count > 0 && (!src || !dst))) return ARU_EINVAL;
+  cpu_set_t set;
+  int avail = 1;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) avail = std::max(1, CPU_COUNT(&set));
+  int nt = threads > 0 ? threads : std::min(avail, 16);
+  nt = (int)std::max<long long>(1, std::min<long long>(nt, count / 65536));
+  auto work = [=](int t) {
+    const long long b = count * t / nt, e2 = count * (t + 1) / nt;
+    for (long long i = b; i < e2; ++i) dst[i] = (float)src[i];
+  };
+  if (nt == 1) { work(0); return ARU_OK; }
+  std::vector<std::thread> pool;
+  pool.reserve(nt - 1);
+  try {
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+  } catch (...) {   // no more threads to be had: the caller's thread does the rest
+    const int started = (int)pool.size();
+    for (int t = started + 1; t < nt; ++t) work(t);
+  }
+  work(0);
+  for (auto& th : pool) th.join();
+  return ARU_OK;
+}
 
 // One process per GPU: the host buffers a rank page-locks must live on the NUMA node its GPU hangs off, or the
 // host<->device copies of the ranks on the other socket cross the inter-socket link and the 8-GPU end-to-end rate

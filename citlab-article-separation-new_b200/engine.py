@@ -33,6 +33,7 @@ EXPORTS = [
     "aru_separator_pages", "aru_separator_post", "aru_open_rect", "aru_pages_to_input", "aru_heading_pages",
     "aru_box_sums", "aru_cc_filter", "aru_scaled_size", "aru_scale_pages", "aru_separator_images", "aru_heading_images",
     "aru_bind_host_to_device", "aru_swt_distance", "aru_last_ticket", "aru_wait", "aru_last_warning",
+    "aru_f64_to_f32",
 ]
 
 _lib = None
@@ -93,6 +94,7 @@ def load_library() -> ctypes.CDLL:
         lib.aru_host_free.argtypes = [vp]
         lib.aru_host_free.restype = None
         lib.aru_bind_host_to_device.argtypes = [i32, ctypes.POINTER(i32)]
+        lib.aru_f64_to_f32.argtypes = [vp, vp, ctypes.c_longlong, i32]
         lib.aru_swt_distance.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
         lib.aru_last_ticket.argtypes = [vp]
         lib.aru_last_ticket.restype = ctypes.c_uint64
@@ -252,7 +254,10 @@ class Engine:
         n, h, w = x.shape
         if not (x.dtype == np.float32 and x.flags.c_contiguous):
             xin = pinned_empty((n, h, w), np.float32)
-            np.copyto(xin, x, casting="unsafe")
+            if x.dtype == np.float64 and x.flags.c_contiguous:   # what get_net_output's callers pass (helper.py:31)
+                self._check(self.lib.aru_f64_to_f32(ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(xin.ctypes.data), x.size, 0))
+            else:
+                np.copyto(xin, x, casting="unsafe")
             x = xin
         if self._collect:
             self._staged.append(x)

@@ -144,6 +144,11 @@ int aru_device_count(void);
  * *numa_node receives the node (-1: unknown); ARU_EUNSUP when the topology cannot be read or applied (nothing changed). */
 int aru_bind_host_to_device(int device, int* numa_node);
 
+/* get_net_output receives a float64 page (image / 255.0, net_post_processing_helper.py:31,56-59): dst[i] = (float)src[i]
+ * for `count` values on up to `threads` host threads (0 = as many as the process may use, at most 16) - the one CPU pass
+ * over the page before it is copied up; dst is normally a page-locked buffer from aru_host_alloc. */
+int aru_f64_to_f32(const double* src, float* dst, long long count, int threads);
+
 /* load_graph: build an engine for `g` on CUDA device `device`. Fails with ARU_ENODEV without a GPU. */
 int aru_create(const aru_graph_desc* g, int device, aru_engine** out);
 void aru_destroy(aru_engine* e);

@@ -63,3 +63,21 @@ def test_missing_library_is_a_loud_error(monkeypatch):
     monkeypatch.setattr(engine, "LIB_PATH", "/nonexistent/libaru_b200.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         engine.load_library()
+
+
+def test_f64_to_f32_staging_conversion_equals_numpy(built_lib):
+    """Host helper (no GPU involved): the float64 page get_net_output receives -> the float32 staging buffer, on several
+    threads; the same bits as numpy's astype (round to nearest even, overflow to inf, NaN kept)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for count, threads in ((0, 0), (1, 0), (65535, 0), (1024 * 768, 0), (1856 * 1344 + 3, 5), (400000, 1), (3000000, 64)):
+        src = rng.random(count) if count else np.zeros(0)
+        if count > 10:
+            src[:6] = [1e39, -1e39, np.nan, 1e-46, 0.1, 1.0 + 2.0 ** -24]
+        dst = np.full(count, -7.0, dtype=np.float32)
+        rc = built_lib.aru_f64_to_f32(ctypes.c_void_p(src.ctypes.data), ctypes.c_void_p(dst.ctypes.data), count, threads)
+        assert rc == 0
+        with np.errstate(over="ignore"):
+            want = src.astype(np.float32)
+        assert np.array_equal(dst, want, equal_nan=True), (count, threads)
+    assert built_lib.aru_f64_to_f32(None, None, 5, 0) != 0
