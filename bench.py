@@ -267,7 +267,14 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
             traffic = json.load(fh).get(key, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    dominant = {"kernel": key, "bound": bound, "achieved": round(achieved, 2), "peak": peak,
+    extra = {}
+    if key.startswith(("block_mma", "combine_head")):
+        # these launches keep their intermediates in shared memory and run on the warp-level tensor path (mma.sync); its
+        # measured dense peak on this part is 557 TFLOP/s (tools/hmma_rate_bench.cu, profiles/r02l_hmma_rate.txt), a
+        # third of the tcgen05 / cuBLAS figure in MEASURED_PEAKS.json that `peak` must quote
+        extra = {"pipe": "mma.sync m16n8k16 (operands in registers; DESIGN.md 4.6)", "mma_sync_peak_tflops": 557.0,
+                 "frac_of_mma_sync_peak": round(f / t / 557.0e12, 4)}
+    dominant = {"kernel": key, "bound": bound, **extra, "achieved": round(achieved, 2), "peak": peak,
                 "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "launches_per_pass": g["launches"], "us_per_launch": round(t * 1e6, 2),
                 "algorithmic_bytes_per_launch": int(b), "flops_per_launch": int(f),

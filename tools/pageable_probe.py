@@ -43,4 +43,11 @@ print(f"  pinned_empty of the result                {timed(lambda: pinned_empty(
 print(f"  device-resident pass (1 page)             {timed(lambda: (eng.forward_device(x_dev.data_ptr(), 1, h, w, out_ptr=y_dev.data_ptr()), eng.sync())):7.3f} ms")
 print(f"  forward(pinned float32 page)              {timed(lambda: eng.forward(page32)):7.3f} ms")
 print(f"  forward(pinned float32 page), uint8 ch 0  {timed(lambda: eng.forward(page32, want_u8=True, want_prob=False, u8_channels=1)):7.3f} ms")
+def by_hand():
+    xin = pinned_empty((1, h, w), np.float32)
+    eng.lib.aru_f64_to_f32(ctypes.c_void_p(page64.ctypes.data), ctypes.c_void_p(xin.ctypes.data), page64.size, 0)
+    return eng.forward(xin)
+
+
+print(f"  pinned_empty + aru_f64_to_f32 + forward   {timed(by_hand):7.3f} ms")
 print(f"  forward(pageable float64 page)            {timed(lambda: eng.forward(page64)):7.3f} ms")
