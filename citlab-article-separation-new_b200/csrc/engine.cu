@@ -714,8 +714,19 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     // flip.  ARU_AUTOTUNE=1 times both on this plan's geometry and keeps the faster (benchmarking only).
     const char* env = getenv("ARU_AUTOTUNE");
     const bool tune = env && env[0] == '1';
+    // The rule is a function of the op's signature only (never of the batch or the page size: a page must give the same
+    // bits alone and inside a batch).  Row-banded for C_out <= 16 - except the two 16-channel shapes whose extra stream
+    // loads the banded kernel's store warps: a residual operand, or a pre-activation export behind 8 input channels;
+    // those run position-major (measured at 32 x 1856x1344, profiles/r02q_profile_autotune.txt: 0.41 -> 0.33 ms,
+    // 0.37 -> 0.30 ms, 0.48 -> 0.33 + 0.12 ms for the separate pool; -0.3 ms per pass).
+    auto fixed_rule = [&](int i) -> char {
+      const aru_op& op = e->ops[i];
+      if (p->band[i].cop > 16) return 0;
+      if (p->band[i].cop == 16 && (op.res.buf >= 0 || (op.out_pre.buf >= 0 && op.in.ch <= 8))) return 0;
+      return 1;
+    };
     for (int i = 0; i < no && !tune; ++i)
-      if (p->band[i].ok && !p->tc[i].empty()) p->use_band[i] = p->band[i].cop <= 16 ? 1 : 0;
+      if (p->band[i].ok && !p->tc[i].empty()) p->use_band[i] = fixed_rule(i);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     for (int i = 0; i < no && tune; ++i) {
       if (!p->band[i].ok || p->tc[i].empty()) continue;
@@ -726,7 +737,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
         // small launches are timing noise: fixed rule (keeps small-page results identical from process to process)
         const Geo& og = p->bufs[e->ops[i].in.buf].geo;
         if ((long long)og.N * og.H * og.W < (1LL << 21)) {
-          p->use_band[i] = p->band[i].cop <= 16 ? 1 : 0;
+          p->use_band[i] = fixed_rule(i);
           e->tune_cache[key] = p->use_band[i];
           continue;
         }
