@@ -186,7 +186,7 @@ def class_rooflines(eng, n, h, w, peaks, iters=3):
             ih, iw = hw(op.inp.buf)
             f0, b0 = pending.pop(op.inp.buf, (0.0, None))
             if b0 is None:              # first op of the chain: its input is what the launch reads
-                b0 = n * ih * iw * op.inp.ch * 2
+                b0 = n * ih * iw * op.inp.ch * (4 if op.inp.ch == 1 else 2)
             pending[op.out.buf] = (f0 + 2.0 * n * oh * ow * op.ksize * op.ksize * op.inp.ch * op.out.ch,
                                    b0 + (n * oh * ow * op.out.ch * 2 if op.out_pre.buf >= 0 and not kernel_of_chain_is_block(op, prog, prof) else 0))
             continue
