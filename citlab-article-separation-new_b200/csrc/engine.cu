@@ -90,6 +90,14 @@ struct Plan {
   std::vector<BlockMmaPlan> blk;
   std::vector<char> blk_from_x0;        // per op c: conv1 runs as its own launch and the block starts from its pre-activation
   std::vector<char> pre_only;           // per conv1 op of such a block: only the pre-activation is stored
+  // Independent branches of a pass (the smaller scales of the pyramid, the attention CNNs) run on their own streams:
+  // op_stream[i] = 0 (the caller's stream) or 1 + aux stream; op_event[i] is recorded after op i when an op of another
+  // stream reads what it wrote; op_waits[i] = the ops whose events op i waits for.
+  bool branched = false;
+  std::vector<int> op_stream;
+  std::vector<cudaEvent_t> op_event;
+  std::vector<std::vector<int>> op_waits;
+  cudaEvent_t ev_start = nullptr, ev_end[3] = {nullptr, nullptr, nullptr};
   std::vector<int> head_combine;        // per classifier conv op: the COMBINE op its launch also performs (-1: none)
   act_t* scratch = nullptr;             // partial sums of split-K launches
   size_t scratch_bytes = 0;
@@ -136,11 +144,13 @@ struct aru_engine {
   std::vector<OpWeights> opw;
   std::vector<int> kind;  // per buffer
   int input_buf = -1, output_buf = -1, n_class = 0;
-  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0, fuse_blocks = 1, u8_channels = 0, async_calls = 0;
+  int conv_path = 0, use_graph = 1, micro_batch = 0, keep_all = 0, fuse_pairs = 0, fuse_blocks = 1, u8_channels = 0, async_calls = 0, branch_streams = 1;
   // ARU_OPT_ASYNC: completion events of the host-buffer calls in flight (ticket t lives in tickets[t % 8])
   cudaEvent_t tickets[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t last_ticket = 0;
   cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  static constexpr int N_AUX = 3;
+  cudaStream_t s_aux[N_AUX] = {nullptr, nullptr, nullptr};   // branch streams of a pass (low priority), see plan_branches
   int* err_flag = nullptr;
   float* zero_bias = nullptr;
   std::vector<std::unique_ptr<Plan>> plans;
@@ -275,6 +285,9 @@ void free_plan(Plan* p) {
     if (p->graph[i]) { cudaGraphExecDestroy(p->graph[i]); p->graph[i] = nullptr; }
     p->in_dev[i] = p->out_dev[i] = nullptr;
   }
+  for (cudaEvent_t& ev : p->op_event) ev_free(ev);
+  ev_free(p->ev_start);
+  for (cudaEvent_t& ev : p->ev_end) ev_free(ev);
   dev_free(p->arena); dev_free(p->scratch); dev_free(p->post_scratch);
   p->src_dev_bytes = 0;
 }
@@ -486,10 +499,112 @@ int run_op(aru_engine* e, Plan* p, int oi, int parity, cudaStream_t st) {
 }
 
 int run_all(aru_engine* e, Plan* p, int parity, cudaStream_t st) {
-  for (int i = 0; i < (int)e->ops.size(); ++i) {
-    int rc = run_op(e, p, i, parity, st);
-    if (rc) return rc;
+  const int no = (int)e->ops.size();
+  if (!p->branched) {
+    for (int i = 0; i < no; ++i) {
+      int rc = run_op(e, p, i, parity, st);
+      if (rc) return rc;
+    }
+    return ARU_OK;
   }
+  // fork: the branch streams start after everything `st` holds so far (the previous pass included) ...
+  CU(e, cudaEventRecord(p->ev_start, st));
+  for (int a = 0; a < aru_engine::N_AUX; ++a) CU(e, cudaStreamWaitEvent(e->s_aux[a], p->ev_start, 0));
+  for (int i = 0; i < no; ++i) {
+    cudaStream_t s = p->op_stream[i] ? e->s_aux[p->op_stream[i] - 1] : st;
+    for (int w : p->op_waits[i]) CU(e, cudaStreamWaitEvent(s, p->op_event[w], 0));
+    int rc = run_op(e, p, i, parity, s);
+    if (rc) return rc;
+    if (p->op_event[i]) CU(e, cudaEventRecord(p->op_event[i], s));
+  }
+  // ... and join: the pass is complete on `st` when every branch is
+  for (int a = 0; a < aru_engine::N_AUX; ++a) {
+    CU(e, cudaEventRecord(p->ev_end[a], e->s_aux[a]));
+    CU(e, cudaStreamWaitEvent(st, p->ev_end[a], 0));
+  }
+  return ARU_OK;
+}
+
+// Stream assignment of a pass.  The pyramid scales of the shared-weight RU-Net and the attention CNNs are independent
+// until the attention combine (ARU_v1.py:105-153); run one after the other, the small scales spend most of their time in
+// launch prologues and tails (a sixteenth of the pixels takes 1.25 of 15.65 ms).  On streams of their own their kernels
+// fill the SMs the full-resolution chain leaves idle.  Scale k of the detection branch -> stream k mod 3 (scale 0 = the
+// caller's stream), ops that only feed attention operands -> the last branch stream, everything else -> the caller's.
+// Dependencies across streams become events.  Buffers are written once per pass (no aliasing), so there are no other
+// hazards; the split-K scratch is only used on the caller's stream (checked).
+int plan_branches(aru_engine* e, Plan* p) {
+  const int no = (int)e->ops.size(), nb = (int)e->buffers.size();
+  p->op_stream.assign(no, 0);
+  p->op_event.assign(no, nullptr);
+  p->op_waits.assign(no, {});
+  p->branched = false;
+  const char* env = getenv("ARU_BRANCH_STREAMS");
+  if (!(env ? env[0] == '1' : e->branch_streams != 0) || e->keep_all || e->conv_path != 0) return ARU_OK;
+  int c = -1;
+  for (int i = 0; i < no && c < 0; ++i)
+    if (e->ops[i].kind == ARU_OP_COMBINE) c = i;
+  if (c < 0 || e->ops[c].n_scales < 2) return ARU_OK;
+  auto reads = [&](const aru_op& op, std::vector<int>& out) {
+    out.clear();
+    if (op.kind == ARU_OP_COMBINE) {
+      for (int k = 0; k < op.n_scales; ++k) { out.push_back(op.att[k].buf); out.push_back(op.det[k].buf); }
+    } else {
+      if (op.in.buf >= 0) out.push_back(op.in.buf);
+      if (op.res.buf >= 0) out.push_back(op.res.buf);
+    }
+  };
+  // producers of every op's operands (program order = a topological order)
+  std::vector<int> writer(nb, -1), rd;
+  std::vector<std::vector<int>> deps(no);
+  for (int i = 0; i < no; ++i) {
+    reads(e->ops[i], rd);
+    for (int b : rd)
+      if (writer[b] >= 0) deps[i].push_back(writer[b]);
+    if (e->ops[i].out.buf >= 0) writer[e->ops[i].out.buf] = i;
+    if (e->ops[i].out_pre.buf >= 0) writer[e->ops[i].out_pre.buf] = i;
+  }
+  // ancestors of the combine's operands: bit k = feeds det[k], bit 16 = feeds an attention operand
+  std::vector<unsigned> feeds(no, 0u);
+  {
+    std::vector<int> w2(nb, -1);
+    for (int i = 0; i < c; ++i) {
+      if (e->ops[i].out.buf >= 0) w2[e->ops[i].out.buf] = i;
+      if (e->ops[i].out_pre.buf >= 0) w2[e->ops[i].out_pre.buf] = i;
+    }
+    const aru_op& oc = e->ops[c];
+    for (int k = 0; k < oc.n_scales; ++k) {
+      if (w2[oc.det[k].buf] >= 0) feeds[w2[oc.det[k].buf]] |= 1u << std::min(k, 15);
+      if (w2[oc.att[k].buf] >= 0) feeds[w2[oc.att[k].buf]] |= 1u << 16;
+    }
+    for (int i = c - 1; i >= 0; --i)
+      for (int d : deps[i]) feeds[d] |= feeds[i];
+  }
+  bool any = false;
+  for (int i = 0; i < c; ++i) {
+    const unsigned det = feeds[i] & 0xffffu;
+    int s = 0;
+    if (det) { int k = 0; while (!((det >> k) & 1u)) ++k; s = k % 3; }      // the first scale it feeds
+    else if (feeds[i] & (1u << 16)) s = aru_engine::N_AUX;                   // attention only
+    p->op_stream[i] = s;
+    any = any || s != 0;
+  }
+  if (!any) return ARU_OK;
+  for (int i = 0; i < no; ++i)
+    if (p->tc[i].size() > 1) p->op_stream[i] = 0;   // split-K launches share one scratch buffer: the caller's stream only
+  // events for the edges that cross streams; an op without a launch of its own must not be such a producer unless the
+  // launch that performs its work comes earlier on the same stream (fused pools), which stream order already covers
+  for (int i = 0; i < no; ++i)
+    for (int d : deps[i]) {
+      if (p->op_stream[d] == p->op_stream[i]) continue;
+      if (p->skip[d]) { p->op_stream.assign(no, 0); p->op_waits.assign(no, {}); return ARU_OK; }   // fused away: stay serial
+      if (std::find(p->op_waits[i].begin(), p->op_waits[i].end(), d) == p->op_waits[i].end()) p->op_waits[i].push_back(d);
+    }
+  for (int i = 0; i < no; ++i)
+    for (int d : p->op_waits[i])
+      if (!p->op_event[d]) CU(e, cudaEventCreateWithFlags(&p->op_event[d], cudaEventDisableTiming));
+  CU(e, cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+  for (cudaEvent_t& ev : p->ev_end) CU(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  p->branched = true;
   return ARU_OK;
 }
 
@@ -949,6 +1064,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     }
   }
   const double t_kernels = ms_since(t_begin);
+  if ((rc = plan_branches(e, p.get()))) { free_plan(p.get()); return rc; }
   // one eager pass (sets function attributes, validates every launch), then capture
   rc = run_all(e, p.get(), 0, e->s_comp);
   if (rc) { free_plan(p.get()); return rc; }
@@ -1655,6 +1771,12 @@ int aru_create(const aru_graph_desc* g, int device, aru_engine** out) {
   err = cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking);
+  {
+    int prio_lo = 0, prio_hi = 0;   // branch streams yield to the full-resolution chain on the caller's stream
+    if (err == cudaSuccess) err = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (int a2 = 0; a2 < aru_engine::N_AUX && err == cudaSuccess; ++a2)
+      err = cudaStreamCreateWithPriority(&e->s_aux[a2], cudaStreamNonBlocking, prio_lo);
+  }
   if (err == cudaSuccess) err = cudaMalloc((void**)&e->err_flag, sizeof(int));
   if (err == cudaSuccess) err = cudaMemset(e->err_flag, 0, sizeof(int));
   if (err == cudaSuccess) err = cudaMalloc((void**)&e->zero_bias, 256 * sizeof(float));
@@ -1695,6 +1817,7 @@ void aru_destroy(aru_engine* e) {
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
   if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
   if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+  for (cudaStream_t q : e->s_aux) if (q) cudaStreamDestroy(q);
   delete e;
 }
 
@@ -1740,6 +1863,15 @@ int aru_set_option(aru_engine* e, int option, int64_t value) {
         e->cur = nullptr;
       }
       e->fuse_blocks = value ? 1 : 0;
+      return ARU_OK;
+    case ARU_OPT_BRANCH_STREAMS:
+      if (e->branch_streams != (value ? 1 : 0)) {
+        cudaSetDevice(e->device);
+        cudaDeviceSynchronize();
+        e->plans.clear();
+        e->cur = nullptr;
+      }
+      e->branch_streams = value ? 1 : 0;
       return ARU_OK;
     case ARU_OPT_ASYNC:   // calls already in flight stay in flight; any later synchronous call or aru_sync completes them
       e->async_calls = value ? 1 : 0;

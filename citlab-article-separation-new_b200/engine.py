@@ -24,6 +24,7 @@ LIB_PATH = os.environ.get("ARU_B200_LIB") or os.path.join(_PKG_DIR, "libaru_b200
 ARU_OK, ARU_EINVAL, ARU_ECUDA, ARU_ENOMEM, ARU_EUNSUP, ARU_ENODEV = 0, 1, 2, 3, 4, 5
 OPT_CONV_PATH, OPT_USE_GRAPH, OPT_MICRO_BATCH, OPT_KEEP_ALL, OPT_FUSE_PAIRS, OPT_U8_CHANNELS, OPT_ASYNC = 1, 2, 3, 4, 5, 6, 7
 OPT_FUSE_BLOCKS = 8
+OPT_BRANCH_STREAMS = 9
 
 # every symbol include/aru_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = [

@@ -134,6 +134,10 @@ typedef struct aru_engine aru_engine;
                                  [-> max-pool], ARU_v1.py:212-227, 266-281) runs as ONE launch on the warp-level tensor
                                  path with its intermediates in shared memory (block_mma.cu); 0 = one launch per layer.
                                  ARU_FUSE_BLOCKS=0 / 1 in the environment overrides the option. */
+#define ARU_OPT_BRANCH_STREAMS 9 /* 1 (default) = the independent branches of a pass (the smaller scales of the pyramid, the
+                                    attention CNNs) are enqueued on the engine's own low-priority streams and joined before
+                                    the attention combine, inside the captured graph as well; 0 = one stream.  Same bits
+                                    either way.  ARU_BRANCH_STREAMS=0 / 1 in the environment overrides the option. */
 
 int aru_abi_version(void);
 int aru_device_count(void);

@@ -269,6 +269,38 @@ def test_two_fresh_engines_give_identical_bits(built_lib, fuse):
         assert np.array_equal(outs[0], o)
 
 
+@pytest.mark.parametrize("net,n,h,w", [("separator", 3, 150, 213), ("aru_s6a5", 2, 129, 97), ("heading", 1, 257, 130),
+                                        ("tiny", 2, 9, 200), ("ru", 1, 64, 48)])
+def test_branch_streams_give_the_same_bits(built_lib, net, n, h, w):
+    """ARU_OPT_BRANCH_STREAMS: the pyramid scales and the attention CNNs of a pass on streams of their own (events on the
+    edges that cross streams, fork / join inside the captured graph) against everything on one stream: the same launches,
+    so the same bits - eagerly (first pass), from the captured graph (later passes), through the host-buffer pipeline with
+    micro-batches and through the device-resident call."""
+    import torch
+    from aru_b200.engine import Engine, OPT_BRANCH_STREAMS, OPT_MICRO_BATCH
+    from aru_b200.synth import synth_pb, synth_page, page_to_net_input
+    x = np.stack([page_to_net_input(synth_page(h, w, seed=17 * h + w + i)) for i in range(n)]).astype(np.float32)
+    outs = {}
+    for branch in (1, 0):
+        eng = Engine(synth_pb(net), device=0)
+        eng.set_option(OPT_BRANCH_STREAMS, branch)
+        runs = [eng.forward(x).copy() for _ in range(4)]          # eager pass, capture, two replays
+        eng.set_option(OPT_MICRO_BATCH, 2)
+        runs.append(eng.forward(x).copy())
+        eng.set_option(OPT_MICRO_BATCH, 0)
+        x_dev = torch.from_numpy(x).cuda()
+        y_dev = torch.zeros((n, h, w, eng.n_class), dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            eng.forward_device(x_dev.data_ptr(), n, h, w, out_ptr=y_dev.data_ptr())
+        eng.sync()
+        runs.append(y_dev.cpu().numpy())
+        for r in runs[1:]:
+            assert np.array_equal(runs[0], r), (net, branch)
+        outs[branch] = runs[0]
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_device_resident_call_binds_caller_buffers_in_place(built_lib):
     """aru_forward_device on caller-owned device buffers (torch tensors): the first layers read the caller's input and
     the classifier writes the caller's output, no staging copies, one captured graph per (in, out) binding.  Same bits
