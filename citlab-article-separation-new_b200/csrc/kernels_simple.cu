@@ -345,6 +345,95 @@ __global__ void __launch_bounds__(128) k_conv_stem4_pool_mma(const float* __rest
   }
 }
 
+// The 3x3 stem of a fused residual block (block_mma.cu starts from the stem's PRE-ACTIVATION): 1 -> 8 channels, only the
+// un-activated result is stored.  Same scheme as k_conv_stem4_pool_mma - the 3x3 SAME window (one row / column before,
+// one after) is the 4x4 window of that kernel with a zero fourth row and column, so the tile, its two copies and the
+// fragment addressing are identical and the 9 taps are one K = 16 step of mma.sync.m16n8k16: 1 HMMA per 16 pixels
+// instead of 72 FFMA per pixel (the CUDA-core kernel ran at 0.64 of the HBM roofline, FMA bound).
+__global__ void __launch_bounds__(128) k_conv_stem3_pre_mma(const float* __restrict__ in, act_t* __restrict__ out,
+                                                            act_t* __restrict__ out_pre, const float* __restrict__ w_dev,
+                                                            const float* __restrict__ bias_dev, Geo g, int act) {
+  // out (may be null): the activated result; out_pre (may be null): the un-activated one
+  // w_dev: filter [9 taps][16] (float32, device memory), bias_dev [16]
+  __shared__ __align__(16) act_t tile_mem[2 * SM_COPY];
+  auto tile = [&](int copy, int r, int c) -> act_t& { return tile_mem[copy * SM_COPY + r * SM_STRIDE + c]; };
+  const int n = blockIdx.z, y0 = blockIdx.y * STEM_ROWS, x0 = blockIdx.x * SM_TILE_W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const float* img = in + (long long)n * g.H * g.W;
+  {   // tile[.][r][c] = pixel (y0 + r - 1, x0 + c - 1); copy 1 holds element c at index c + 1
+    float v[SM_ROWS];
+    const int gx = x0 + tid - 1;
+    const bool okx = (unsigned)gx < (unsigned)g.W;
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) {
+      const int gy = y0 + r - 1;
+      v[r] = (okx && (unsigned)gy < (unsigned)g.H) ? __ldg(img + (long long)gy * g.W + gx) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < SM_ROWS; ++r) {
+      const act_t h = f_to_act(v[r]);
+      tile(0, r, tid) = h;
+      tile(1, r, tid + 1) = h;
+    }
+    if (tid < 3 * SM_ROWS) {   // the three extra columns 128..130
+      const int r = tid / 3, c = SM_TILE_W + tid % 3;
+      const int gy = y0 + r - 1, gx2 = x0 + c - 1;
+      const float u = ((unsigned)gy < (unsigned)g.H && (unsigned)gx2 < (unsigned)g.W) ? __ldg(img + (long long)gy * g.W + gx2) : 0.f;
+      const act_t h = f_to_act(u);
+      tile(0, r, c) = h;
+      tile(1, r, c + 1) = h;
+    }
+  }
+  // filter fragments over the 4 x 4 window index k = 4 ky + kx (zero for ky = 3 or kx = 3):
+  // b0 = taps k = 2t, 2t + 1, b1 = taps k + 8 of channel g
+  auto tap = [&](int k) {
+    const int ky = k >> 2, kx = k & 3;
+    return (ky < 3 && kx < 3) ? __ldg(w_dev + (ky * 3 + kx) * 16 + gq) : 0.f;
+  };
+  uint32_t bw[2];
+  bw[0] = pack2(tap(2 * t), tap(2 * t + 1));
+  bw[1] = pack2(tap(2 * t + 8), tap(2 * t + 9));
+  float bias[2] = {__ldg(bias_dev + 2 * t), __ldg(bias_dev + 2 * t + 1)};
+  __syncthreads();
+  if (y0 >= g.H) return;
+  const int ky0 = t >> 1, kx0 = 2 * (t & 1);
+  const int copy = gq & 1;
+  const int pl0 = warp * 32 + gq;
+  uint32_t ta = (uint32_t)__cvta_generic_to_shared(&tile(copy, ky0, pl0 + kx0 + copy));
+  constexpr uint32_t ROWB = SM_STRIDE * 2;
+  const int xa0 = x0 + pl0;
+  bool live[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) live[mt][h] = xa0 + mt * 16 + h * 8 < g.W;
+  const long long p0 = g.pos(n, y0, xa0) * 8 + 2 * t;
+  const int rows = min(STEM_ROWS, g.H - y0);
+  long long po = p0;
+  for (int r = 0; r < rows; ++r, ta += ROWB, po += (long long)g.Wp * 8) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint32_t base = ta + mt * 32;
+      uint32_t a[4];
+      a[0] = lds32(base);
+      a[1] = lds32(base + 16);
+      a[2] = lds32(base + 2 * ROWB);
+      a[3] = lds32(base + 2 * ROWB + 16);
+      float d[4];
+      mma_16816(d, a, bw, bias);
+      if (out_pre) {
+        if (live[mt][0]) *reinterpret_cast<uint32_t*>(out_pre + po + mt * 128) = pack2_fin<false>(d[0], d[1]);
+        if (live[mt][1]) *reinterpret_cast<uint32_t*>(out_pre + po + mt * 128 + 64) = pack2_fin<false>(d[2], d[3]);
+      }
+      if (out) {
+        if (live[mt][0]) *reinterpret_cast<uint32_t*>(out + po + mt * 128) = act == 1 ? pack2_fin<true>(d[0], d[1]) : pack2_fin<false>(d[0], d[1]);
+        if (live[mt][1]) *reinterpret_cast<uint32_t*>(out + po + mt * 128 + 64) = act == 1 ? pack2_fin<true>(d[2], d[3]) : pack2_fin<false>(d[2], d[3]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Direct conv, chunk-planar -> chunk-planar (validation twin of conv_tc).  One thread = one pixel x
 // one output chunk.  Weights packed [tap][cin_chunk][cout_chunk][ci 8][co 8] (16-bit).
@@ -877,6 +966,12 @@ cudaError_t launch_conv_stem(cudaStream_t st, int ks, const float* in, PV out, P
   }
     ARU_STEM_POOL(3, 8) ARU_STEM_POOL(3, 12) ARU_STEM_POOL(3, 16) ARU_STEM_POOL(4, 8) ARU_STEM_POOL(4, 12) ARU_STEM_POOL(4, 16)
 #undef ARU_STEM_POOL
+    return cudaGetLastError();
+  }
+  if (ks == 3 && cout <= 8 && (out.p || out_pre.p) && (act == 0 || act == 1) && w_dev16 && bias_dev16 && !stem_force_ffma()) {
+    // 1 -> 8 channels (unet_down_0/conv1): the 9 taps as one tensor-core K step; with a fused residual block behind it
+    // only the pre-activation is stored
+    k_conv_stem3_pre_mma<<<grid, 128, 0, st>>>(in, out.p, out_pre.p, w_dev16, bias_dev16, g, act);
     return cudaGetLastError();
   }
 #define ARU_STEM(KK, CC)                                                                                              \
