@@ -1578,7 +1578,10 @@ int aru_f64_to_f32(const double* src, float* dst, long long count, int threads) 
   cpu_set_t set;
   int avail = 1;
   if (sched_getaffinity(0, sizeof set, &set) == 0) avail = std::max(1, CPU_COUNT(&set));
-  int nt = threads > 0 ? threads : std::min(avail, 16);
+  // one process per GPU: the ranks of a box share its cores (torchrun exports LOCAL_WORLD_SIZE)
+  int ranks = 1;
+  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(lw));
+  int nt = threads > 0 ? threads : std::max(1, std::min(avail / ranks, 16));
   nt = (int)std::max<long long>(1, std::min<long long>(nt, count / 65536));
   // Streaming (non-temporal) stores where the target is 16-byte aligned: the staging buffer is read next by the copy
   // engine, not by the CPU, and lines left dirty in the caches slow that read down.

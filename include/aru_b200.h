@@ -149,7 +149,8 @@ int aru_device_count(void);
 int aru_bind_host_to_device(int device, int* numa_node);
 
 /* get_net_output receives a float64 page (image / 255.0, net_post_processing_helper.py:31,56-59): dst[i] = (float)src[i]
- * for `count` values on up to `threads` host threads (0 = as many as the process may use, at most 16) - the one CPU pass
+ * for `count` values on up to `threads` host threads (0 = the process's share of the cores - its affinity mask divided by
+ * LOCAL_WORLD_SIZE when a launcher exports it - at most 16) - the one CPU pass
  * over the page before it is copied up; dst is normally a page-locked buffer from aru_host_alloc. */
 int aru_f64_to_f32(const double* src, float* dst, long long count, int threads);
 
