@@ -534,6 +534,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
           // eight chunks) was a chain of eight exposed memory latencies (measured 91 us against 52 us without residual).
           constexpr int PD = T == 1 ? 4 : 2;
           uint4 rr[PD][T];
+          // ... and the residual of the pass this warpgroup handles NEXT (two units further) is pulled into L2 now: when
+          // the accumulators are ready on arrival (the epilogue is the slower side of a residual launch) the first use
+          // of rr below waits for its loads, and an L2 hit costs a third of a DRAM access (ncu: 37 % of the samples of
+          // the 16 -> 16 + residual launch sat on that wait, profiles/r02z_ncu_conv_tc_16x16_res.txt)
+          if (has_res && pi + 2 < n_pass && (lane & 7) == 0) {
+#pragma unroll 1
+            for (int d = 0; d < a.cout_chunks; ++d)
+#pragma unroll
+              for (int t = 0; t < T; ++t)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + (long long)d * a.res_plane * 8 + pt[t] + 2LL * UNIT * 8));
+          }
           if (has_res) {
 #pragma unroll
             for (int d = 0; d < PD; ++d)
