@@ -104,6 +104,7 @@ struct Plan {
   std::vector<const char*> kernel;   // per op label
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
+  std::vector<char> buf_dead;   // per buffer: no launch of this plan touches it (an intermediate of a fused launch): not in the arena
   // [0], [1]: the plan's own double-buffered staging; [2 .. 2 + EXT_SLOTS): caller-owned device buffers bound in place
   // by aru_forward_device (no staging copy; one captured graph per binding, least recently used slot recycled)
   static constexpr int EXT_SLOTS = 4;
@@ -707,26 +708,50 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
         return fail(e, ARU_EUNSUP, "op %d: unknown kind %d", i, op.kind);
     }
   }
-  // arena layout (no aliasing between buffers: the zero frame of every tensor must stay intact)
-  size_t off = 0;
+  // arena: every tensor a launch of this plan touches gets a region of its own (no aliasing: the zero frame of a tensor
+  // must stay intact); the intermediates of the fused launches (block_mma.cu, combine_head.cu) are never materialised
+  // and get none - they are known once the fusion decisions below are taken, so the arena is laid out after them
+  // (at once when the plan-time tuner has to run launches)
+  p->buf_dead.assign(nb, 0);
   for (int i = 0; i < nb; ++i) {
     BufPlan& b = p->bufs[i];
+    b.offset = 0;
     if (!b.sized) { b.bytes = 0; continue; }
-    if (b.kind == KIND_PLANAR) {
-      b.geo = make_geo(n, b.h, b.w);
-      b.bytes = (size_t)b.chunks * b.geo.plane * 16;
-    } else {
-      b.geo = make_geo(n, b.h, b.w);
-      b.bytes = (size_t)n * b.h * b.w * b.channels * sizeof(float);
-    }
-    if (i == e->input_buf || i == e->output_buf) { b.offset = 0; continue; }  // separate, double-buffered
-    b.offset = off;
-    off += (b.bytes + 255) / 256 * 256;
+    b.geo = make_geo(n, b.h, b.w);
+    b.bytes = b.kind == KIND_PLANAR ? (size_t)b.chunks * b.geo.plane * 16 : (size_t)n * b.h * b.w * b.channels * sizeof(float);
   }
-  p->arena_bytes = std::max<size_t>(off, 256);
+  auto layout_arena = [&]() -> int {
+    if (p->arena) return ARU_OK;
+    size_t off = 0;
+    for (int i = 0; i < nb; ++i) {
+      BufPlan& b = p->bufs[i];
+      if (!b.sized || p->buf_dead[i] || i == e->input_buf || i == e->output_buf) continue;   // in / out: separate, double-buffered
+      b.offset = off;
+      off += (b.bytes + 255) / 256 * 256;
+    }
+    p->arena_bytes = std::max<size_t>(off, 256);
+    CU(e, cudaMalloc((void**)&p->arena, p->arena_bytes));
+    CU(e, cudaMemsetAsync(p->arena, 0, p->arena_bytes, e->s_comp));
+    return ARU_OK;
+  };
+  // a view's buffer is dead when the view covers it and every op that names it is one of `ops` (the members of a fused launch)
+  auto mark_dead = [&](const aru_view& v, std::initializer_list<int> ops) {
+    if (v.buf < 0 || v.buf == e->input_buf || v.buf == e->output_buf) return;
+    if (v.ch_off != 0 || v.ch != e->buffers[v.buf].channels) return;
+    for (int j = 0; j < no; ++j) {
+      const aru_op& o = e->ops[j];
+      bool names = o.in.buf == v.buf || o.res.buf == v.buf || o.out.buf == v.buf || o.out_pre.buf == v.buf;
+      if (o.kind == ARU_OP_COMBINE)
+        for (int k = 0; k < o.n_scales; ++k) names = names || o.att[k].buf == v.buf || o.det[k].buf == v.buf;
+      if (names && std::find(ops.begin(), ops.end(), j) == ops.end()) return;
+    }
+    p->buf_dead[v.buf] = 1;
+  };
   const double t_shapes = ms_since(t_begin);
-  CU(e, cudaMalloc((void**)&p->arena, p->arena_bytes));
-  CU(e, cudaMemsetAsync(p->arena, 0, p->arena_bytes, e->s_comp));
+  {
+    const char* tune_env = getenv("ARU_AUTOTUNE");
+    if (tune_env && tune_env[0] == '1' && (rc = layout_arena())) { free_plan(p.get()); return rc; }
+  }
   const size_t in_bytes = (size_t)n * h * w * sizeof(float);
   const size_t out_bytes = (size_t)n * h * w * e->n_class * sizeof(float);
   for (int i = 0; i < 2; ++i) {
@@ -948,6 +973,12 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       p->skip[ia] = p->skip[ib] = 1;
       if (cin > 0) p->skip[i] = 1;
       else if (p->bufs[o1.in.buf].kind == KIND_F32) p->pre_only[i] = 1;
+      if (!p->arena) {   // the intermediates of the launch stay in shared memory
+        mark_dead(oa.out, {i, ia, ib, ic});
+        mark_dead(ob.out, {i, ia, ib, ic});
+        if (cin > 0 || p->pre_only[i]) mark_dead(o1.out, {i, ia, ib, ic});
+        if (cin > 0) mark_dead(o1.out_pre, {i, ia, ib, ic});
+      }
     }
   }
   // The attention combine runs inside the launch of the classifier that is its only reader (combine_head.cu).
@@ -979,6 +1010,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
       }
       p->head_combine[h] = c;
       p->skip[c] = 1;
+      if (!p->arena) mark_dead(oc.out, {c, h});
     }
   }
   // Pairs of chained 3x3 convolutions with C_out = 8 / 16 run as one launch (conv_band2.cu): greedy in program order,
@@ -1064,6 +1096,7 @@ int build_plan(aru_engine* e, int n, int h, int w, Plan** out) {
     }
   }
   const double t_kernels = ms_since(t_begin);
+  if ((rc = layout_arena())) { free_plan(p.get()); return rc; }
   if ((rc = plan_branches(e, p.get()))) { free_plan(p.get()); return rc; }
   // one eager pass (sets function attributes, validates every launch), then capture
   rc = run_all(e, p.get(), 0, e->s_comp);
@@ -1205,7 +1238,7 @@ int pick_micro_batch(const aru_engine* e, int n, int h, int w) {
   const long long px = (long long)h * w;
   // ~80 Mpx per pass: every launch carries ~10 us of fixed cost (prologue, pipeline fill, tail) and the deep levels of
   // the pyramid are small, so a pass of 32 pages of 2.5 Mpx is 7 % faster per page than one of 16 (measured); the arena
-  // of such a pass is ~34 GB of the 180 GB
+  // of such a pass is ~30 GB of the 180 GB
   long long mb = (80LL << 20) / std::max<long long>(px, 1);
   mb = std::max<long long>(1, std::min<long long>(mb, 32));
   return (int)std::min<long long>(mb, n);
@@ -1326,7 +1359,7 @@ int range_check(aru_engine* e, Plan* p) {
   CU(e, cudaMemsetAsync(cnt, 0, (size_t)nb * sizeof(unsigned long long), e->s_comp));
   for (int b = 0; b < nb; ++b) {
     const BufPlan& bp = p->bufs[b];
-    if (!bp.sized || bp.kind != KIND_PLANAR || b == e->input_buf || b == e->output_buf) continue;
+    if (!bp.sized || p->buf_dead[b] || bp.kind != KIND_PLANAR || b == e->input_buf || b == e->output_buf) continue;
     cudaError_t err = launch_range_scan(e->s_comp, reinterpret_cast<const act_t*>(p->arena + bp.offset),
                                         (long long)bp.chunks * bp.geo.plane * 8, cnt + b);
     if (err != cudaSuccess) { cudaFree(cnt); return fail(e, ARU_ECUDA, "range scan: %s", cudaGetErrorString(err)); }
@@ -2366,6 +2399,7 @@ int aru_read_buffer(aru_engine* e, int buf, int n_index, float* out_nhwc, size_t
   Plan* p = e->cur;
   const BufPlan& b = p->bufs[buf];
   if (!b.sized || n_index < 0 || n_index >= p->n) return fail(e, ARU_EINVAL, "aru_read_buffer: bad buffer / page index");
+  if (p->buf_dead[buf]) return fail(e, ARU_EINVAL, "aru_read_buffer: buffer %d is an intermediate of a fused launch (set ARU_OPT_KEEP_ALL)", buf);
   const size_t cnt = (size_t)b.h * b.w * b.channels;
   if (out_floats < cnt) return fail(e, ARU_EINVAL, "aru_read_buffer: output too small (%zu < %zu)", out_floats, cnt);
   CU(e, cudaSetDevice(e->device));
